@@ -1,0 +1,129 @@
+/*
+ * b200_tetris_mcts.h — C-ABI of the B200-native batched Tetris-MCTS engine (libb200_tetris_mcts.so).
+ *
+ * This is the drop-in boundary for the reference's per-move simulation loop.  Every entry point names the
+ * reference interface it replaces (file:line in hrpan/tetris_mcts @ 7f24f8d).  Conventions:
+ *   - extern "C", plain pointers and sizes, no C++/torch types; the caller owns every buffer it passes;
+ *   - pointers are HOST pointers unless the name says `_dev`;
+ *   - every function returns 0 on success or a B200_ERR_* code; b200_last_error() gives the text;
+ *   - one host thread per engine; all work of an engine is issued on its own CUDA stream;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns B200_ERR_CUDA.
+ * Games travel as the 80-byte packed record of SPEC_PYTETRIS.md §6 (20 uint32 words).
+ */
+#ifndef B200_TETRIS_MCTS_H
+#define B200_TETRIS_MCTS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_BAD_ARG 1
+#define B200_ERR_CUDA 2
+#define B200_ERR_ARENA_FULL 3   /* reference: "MAX_NODES EXCEEDED" then UB, agents/cppmodule/agent.cpp:227-231 */
+#define B200_ERR_TRACE_FULL 4
+#define B200_ERR_NO_WEIGHTS 5
+
+#define B200_REC_WORDS 20
+#define B200_KEY_WORDS 12
+#define B200_N_ACTIONS 7        /* agents/cppmodule/core.h:17 */
+#define B200_N_WEIGHTS 478342   /* model/model_vv.py:13-46 Net: state_dict order, PyTorch layouts, + out_ubound, out_lbound */
+
+enum { B200_MODE_LP = 0,        /* agents/ValueSimLP.py:13-70 */
+       B200_MODE_SINGLE = 1,    /* agents/ValueSim.py:52-94 */
+       B200_MODE_VANILLA = 2 }; /* agents/Vanilla.py:17-64 */
+enum { B200_EVAL_SYNTHETIC = 0, /* test evaluator (hash of the observation), shared with the CPU oracle */
+       B200_EVAL_NET = 1,       /* model/model_vv.py Model_VV.inference, fp32 CUDA cores */
+       B200_EVAL_NET_TC = 2 };  /* same network on tcgen05 tensor cores (3xTF32 split) */
+
+typedef struct b200_engine b200_engine;
+
+typedef struct {
+    int32_t n_games;            /* concurrent, independent game trees */
+    int32_t max_nodes;          /* per-game arena, agents/agent.py:36 / agents/ValueSim.py:16 */
+    int32_t mode;               /* B200_MODE_* */
+    int32_t low;                /* check_low threshold: 1 (ValueSimLP.py:27), 5 (Vanilla.py:27) */
+    int32_t lp_end_from_obs;    /* 0: ValueSimLP.py:25 behaviour; 1: agent.cpp:538 */
+    int32_t lp_var_gamma2;      /* 1: core.h:365; 0: agent.cpp:558 */
+    int32_t stale_pop;          /* 1: reproduce agents/agent.py:229-232 literally */
+    int32_t eval_kind;          /* B200_EVAL_* */
+    int32_t trace_max;          /* longest root-to-leaf path stored (0 -> 128) */
+    int32_t actions_per_drop, scoring, randomizer;   /* play.py:75 env_args */
+    int32_t device;             /* CUDA device ordinal */
+    uint32_t seed;              /* search RNG stream base (replaces libc rand(), core.h:62,76, and random.randint, Vanilla.py:52) */
+    double gamma;               /* ValueSim.py:14 0.999 / Vanilla.py:9 0.99 */
+    double rollout_variance;    /* Vanilla.py:54 1e3 / VanillaC.py:8 1e5 */
+} b200_config;
+
+const char *b200_last_error(void);
+int b200_device_count(void);
+
+/* --- engine lifetime: replaces TreeAgent.__init__/init_array (agents/agent.py:36-88), Agent.close (:303-307) */
+int b200_engine_create(const b200_config *cfg, b200_engine **out);
+int b200_engine_destroy(b200_engine *e);
+
+/* --- Model.load (model/model.py:163-174): weights = the state_dict tensors concatenated (B200_N_WEIGHTS floats) */
+int b200_load_weights(b200_engine *e, const float *weights);
+
+/* --- TreeAgent.update_root (agents/agent.py:296-301) for all games: recs[n_games][20] */
+int b200_set_games(b200_engine *e, const uint32_t *recs);
+int b200_get_games(b200_engine *e, uint32_t *recs);
+int b200_update_root(b200_engine *e, int auto_reset);
+
+/* --- TreeAgent.mcts (agents/ValueSimLP.py:13, ValueSim.py:52, Vanilla.py:17): `sims` simulations on every game */
+int b200_run_sims(b200_engine *e, int sims);
+
+/* --- TreeAgent.compute_stats / get_action (agents/agent.py:153-185): stats[n][3][7], action[n] */
+int b200_get_stats(b200_engine *e, float *stats, int32_t *action);
+
+/* --- Tetris.play on the engine's live games (play.py:150): actions[n]; NULL = the argmax actions of the last stats */
+int b200_env_step(b200_engine *e, const int32_t *actions);
+
+/* --- one whole move of play.py:118-177 for every game: mcts -> get_action -> play -> update_root (-> reset) */
+int b200_play_move(b200_engine *e, int sims, int auto_reset, int32_t *actions_out, float *stats_out);
+
+int b200_status(b200_engine *e, int32_t *status);            /* per-game 0 ok / B200_ERR_ARENA_FULL / B200_ERR_TRACE_FULL */
+int b200_counters(b200_engine *e, uint64_t *out16);          /* 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels
+                                                                5 rollout steps 6 new nodes 8 games finished 9 score sum 10 lines sum */
+int b200_sync(b200_engine *e);
+int b200_set_timing(b200_engine *e, int on);                 /* CUDA-event timing of each phase on the engine's stream */
+int b200_phase_ms(b200_engine *e, float *ms8, uint64_t *launches8);   /* 0 select+expand 1 conv 2 fc 3 backup 4 rollout 5 synth 6 stats/step/root */
+
+/* --- the arena of one game in the reference's array layout (agents/agent.py:58-88); any pointer may be NULL */
+int b200_export_game(b200_engine *e, int game, int32_t *child, float *score, int32_t *episode, int32_t *n2o,
+                     int32_t *visit, float *value, float *variance, uint8_t *obs_end, uint32_t *game_recs,
+                     uint32_t *obs_keys, int32_t *root, int32_t *last_trace, int32_t *last_trace_len);
+
+/* --- Model_VV.inference (model/model_vv.py:210-217): states[k][200] int8 -> v[k], var[k] */
+int b200_valuenet_forward(b200_engine *e, const int8_t *states, int k, float *v, float *var);
+
+/* --- pyTetris.Tetris ctor / reset / play / getState for host-resident games (play.py:75-76,150,169,
+ *     agents/agent.py:116).  b200_tetris_new: reset == 0 builds n fresh games (seeds[n] or NULL = default seed),
+ *     reset != 0 applies Tetris.reset() to the n records in place (keeps each RNG stream, SPEC §4). */
+int b200_tetris_new(uint32_t *recs, int n, int actions_per_drop, int scoring, int randomizer, const uint32_t *seeds, int reset);
+int b200_tetris_step(uint32_t *recs, const int32_t *actions, int n);
+int b200_tetris_state(const uint32_t *recs, int8_t *out, int n);
+
+/* --- single-call twins of agents/cppmodule/core.cpp:20-26 on the reference's own arrays (mutated in place) */
+int b200_select_trace_obs(int index, const int32_t *child, const int32_t *visit, const float *value,
+                          const float *variance, const float *score, const int32_t *n_to_o, int M, int low,
+                          uint32_t *rng_state, int32_t *trace_out, int max_trace, int32_t *trace_len);
+int b200_backup_trace_obs(const int32_t *trace, int D, int32_t *visit, float *value, float *variance,
+                          const int32_t *n_to_o, const float *score, int M, double v, double var, double gamma);
+int b200_backup_trace_obs_LP(const int32_t *trace, int D, int32_t *visit, float *value, float *variance,
+                             const int32_t *n_to_o, const float *score, const uint8_t *end, int M,
+                             const int32_t *c_nodes, const int32_t *c_obs, int k, const float *v, const float *var,
+                             double gamma, int mixture, int averaged);
+int b200_get_unique_child_obs(int index, const int32_t *child, const float *score, const int32_t *n_to_o, int M,
+                              int32_t *c_nodes, int32_t *c_obs, int32_t *k_out);
+int b200_get_all_childs(int index, const int32_t *child, int M, uint8_t *mark);
+
+/* --- replay samples of the live search (ValueSim.store_nodes, agents/ValueSim.py:122-159): observations with
+ *     visit >= min_visits and not end, packed as {int8 state[200], f32 value, f32 variance, f32 visit} = 212 B.
+ *     out_dev is a DEVICE buffer of capacity*212 bytes (e.g. a torch tensor handed to the NCCL all-gather). */
+int b200_collect_samples_dev(b200_engine *e, int min_visits, void *out_dev, int capacity, int32_t *count_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -53,6 +53,14 @@ int mo_policy_clt(const int32_t *nodes, const int32_t *visit, const float *value
 
 static uint32_t libc_rand(void *ctx) { (void)ctx; return (uint32_t)rand(); }
 
+/* xorshift32 on a caller-owned state: the injectable stand-in for rand() that the device twins also use */
+uint32_t mo_xorshift32(void *ctx) {
+    uint32_t *st = (uint32_t *)ctx, s = *st;
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    *st = s;
+    return s;
+}
+
 /* ------------------------------------------------------------------ core.h:167-224 (check_low core.h:65-77) */
 int mo_select_trace_obs(int index, const int32_t *child, const int32_t *visit, const float *value,
                         const float *variance, const float *score, const int32_t *n2o, int low,

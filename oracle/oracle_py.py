@@ -163,10 +163,16 @@ def obskey_to_state(key):
 
 
 # ----------------------------------------------------------------------------- core twins
-def select_trace_obs(index, child, visit, value, variance, score, n2o, low, max_trace=512):
+def select_trace_obs(index, child, visit, value, variance, score, n2o, low, max_trace=512, rng_state=None):
+    """rng_state: uint32[1] array -> check_low draws come from xorshift32 on it (as in the device twin);
+    None -> libc rand() like the reference (core.h:76)."""
     tr = np.zeros(max_trace, np.int32)
+    fn = ctx = None
+    if rng_state is not None:
+        fn = C.cast(lib().mo_xorshift32, C.c_void_p)
+        ctx = _p(rng_state)
     D = lib().mo_select_trace_obs(int(index), _p(child), _p(visit), _p(value), _p(variance), _p(score), _p(n2o),
-                                  int(low), _p(tr), max_trace, None, None)
+                                  int(low), _p(tr), max_trace, fn, ctx)
     assert D > 0
     return tr[:D].copy()
 

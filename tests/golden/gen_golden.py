@@ -1,0 +1,139 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF in the build container (it cannot travel to the GPU box):
+  core_golden.npz     outputs of the reference's own agents/cppmodule/core.cpp (compiled unchanged -> oracle/_ref/core*.so)
+  valuenet_golden.npz outputs of the reference's own model/model_vv.py Model_VV (torch CPU) with seeded weights
+  agent_golden.npz    per-move statistics of the reference's own agents/ValueSimLP.py + agents/agent.py driving
+                      the oracle env (the only non-reference part: pyTetris is absent upstream) with the synthetic
+                      evaluator patched onto the agent instance (no reference file is modified)
+Run:  python tests/golden/gen_golden.py      (needs /root/reference and `make -C oracle`)"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import oracle_py as O  # noqa: E402
+from arena_gen import make_arena, boards, state_to_obskey  # noqa: E402
+
+
+def gen_core(core):
+    out = {}
+    cases = [dict(seed=s, M=1024, max_depth=4 + s % 6) for s in range(8)]
+    cases += [dict(seed=20 + s, M=1024, max_depth=6, unvisited=0.3, single_low=True) for s in range(4)]
+    rng = np.random.default_rng(0)
+    for i, kw in enumerate(cases):
+        a = make_arena(**kw)
+        p = "c%d_" % i
+        low = 1 if "unvisited" in kw else int(rng.choice([0, 1]))
+        for k in ("child", "visit", "value", "variance", "score", "n2o"):
+            out[p + k] = a[k]
+        out[p + "low"] = low
+        tr = core.select_trace_obs(1, a["child"], a["visit"], a["value"], a["variance"], a["score"], a["n2o"], low)
+        out[p + "trace"] = np.asarray(tr, np.int32)
+        un = int(tr[len(tr) // 2])
+        c, o = core.get_unique_child_obs(un, a["child"], a["score"], a["n2o"])
+        out[p + "uniq_node"], out[p + "uniq_c"], out[p + "uniq_o"] = un, np.asarray(c, np.int32), np.asarray(o, np.int32)
+        v, var, gamma = float(rng.uniform(0, 400)), float(rng.uniform(0, 200)), float(rng.choice([0.999, 0.99]))
+        out[p + "bk_v"], out[p + "bk_var"], out[p + "gamma"] = v, var, gamma
+        b = {k: a[k].copy() for k in ("visit", "value", "variance")}
+        core.backup_trace_obs(np.asarray(tr, np.int32), b["visit"], b["value"], b["variance"], a["n2o"], a["score"], v, var, gamma)
+        for k in b:
+            out[p + "bk_" + k] = b[k]
+        lp_tr = np.asarray(tr[:-1] if len(tr) > 1 else tr, np.int32)
+        c, o = core.get_unique_child_obs(int(lp_tr[-1]), a["child"], a["score"], a["n2o"])
+        end = (rng.random(len(a["visit"])) < 0.1)
+        lv = rng.uniform(0, 100, len(c)).astype(np.float32)
+        lvar = rng.uniform(0.1, 1000, len(c)).astype(np.float32)
+        out[p + "lp_trace"], out[p + "lp_c"], out[p + "lp_o"] = lp_tr, np.asarray(c, np.int32), np.asarray(o, np.int32)
+        out[p + "lp_end"], out[p + "lp_v"], out[p + "lp_var"] = end.astype(np.uint8), lv, lvar
+        for m in (0, 1):
+            for av in (0, 1):
+                b = {k: a[k].copy() for k in ("visit", "value", "variance")}
+                core.backup_trace_obs_LP(lp_tr, b["visit"], b["value"], b["variance"], a["n2o"], a["score"], end, list(c), list(o), lv, lvar,
+                                         gamma, bool(m), bool(av))
+                for k in b:
+                    out[p + "lp%d%d_" % (m, av) + k] = b[k]
+        out[p + "reach"] = np.asarray(sorted(core.get_all_childs(1, a["child"])), np.int32)
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, "core_golden.npz"), **out)
+    print("core_golden: %d cases" % len(cases))
+
+
+def gen_valuenet():
+    import torch
+    from model.model_vv import Model_VV
+    torch.set_num_threads(1)
+    states = np.concatenate([boards(48, 1), np.zeros((1, 20, 10), np.int8), -np.ones((1, 20, 10), np.int8) * 0 + 1])
+    # real game positions too
+    g = O.Game(seed=5)
+    rng = np.random.default_rng(2)
+    real = []
+    while not g.end and len(real) < 14:
+        g.play(int(rng.integers(0, 7)))
+        real.append(g.state())
+    states = np.concatenate([states, np.stack(real)]).astype(np.int8)
+    out = dict(states=states, seeds=np.array([0, 1]))
+    for seed in (0, 1):
+        m = Model_VV(use_cuda=False)
+        sd = {k: torch.from_numpy(v.copy()) for k, v in O.weights_to_state_dict(O.seeded_weights(seed)).items()}
+        m.model.load_state_dict(sd)
+        m.training(False)
+        v, var = m.inference(states[:, None, :, :])
+        out["v_%d" % seed], out["var_%d" % seed] = v.ravel().astype(np.float32), var.ravel().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "valuenet_golden.npz"), **out)
+    print("valuenet_golden: %d boards x 2 weight seeds" % len(states))
+
+
+def synthetic_inference(batch):
+    b = np.asarray(batch).reshape(-1, 20, 10)
+    v = np.zeros((len(b), 1), np.float32)
+    var = np.zeros((len(b), 1), np.float32)
+    for i, s in enumerate(b):
+        v[i, 0], var[i, 0] = O.synthetic_eval(state_to_obskey(s))
+    return [v, var]
+
+
+def gen_agent(pt):
+    from agents.ValueSimLP import ValueSimLP
+    out = {}
+    cases = [dict(M=20000, sims=50, moves=20, seed=123), dict(M=2500, sims=40, moves=45, seed=321)]
+    for i, cs in enumerate(cases):
+        p = "a%d_" % i
+        game = pt.Tetris((20, 10), 1, 0, 0)
+        game.seed(cs["seed"])
+        ag = ValueSimLP(sims=cs["sims"], env=pt.Tetris, env_args=((20, 10), 1, 0, 0), benchmark=False, online=False, min_visit=40)
+        ag.max_nodes = cs["M"]          # public attribute + public method: the arena size is the only thing changed
+        ag.init_array()
+        ag.model.inference = synthetic_inference
+        out[p + "start"] = np.array(game.get_record(), np.uint32)
+        ag.update_root(game)
+        acts, stats = [], []
+        for mv in range(cs["moves"]):
+            a = ag.play()
+            acts.append(int(a))
+            stats.append(ag.get_stats())
+            game.play(a)
+            ag.update_root(game)
+            if game.end:
+                game.reset()
+                ag.update_root(game)
+        out[p + "M"], out[p + "sims"] = cs["M"], cs["sims"]
+        out[p + "actions"], out[p + "stats"] = np.array(acts, np.int32), np.stack(stats).astype(np.float32)
+        for k in ("child", "score", "episode"):
+            out[p + k] = ag.arrays[k]
+        out[p + "n2o"] = ag.node_to_obs
+        for k in ("visit", "value", "variance"):
+            out[p + k] = ag.obs_arrays[k]
+        out[p + "root"] = ag.root
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, "agent_golden.npz"), **out)
+    print("agent_golden: %d cases" % len(cases))
+
+
+if __name__ == "__main__":
+    O.build(ref=True)
+    pt, core = O.mount_reference()
+    gen_core(core)
+    gen_valuenet()
+    gen_agent(pt)

@@ -1,0 +1,180 @@
+"""The whole per-move simulation loop on the GPU (k_select_expand -> evaluator -> k_backup, tree reuse, garbage
+collection, root statistics) against the C oracle agent, which is itself pinned to the reference's UNMODIFIED
+agents/agent.py + ValueSimLP.py + compiled core.cpp (tests/golden/gen_golden.py, tests/test_oracle_pins.py).
+Everything is compared exactly: action, stats[3,7], and the full arena in the reference's array layout."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ARGS = (1, 0, 0)
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "agent_golden.npz")
+
+
+def search_seed(seed, g):
+    s = (seed + 0x9E3779B9 * (g + 1)) & 0xffffffff
+    return s or 0x2545F491
+
+
+def run_pair(oracle, mode, n, M, sims, moves, seed=123, eval_kind="synthetic", weights=None, engine_kw=None, agent_kw=None,
+             eval_cb=None, check_arena=True):
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    mode_id = {"lp": 0, "single": 1, "vanilla": 2}[mode]
+    recs = PT.new_games(n, ARGS, np.arange(seed, seed + n, dtype=np.uint32))
+    eng = BatchedEngine(n, max_nodes=M, mode=mode, eval_kind=eval_kind, weights=weights, seed=seed, **(engine_kw or {}))
+    eng.set_games(recs)
+    kw = dict(max_nodes=M, mode=mode_id, gamma=0.99 if mode == "vanilla" else 0.999, low=5 if mode == "vanilla" else 1,
+              eval_mode=0 if eval_cb is None else 2, eval_cb=eval_cb)
+    kw.update(agent_kw or {})
+    agents = [oracle.Agent(search_seed=search_seed(seed, g), **kw) for g in range(n)]
+    games = [oracle.Game(record=recs[g]) for g in range(n)]
+    for g in range(n):
+        agents[g].update_root(games[g].record())
+    gcs = 0
+    for mv in range(moves):
+        eng.run_sims(sims)
+        stats, action = eng.get_stats()
+        for g in range(n):
+            agents[g].mcts(sims)
+            a, st = agents[g].get_action()
+            assert np.array_equal(st, stats[g]), "move %d game %d\n%s\n%s" % (mv, g, st, stats[g])
+            assert a == action[g]
+            games[g].play(a)
+            agents[g].update_root(games[g].record())
+            if games[g].end:
+                games[g].reset()
+                agents[g].update_root(games[g].record())
+        eng.env_step(None)
+        eng.update_root(auto_reset=True)
+        assert np.array_equal(eng.get_games(), np.stack([gm.record() for gm in games])), "live games differ after move %d" % mv
+    c = eng.counters()
+    if check_arena:
+        for g in range(min(n, 8)):
+            ex = eng.export_game(g)
+            want = agents[g].export()
+            assert ex["root"] == agents[g].root
+            for k in ("child", "n2o", "episode", "score", "visit", "value", "variance", "obs_end", "obs_key", "game"):
+                assert np.array_equal(ex[k], want[k]), (g, k)
+    assert c["sims"] == n * sims * moves
+    assert c["gcs"] == sum(a.counter(3) for a in agents)
+    assert c["expansions"] == sum(a.counter(1) for a in agents)
+    eng.close()
+    return c
+
+
+def test_lp_synthetic_exact(gpu_lib, oracle):
+    c = run_pair(oracle, "lp", n=24, M=4096, sims=60, moves=12)
+    assert c["gcs"] == 0
+
+
+def test_lp_with_garbage_collection(gpu_lib, oracle):
+    """Small arenas force remove_nodes (agents/agent.py:206-257) in the middle of expansions, several times per game."""
+    c = run_pair(oracle, "lp", n=12, M=2500, sims=40, moves=45)
+    assert c["gcs"] >= 12
+
+
+def test_lp_long_games_until_game_over(gpu_lib, oracle):
+    c = run_pair(oracle, "lp", n=8, M=1500, sims=12, moves=140)
+    assert c["games_finished"] >= 1
+
+
+def test_lp_agent_cpp_variants(gpu_lib, oracle):
+    """end taken from the observation (agent.cpp:538) and variance averaged without gamma^2 (agent.cpp:558)."""
+    run_pair(oracle, "lp", n=8, M=2048, sims=40, moves=8, engine_kw=dict(lp_end_from_obs=True, lp_var_gamma2=False),
+             agent_kw=dict(lp_end_from_obs=1, lp_var_gamma2=0))
+
+
+def test_single_eval_mode_exact(gpu_lib, oracle):
+    """ValueSim.py:52-94 (leaf itself evaluated; check_low draws from the injected RNG stream)."""
+    run_pair(oracle, "single", n=16, M=2048, sims=60, moves=10)
+
+
+def test_vanilla_rollouts_exact(gpu_lib, oracle):
+    """Vanilla.py:17-64: low=5, gamma=0.99, random playouts from the shared xorshift stream, variance 1e3."""
+    c = run_pair(oracle, "vanilla", n=16, M=4096, sims=80, moves=6)
+    assert c["rollout_steps"] > 0
+
+
+def test_no_stale_pop_variant(gpu_lib, oracle):
+    run_pair(oracle, "lp", n=8, M=2500, sims=40, moves=40, engine_kw=dict(stale_pop=False), agent_kw=dict(stale_pop=0))
+
+
+def test_real_network_search_is_exact_given_the_same_evaluator(gpu_lib, oracle):
+    """With the value network as evaluator the search must still be trace-for-trace identical when the oracle agent is
+    fed the SAME network outputs (the LP path is deterministic given evaluator and piece sequence)."""
+    from tetris_mcts_b200.engine import BatchedEngine
+    w = oracle.seeded_weights(0)
+    side = BatchedEngine(1, max_nodes=64, eval_kind="net", weights=w)
+
+    def cb(states):
+        v, var = side.valuenet(states)
+        return v, var
+
+    run_pair(oracle, "lp", n=3, M=2048, sims=25, moves=4, eval_kind="net", weights=w, eval_cb=cb)
+    side.close()
+
+
+def test_arena_overflow_is_reported_not_ub(gpu_lib):
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    from tetris_mcts_b200._lib import B200Error
+    eng = BatchedEngine(4, max_nodes=40, mode="lp", eval_kind="synthetic")
+    eng.set_games(PT.new_games(4, ARGS, np.arange(1, 5, dtype=np.uint32)))
+    with pytest.raises(B200Error) as ei:
+        for _ in range(50):
+            eng.run_sims(20)
+            eng.get_stats()
+            eng.env_step(None)
+            eng.update_root(True)
+    assert ei.value.code == 3
+    eng.close()
+
+
+@pytest.mark.skipif(not os.path.exists(GOLD), reason="golden vectors not generated")
+def test_against_reference_python_agent_golden(gpu_lib):
+    """Per-move stats/actions recorded from the reference's own ValueSimLP (agents/ValueSimLP.py, agents/agent.py,
+    compiled core.cpp) playing on the oracle env with the synthetic evaluator (tests/golden/gen_golden.py)."""
+    from tetris_mcts_b200.engine import BatchedEngine
+    z = np.load(GOLD)
+    for case in range(int(z["n_cases"])):
+        p = "a%d_" % case
+        M, sims = int(z[p + "M"]), int(z[p + "sims"])
+        eng = BatchedEngine(1, max_nodes=M, mode="lp", eval_kind="synthetic")
+        eng.set_games(z[p + "start"].reshape(1, 20))
+        for mv in range(len(z[p + "actions"])):
+            eng.run_sims(sims)
+            stats, action = eng.get_stats()
+            assert np.array_equal(stats[0], z[p + "stats"][mv]), (case, mv)
+            assert action[0] == z[p + "actions"][mv]
+            eng.env_step(None)
+            eng.update_root(True)
+        ex = eng.export_game(0)
+        for k in ("child", "score", "n2o", "visit", "value", "variance", "episode"):
+            assert np.array_equal(ex[k], z[p + k]), (case, k)
+        eng.close()
+
+
+def test_full_size_properties(gpu_lib):
+    """BASELINE config sizes are too large for the oracle; check size-independent invariants instead:
+    every simulation adds exactly one visit to the root observation, child visits never exceed the root's,
+    statuses stay clean, and two identical engines produce identical results (determinism)."""
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    n, sims = 16384, 40
+    recs = PT.new_games(n, ARGS, np.arange(123, 123 + n, dtype=np.uint32))
+    outs = []
+    for rep in range(2):
+        eng = BatchedEngine(n, max_nodes=1024, mode="lp", eval_kind="synthetic")
+        eng.set_games(recs)
+        eng.run_sims(sims)
+        stats, action = eng.get_stats()
+        ex = eng.export_game(n - 1)
+        root_obs = ex["n2o"][ex["root"]]
+        assert ex["visit"][root_obs] == sims
+        assert (eng.status() == 0).all()
+        assert stats[:, 0].sum(axis=1).max() <= sims * 7
+        outs.append((stats.copy(), action.copy()))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])

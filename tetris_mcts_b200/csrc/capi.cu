@@ -1,0 +1,729 @@
+// capi.cu — host side of libb200_tetris_mcts.so: the C-ABI declared in include/b200_tetris_mcts.h.
+// One engine = one CUDA stream + the per-game arenas in HBM.  No CPU compute path exists in this file: every
+// entry point either launches kernels or moves bytes.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_tetris_mcts.h"
+#include "kernels.cuh"
+#include "valuenet_simt.cuh"
+#ifdef B200_WITH_TC
+#include "valuenet_tc.cuh"
+#endif
+
+using namespace b200;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));           \
+    } while (0)
+
+extern "C" const char *b200_last_error(void) { return g_err.c_str(); }
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+enum { PH_SELECT = 0, PH_CONV, PH_FC, PH_BACKUP, PH_ROLLOUT, PH_SYNTH, PH_MISC, PH_N = 8 };
+
+struct b200_engine {
+    b200_config cfg;
+    Arena A;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    uint32_t *d_default_rec = nullptr;
+    float *d_stats = nullptr; int32_t *d_action = nullptr;
+    unsigned long long *d_game_stats = nullptr;
+    // network
+    bool have_weights = false;
+    float *d_wraw = nullptr;
+    NetWeights W{};
+    float *d_act3 = nullptr; size_t act3_rows = 0;
+    void *tc_state = nullptr;
+    int n_sm = 148;
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev; size_t ev_used = 0;
+    std::vector<int> ev_phase;
+    float phase_ms[PH_N] = {0}; uint64_t phase_launches[PH_N] = {0};
+    // sampling
+    uint8_t *d_samples = nullptr; int sample_cap = 0; int32_t *d_sample_count = nullptr;
+};
+
+template <typename T>
+static int dalloc(b200_engine *e, T **p, size_t n, bool zero = true) {
+    void *q = nullptr;
+    cudaError_t err = cudaMalloc(&q, n * sizeof(T));
+    if (err != cudaSuccess) return fail(B200_ERR_CUDA, std::string("cudaMalloc ") + std::to_string(n * sizeof(T)) + " B: " + cudaGetErrorString(err));
+    if (zero) cudaMemsetAsync(q, 0, n * sizeof(T), e->stream);
+    e->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+
+// SPEC §2-4 fresh games, produced ON THE DEVICE so that no host restatement of the env exists in this library.
+// seeds == nullptr: every game gets the default seed (SPEC §4); reset != 0: SPEC §4 reset() of the records in place.
+__global__ void k_new_games(uint32_t *recs, int n, int app, int scoring, int randomizer, const uint32_t *seeds, int reset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Game g;
+    uint32_t w[REC_WORDS];
+    if (reset) {
+        load_rec(recs + (size_t)i * REC_WORDS, w);
+        unpack(g, w);
+        reset_game(g);
+    } else {
+        for (int q = 0; q < 10; ++q) g.w[q] = 0;
+        g.piece = 0; g.rot = 0; g.px = 3; g.py = 0; g.bag = 0x7fu; g.dropcnt = 0; g.end = 0;
+        g.app = app < 1 ? 1 : (app > 255 ? 255 : app); g.scoring = scoring ? 1 : 0; g.randomizer = randomizer ? 1 : 0;
+        uint32_t seed = seeds ? seeds[i] : 0u;
+        g.combo = 0; g.rng = seed ? seed : 0x9E3779B9u; g.score = 0; g.lines = 0;
+        for (int q = 0; q < 4; ++q) g.ls[q] = 0;
+        spawn(g);
+    }
+    pack(g, w);
+    store_rec(recs + (size_t)i * REC_WORDS, w);
+}
+
+struct PhaseTimer {
+    b200_engine *e; int ph;
+    PhaseTimer(b200_engine *e_, int ph_) : e(e_), ph(ph_) {
+        e->phase_launches[ph] += 1;
+        if (!e->timing) return;
+        if (e->ev_used + 2 > e->ev.size()) {
+            size_t old = e->ev.size();
+            e->ev.resize(old + 4096);
+            for (size_t i = old; i < e->ev.size(); ++i) cudaEventCreate(&e->ev[i]);
+        }
+        cudaEventRecord(e->ev[e->ev_used], e->stream);
+    }
+    ~PhaseTimer() {
+        if (!e->timing) return;
+        cudaEventRecord(e->ev[e->ev_used + 1], e->stream);
+        e->ev_phase.push_back(ph);
+        e->ev_used += 2;
+    }
+};
+
+static void flush_timing(b200_engine *e) {
+    if (!e->timing || e->ev_used == 0) return;
+    cudaStreamSynchronize(e->stream);
+    for (size_t i = 0; i < e->ev_used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
+        e->phase_ms[e->ev_phase[i / 2]] += ms;
+    }
+    e->ev_used = 0; e->ev_phase.clear();
+}
+
+extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
+    if (!cfg || !out) return fail(B200_ERR_BAD_ARG, "null argument");
+    if (cfg->n_games < 1 || cfg->max_nodes < 16 || cfg->max_nodes >= (1 << 28)) return fail(B200_ERR_BAD_ARG, "n_games >= 1, 16 <= max_nodes < 2^28");
+    if (cfg->mode < 0 || cfg->mode > 2) return fail(B200_ERR_BAD_ARG, "mode");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    CK(cudaSetDevice(cfg->device));
+    b200_engine *e = new b200_engine();
+    e->cfg = *cfg;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    e->n_sm = prop.multiProcessorCount;
+    Arena &A = e->A;
+    memset(&A, 0, sizeof(A));
+    A.G = cfg->n_games; A.M = cfg->max_nodes;
+    int H = 16; while (H < 2 * A.M) H <<= 1;
+    A.H = H; A.trace_max = cfg->trace_max > 0 ? cfg->trace_max : 128;
+    A.mode = cfg->mode; A.low = cfg->low; A.lp_end_from_obs = cfg->lp_end_from_obs; A.lp_var_gamma2 = cfg->lp_var_gamma2;
+    A.stale_pop = cfg->stale_pop; A.eval_kind = cfg->eval_kind; A.gamma = cfg->gamma; A.rollout_variance = cfg->rollout_variance;
+    size_t GM = (size_t)A.G * A.M, G = (size_t)A.G;
+    int rc = 0;
+    rc |= dalloc(e, &A.row, GM * ROW_WORDS);
+    rc |= dalloc(e, &A.stat, GM);
+    rc |= dalloc(e, &A.rec, GM * REC_WORDS, false);
+    rc |= dalloc(e, &A.key, GM * KEY_WORDS);
+    rc |= dalloc(e, &A.ntab, G * H);
+    rc |= dalloc(e, &A.otab, G * H);
+    rc |= dalloc(e, &A.nfree, GM); rc |= dalloc(e, &A.ofree, GM);
+    rc |= dalloc(e, &A.n_nfree, G); rc |= dalloc(e, &A.n_ofree, G);
+    rc |= dalloc(e, &A.root, G); rc |= dalloc(e, &A.episode, G); rc |= dalloc(e, &A.status, G); rc |= dalloc(e, &A.srng, G);
+    rc |= dalloc(e, &A.trace, G * A.trace_max); rc |= dalloc(e, &A.trace_len, G); rc |= dalloc(e, &A.leaf_kind, G);
+    rc |= dalloc(e, &A.nmark, GM); rc |= dalloc(e, &A.omark, GM); rc |= dalloc(e, &A.gc_queue, GM * 2);
+    rc |= dalloc(e, &A.cur, G * REC_WORDS);
+    rc |= dalloc(e, &A.req, G * 8); rc |= dalloc(e, &A.n_req, 1);
+    rc |= dalloc(e, &A.eval_out, G * 8); rc |= dalloc(e, &A.rollout_val, G);
+    rc |= dalloc(e, &A.counters, 16);
+    rc |= dalloc(e, &e->d_default_rec, REC_WORDS);
+    rc |= dalloc(e, &e->d_stats, G * 21); rc |= dalloc(e, &e->d_action, G);
+    e->d_game_stats = A.counters + 8;
+    float *zt = nullptr;
+    rc |= dalloc(e, &zt, ZTABLE_N);
+    if (rc) { b200_engine_destroy(e); return B200_ERR_CUDA; }
+    {   // z(n) = norm_quantile(n) narrowed to float: special.h:26-33 + core.h:93, evaluated with the host libm
+        std::vector<float> h(ZTABLE_N);
+        const double l2 = log(2.0), l22 = log(22.0), l41 = log(41.0);
+        for (int n = 0; n < ZTABLE_N; ++n) {
+            double t = (double)n, alpha = 1 - 1 / t;
+            h[n] = (float)(10 * log(1 - log(-log(alpha) / l2) / l22) / l41);
+        }
+        CK(cudaMemcpyAsync(zt, h.data(), ZTABLE_N * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        A.ztable = zt;
+    }
+    k_new_games<<<1, 1, 0, e->stream>>>(e->d_default_rec, 1, cfg->actions_per_drop, cfg->scoring, cfg->randomizer, nullptr, 0);
+    k_init_arena<<<e->n_sm * 8, 256, 0, e->stream>>>(A, e->d_default_rec, cfg->seed);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return B200_OK;
+}
+
+extern "C" int b200_engine_destroy(b200_engine *e) {
+    if (!e) return B200_OK;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+#ifdef B200_WITH_TC
+    tc_destroy(e->tc_state);
+#endif
+    for (void *p : e->allocs) cudaFree(p);
+    for (auto &ev : e->ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- weights
+extern "C" int b200_load_weights(b200_engine *e, const float *w) {
+    if (!e || !w) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    const float *c1w = w, *c1b = c1w + 288, *c2w = c1b + 32, *c2b = c2w + 9216, *c3w = c2b + 32, *c3b = c3w + 9216;
+    const float *f1w = c3b + 32, *f1b = f1w + 458752, *fow = f1b + 256, *fob = fow + 512, *ub = fob + 2, *lb = ub + 2;
+    // pure re-layout (no arithmetic): see NetWeights
+    std::vector<float> h;
+    h.resize(288 + 9216 * 2 + 96 + (size_t)1792 * 256 + 256 + 512 + 6);
+    float *p = h.data();
+    float *w1 = p; p += 288;
+    float *w2 = p; p += 9216;
+    float *w3 = p; p += 9216;
+    float *b123 = p; p += 96;
+    float *wf = p; p += (size_t)1792 * 256;
+    float *bf = p; p += 256;
+    float *wo = p; p += 512;
+    float *tail = p;
+    for (int co = 0; co < 32; ++co)
+        for (int tap = 0; tap < 9; ++tap) w1[tap * 32 + co] = c1w[co * 9 + tap];
+    for (int co = 0; co < 32; ++co)
+        for (int ci = 0; ci < 32; ++ci)
+            for (int tap = 0; tap < 9; ++tap) {
+                w2[(ci * 9 + tap) * 32 + co] = c2w[(co * 32 + ci) * 9 + tap];
+                w3[(ci * 9 + tap) * 32 + co] = c3w[(co * 32 + ci) * 9 + tap];
+            }
+    memcpy(b123, c1b, 128); memcpy(b123 + 32, c2b, 128); memcpy(b123 + 64, c3b, 128);
+    for (int n = 0; n < 256; ++n)
+        for (int c = 0; c < 32; ++c)
+            for (int y = 0; y < 14; ++y)
+                for (int x = 0; x < 4; ++x) wf[(size_t)((y * 32 + c) * 4 + x) * 256 + n] = f1w[(size_t)n * 1792 + c * 56 + y * 4 + x];
+    memcpy(bf, f1b, 1024); memcpy(wo, fow, 2048);
+    tail[0] = fob[0]; tail[1] = fob[1]; tail[2] = ub[0]; tail[3] = ub[1]; tail[4] = lb[0]; tail[5] = lb[1];
+    if (!e->d_wraw) { if (dalloc(e, &e->d_wraw, h.size(), false)) return B200_ERR_CUDA; }
+    CK(cudaMemcpyAsync(e->d_wraw, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    float *d = e->d_wraw;
+    e->W.w1 = d; e->W.w2 = d + 288; e->W.w3 = d + 288 + 9216; e->W.b1 = d + 288 + 18432; e->W.b2 = e->W.b1 + 32; e->W.b3 = e->W.b1 + 64;
+    e->W.wfc1 = e->W.b1 + 96; e->W.bfc1 = e->W.wfc1 + (size_t)1792 * 256; e->W.wout = e->W.bfc1 + 256;
+    e->W.bout = e->W.wout + 512; e->W.ub = e->W.bout + 2; e->W.lb = e->W.bout + 4;
+    CK(cudaFuncSetAttribute(k_vn_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, VN_SMEM_BYTES));
+#ifdef B200_WITH_TC
+    {
+        int rc = tc_prepare(&e->tc_state, w, e->stream);
+        if (rc) return fail(B200_ERR_CUDA, "tensor-core weight preparation failed");
+    }
+#endif
+    e->have_weights = true;
+    return B200_OK;
+}
+
+static int ensure_act3(b200_engine *e, size_t rows) {
+    if (e->act3_rows >= rows) return 0;
+    if (dalloc(e, &e->d_act3, rows * 1792, false)) return B200_ERR_CUDA;
+    e->act3_rows = rows;
+    return 0;
+}
+
+// run the network over the request list req[0..*n_req) -> eval_out; device-side count, no host sync
+static int launch_net(b200_engine *e, const uint2 *req, const int32_t *n_req, const uint32_t *keys, int M, float2 *eval_out,
+                      size_t max_rows) {
+    if (!e->have_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
+    if (ensure_act3(e, max_rows)) return B200_ERR_CUDA;
+#ifdef B200_WITH_TC
+    if (e->cfg.eval_kind == B200_EVAL_NET_TC) {
+        return tc_forward(e->tc_state, req, n_req, keys, M, eval_out, max_rows, e->d_act3, e->W, e->n_sm, e->stream,
+                          [&](int ph) { return new PhaseTimer(e, ph); }, [](void *t) { delete (PhaseTimer *)t; });
+    }
+#endif
+    {
+        PhaseTimer t(e, PH_CONV);
+        k_vn_conv<<<e->n_sm, VN_THREADS, VN_SMEM_BYTES, e->stream>>>(e->W, req, n_req, keys, M, e->d_act3);
+    }
+    {
+        PhaseTimer t(e, PH_FC);
+        k_vn_fc<<<e->n_sm * 2, FC_THREADS, 0, e->stream>>>(e->W, e->d_act3, req, n_req, eval_out);
+    }
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- games / roots
+static inline int blocks_groups(int G) { return (G + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK; }
+
+static int check_status(b200_engine *e) {   // cheap: max over the status array computed on the host after a small copy
+    std::vector<int32_t> st(e->A.G);
+    CK(cudaMemcpyAsync(st.data(), e->A.status, st.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int g = 0; g < e->A.G; ++g)
+        if (st[g] != ST_OK) {
+            int code = st[g] == ST_ARENA_FULL ? B200_ERR_ARENA_FULL : B200_ERR_TRACE_FULL;
+            return fail(code, "game " + std::to_string(g) + (st[g] == ST_ARENA_FULL ? ": arena full after garbage collection (raise max_nodes)" : ": trace longer than trace_max"));
+        }
+    return B200_OK;
+}
+
+extern "C" int b200_update_root(b200_engine *e, int auto_reset) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    {
+        PhaseTimer t(e, PH_MISC);
+        k_update_root<<<blocks_groups(e->A.G), TPB, 0, e->stream>>>(e->A, auto_reset, e->d_game_stats);
+    }
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_set_games(b200_engine *e, const uint32_t *recs) {
+    if (!e || !recs) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(e->A.cur, recs, (size_t)e->A.G * REC_WORDS * 4, cudaMemcpyHostToDevice, e->stream));
+    int rc = b200_update_root(e, 0);
+    if (rc) return rc;
+    return check_status(e);
+}
+
+extern "C" int b200_get_games(b200_engine *e, uint32_t *recs) {
+    if (!e || !recs) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(recs, e->A.cur, (size_t)e->A.G * REC_WORDS * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- simulations
+extern "C" int b200_run_sims(b200_engine *e, int sims) {
+    if (!e || sims < 0) return fail(B200_ERR_BAD_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    const Arena &A = e->A;
+    const int G = A.G;
+    const bool need_net = A.mode != MODE_VANILLA && e->cfg.eval_kind != B200_EVAL_SYNTHETIC;
+    if (need_net && !e->have_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
+    for (int s = 0; s < sims; ++s) {
+        CK(cudaMemsetAsync(A.n_req, 0, sizeof(int32_t), e->stream));
+        {
+            PhaseTimer t(e, PH_SELECT);
+            k_select_expand<<<blocks_groups(G), TPB, 0, e->stream>>>(A);
+        }
+        if (A.mode == MODE_VANILLA) {
+            PhaseTimer t(e, PH_ROLLOUT);
+            k_rollout<<<(G + 63) / 64, 64, 0, e->stream>>>(A);
+        } else if (e->cfg.eval_kind == B200_EVAL_SYNTHETIC) {
+            PhaseTimer t(e, PH_SYNTH);
+            k_eval_synthetic<<<(G * 7 + 255) / 256 < 1184 ? (G * 7 + 255) / 256 : 1184, 256, 0, e->stream>>>(A);
+        } else {
+            int rc = launch_net(e, A.req, A.n_req, A.key, A.M, A.eval_out, (size_t)G * (A.mode == MODE_LP ? 7 : 1));
+            if (rc) return rc;
+        }
+        {
+            PhaseTimer t(e, PH_BACKUP);
+            k_backup<<<(G + 127) / 128, 128, 0, e->stream>>>(A);
+        }
+    }
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_get_stats(b200_engine *e, float *stats, int32_t *action) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    {
+        PhaseTimer t(e, PH_MISC);
+        k_root_stats<<<(e->A.G + 127) / 128, 128, 0, e->stream>>>(e->A, e->d_stats, e->d_action);
+    }
+    CK(cudaGetLastError());
+    if (stats) CK(cudaMemcpyAsync(stats, e->d_stats, (size_t)e->A.G * 21 * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (action) CK(cudaMemcpyAsync(action, e->d_action, (size_t)e->A.G * 4, cudaMemcpyDeviceToHost, e->stream));
+    return check_status(e);
+}
+
+extern "C" int b200_env_step(b200_engine *e, const int32_t *actions) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    if (actions) CK(cudaMemcpyAsync(e->d_action, actions, (size_t)e->A.G * 4, cudaMemcpyHostToDevice, e->stream));
+    {
+        PhaseTimer t(e, PH_MISC);
+        k_env_step<<<(e->A.G + 127) / 128, 128, 0, e->stream>>>(e->A.cur, e->d_action, e->A.G);
+    }
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_play_move(b200_engine *e, int sims, int auto_reset, int32_t *actions_out, float *stats_out) {
+    int rc = b200_run_sims(e, sims);
+    if (rc) return rc;
+    rc = b200_get_stats(e, stats_out, actions_out);
+    if (rc) return rc;
+    rc = b200_env_step(e, nullptr);
+    if (rc) return rc;
+    rc = b200_update_root(e, auto_reset);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_status(b200_engine *e, int32_t *status) {
+    if (!e || !status) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(status, e->A.status, (size_t)e->A.G * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int g = 0; g < e->A.G; ++g) status[g] = status[g] == ST_OK ? 0 : (status[g] == ST_ARENA_FULL ? B200_ERR_ARENA_FULL : B200_ERR_TRACE_FULL);
+    return B200_OK;
+}
+
+extern "C" int b200_counters(b200_engine *e, uint64_t *out16) {
+    if (!e || !out16) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(out16, e->A.counters, 16 * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_sync(b200_engine *e) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_set_timing(b200_engine *e, int on) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    flush_timing(e);
+    e->timing = on != 0;
+    for (int i = 0; i < PH_N; ++i) { e->phase_ms[i] = 0; e->phase_launches[i] = 0; }
+    return B200_OK;
+}
+
+extern "C" int b200_phase_ms(b200_engine *e, float *ms8, uint64_t *launches8) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    flush_timing(e);
+    for (int i = 0; i < PH_N; ++i) { if (ms8) ms8[i] = e->phase_ms[i]; if (launches8) launches8[i] = e->phase_launches[i]; }
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- export
+extern "C" int b200_export_game(b200_engine *e, int game, int32_t *child, float *score, int32_t *episode, int32_t *n2o,
+                                int32_t *visit, float *value, float *variance, uint8_t *obs_end, uint32_t *game_recs,
+                                uint32_t *obs_keys, int32_t *root, int32_t *last_trace, int32_t *last_trace_len) {
+    if (!e || game < 0 || game >= e->A.G) return fail(B200_ERR_BAD_ARG, "bad game index");
+    CK(cudaSetDevice(e->cfg.device));
+    const Arena &A = e->A;
+    size_t M = A.M;
+    std::vector<int32_t> row(M * ROW_WORDS);
+    std::vector<int4> stat(M);
+    CK(cudaMemcpyAsync(row.data(), A.row + (size_t)game * M * ROW_WORDS, row.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(stat.data(), A.stat + (size_t)game * M, M * sizeof(int4), cudaMemcpyDeviceToHost, e->stream));
+    if (game_recs) CK(cudaMemcpyAsync(game_recs, A.rec + (size_t)game * M * REC_WORDS, M * REC_WORDS * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (obs_keys) CK(cudaMemcpyAsync(obs_keys, A.key + (size_t)game * M * KEY_WORDS, M * KEY_WORDS * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (root) CK(cudaMemcpyAsync(root, A.root + game, 4, cudaMemcpyDeviceToHost, e->stream));
+    int32_t tl = 0;
+    CK(cudaMemcpyAsync(&tl, A.trace_len + game, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (last_trace_len) *last_trace_len = tl;
+    if (last_trace && tl > 0) {
+        CK(cudaMemcpyAsync(last_trace, A.trace + (size_t)game * A.trace_max, (size_t)tl * 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    for (size_t i = 0; i < M; ++i) {   // unpack the 96-byte node record into the reference's separate arrays (agent.py:58-88)
+        const int32_t *r = &row[i * ROW_WORDS];
+        if (child) for (int a = 0; a < 7; ++a) child[i * 7 + a] = r[a];
+        if (episode) episode[i] = r[7];
+        if (n2o) n2o[i] = r[15];
+        if (score) memcpy(&score[i], &r[23], 4);
+        if (visit) visit[i] = stat[i].x;
+        if (value) memcpy(&value[i], &stat[i].y, 4);
+        if (variance) memcpy(&variance[i], &stat[i].z, 4);
+        if (obs_end) obs_end[i] = (uint8_t)(stat[i].w != 0);
+    }
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- standalone value net
+__global__ void k_states_to_keys(const int8_t *states, int k, uint32_t *keys, uint2 *req) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const int8_t *s = states + (size_t)i * 200;
+    uint32_t key[KEY_WORDS];
+    for (int q = 0; q < KEY_WORDS; ++q) key[q] = 0;
+    uint32_t cells = 0; int n = 0;
+    for (int c = 0; c < 200; ++c) {
+        int r = c / 10, x = c % 10;
+        if (s[c] > 0) key[r >> 1] |= 1u << ((r & 1) * 16 + x);
+        else if (s[c] < 0 && n < 4) { cells |= (uint32_t)c << (8 * n); ++n; }
+    }
+    for (; n < 4; ++n) cells |= 0xffu << (8 * n);   // fewer than four -1 cells: no such cell index (255)
+    key[10] = cells;
+    for (int q = 0; q < KEY_WORDS; ++q) keys[(size_t)i * KEY_WORDS + q] = key[q];
+    // every standalone request gets its own output slot: game = i/8, slot = i%8 -> eval_out[i]
+    req[i] = make_uint2((uint32_t)(i >> 3), (uint32_t)i | ((uint32_t)(i & 7) << 28));
+}
+
+extern "C" int b200_valuenet_forward(b200_engine *e, const int8_t *states, int k, float *v, float *var) {
+    if (!e || !states || !v || !var || k < 1) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (k >= (1 << 28)) return fail(B200_ERR_BAD_ARG, "k too large");
+    CK(cudaSetDevice(e->cfg.device));
+    int8_t *d_states = nullptr; uint32_t *d_keys = nullptr; uint2 *d_req = nullptr; int32_t *d_n = nullptr; float2 *d_out = nullptr;
+    size_t kp = ((size_t)k + 7) & ~(size_t)7;
+    CK(cudaMalloc(&d_states, (size_t)k * 200)); CK(cudaMalloc(&d_keys, kp * KEY_WORDS * 4)); CK(cudaMalloc(&d_req, kp * 8));
+    CK(cudaMalloc(&d_n, 4)); CK(cudaMalloc(&d_out, kp * 8));
+    CK(cudaMemcpyAsync(d_states, states, (size_t)k * 200, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d_n, &k, 4, cudaMemcpyHostToDevice, e->stream));
+    k_states_to_keys<<<(k + 127) / 128, 128, 0, e->stream>>>(d_states, k, d_keys, d_req);
+    // keys are addressed as keys[(game * M + obs)]: with game = i/8 we pass M = 0 so that only obs (= i) indexes
+    int rc = launch_net(e, d_req, d_n, d_keys, 0, d_out, kp);
+    if (rc == B200_OK) {
+        std::vector<float2> h(k);
+        cudaError_t ce = cudaMemcpyAsync(h.data(), d_out, (size_t)k * 8, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) rc = fail(B200_ERR_CUDA, cudaGetErrorString(ce));
+        else for (int i = 0; i < k; ++i) { v[i] = h[i].x; var[i] = h[i].y; }
+    }
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d_states); cudaFree(d_keys); cudaFree(d_req); cudaFree(d_n); cudaFree(d_out);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------- standalone env
+static int env_stream_op(uint32_t *recs, const int32_t *actions, int8_t *state_out, int n) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    uint32_t *d = nullptr; int32_t *da = nullptr; int8_t *ds = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * REC_WORDS * 4));
+    CK(cudaMemcpy(d, recs, (size_t)n * REC_WORDS * 4, cudaMemcpyHostToDevice));
+    if (actions) {
+        CK(cudaMalloc(&da, (size_t)n * 4));
+        CK(cudaMemcpy(da, actions, (size_t)n * 4, cudaMemcpyHostToDevice));
+        k_env_step<<<(n + 127) / 128, 128>>>(d, da, n);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(recs, d, (size_t)n * REC_WORDS * 4, cudaMemcpyDeviceToHost));
+    }
+    if (state_out) {
+        CK(cudaMalloc(&ds, (size_t)n * 200));
+        k_env_state<<<(n + 127) / 128, 128>>>(d, ds, n);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(state_out, ds, (size_t)n * 200, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d); cudaFree(da); cudaFree(ds);
+    return B200_OK;
+}
+
+extern "C" int b200_tetris_new(uint32_t *recs, int n, int app, int scoring, int randomizer, const uint32_t *seeds, int reset) {
+    if (!recs || n < 1) return fail(B200_ERR_BAD_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    uint32_t *d = nullptr, *ds = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * REC_WORDS * 4));
+    if (reset) CK(cudaMemcpy(d, recs, (size_t)n * REC_WORDS * 4, cudaMemcpyHostToDevice));
+    if (seeds && !reset) { CK(cudaMalloc(&ds, (size_t)n * 4)); CK(cudaMemcpy(ds, seeds, (size_t)n * 4, cudaMemcpyHostToDevice)); }
+    k_new_games<<<(n + 127) / 128, 128>>>(d, n, app, scoring, randomizer, ds, reset);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(recs, d, (size_t)n * REC_WORDS * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(ds);
+    return B200_OK;
+}
+
+extern "C" int b200_tetris_step(uint32_t *recs, const int32_t *actions, int n) {
+    if (!recs || !actions || n < 1) return fail(B200_ERR_BAD_ARG, "bad argument");
+    return env_stream_op(recs, actions, nullptr, n);
+}
+extern "C" int b200_tetris_state(const uint32_t *recs, int8_t *out, int n) {
+    if (!recs || !out || n < 1) return fail(B200_ERR_BAD_ARG, "bad argument");
+    return env_stream_op(const_cast<uint32_t *>(recs), nullptr, out, n);
+}
+
+// ---------------------------------------------------------------------------------------------------- core twins
+struct TwinBufs {
+    int32_t *child = nullptr, *visit = nullptr, *n2o = nullptr, *trace = nullptr, *out = nullptr;
+    float *value = nullptr, *variance = nullptr, *score = nullptr, *zt = nullptr;
+    uint32_t *rng = nullptr;
+    std::vector<void *> all;
+    ~TwinBufs() { for (void *p : all) cudaFree(p); }
+    template <typename T> int up(T **d, const T *h, size_t n) {
+        if (cudaMalloc((void **)d, (n ? n : 1) * sizeof(T)) != cudaSuccess) return 1;
+        all.push_back(*d);
+        if (h && n) return cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess;
+        return cudaMemset(*d, 0, (n ? n : 1) * sizeof(T)) != cudaSuccess;
+    }
+};
+
+static int twin_arena(TwinBufs &b, Arena &A) {
+    memset(&A, 0, sizeof(A));
+    std::vector<float> h(ZTABLE_N);
+    const double l2 = log(2.0), l22 = log(22.0), l41 = log(41.0);
+    for (int n = 0; n < ZTABLE_N; ++n) {
+        double t = (double)n, alpha = 1 - 1 / t;
+        h[n] = (float)(10 * log(1 - log(-log(alpha) / l2) / l22) / l41);
+    }
+    if (b.up(&b.zt, h.data(), (size_t)ZTABLE_N)) return 1;
+    A.ztable = b.zt;
+    return 0;
+}
+
+#define TW(x) do { if (x) return fail(B200_ERR_CUDA, "twin: device allocation/copy failed"); } while (0)
+
+extern "C" int b200_select_trace_obs(int index, const int32_t *child, const int32_t *visit, const float *value,
+                                     const float *variance, const float *score, const int32_t *n_to_o, int M, int low,
+                                     uint32_t *rng_state, int32_t *trace_out, int max_trace, int32_t *trace_len) {
+    if (!child || !visit || !value || !variance || !score || !n_to_o || !trace_out || !trace_len || index < 0 || index >= M)
+        return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; Arena A;
+    TW(twin_arena(b, A));
+    uint32_t seed = rng_state ? *rng_state : 0x2545F491u;
+    TW(b.up(&b.child, child, (size_t)M * 7)); TW(b.up(&b.visit, visit, (size_t)M)); TW(b.up(&b.value, value, (size_t)M));
+    TW(b.up(&b.variance, variance, (size_t)M)); TW(b.up(&b.score, score, (size_t)M)); TW(b.up(&b.n2o, n_to_o, (size_t)M));
+    TW(b.up(&b.trace, (const int32_t *)nullptr, (size_t)max_trace)); TW(b.up(&b.out, (const int32_t *)nullptr, 16)); TW(b.up(&b.rng, &seed, 1));
+    TwinArgs t{b.child, b.visit, b.value, b.variance, b.score, b.n2o, b.trace, b.rng, b.out};
+    k_twin_select<<<1, 32>>>(A, t, index, low, max_trace);
+    CK(cudaGetLastError());
+    int32_t out[2];
+    CK(cudaMemcpy(out, b.out, 8, cudaMemcpyDeviceToHost));
+    if (out[1] != ST_OK) return fail(B200_ERR_TRACE_FULL, "trace longer than max_trace");
+    CK(cudaMemcpy(trace_out, b.trace, (size_t)out[0] * 4, cudaMemcpyDeviceToHost));
+    if (rng_state) CK(cudaMemcpy(rng_state, b.rng, 4, cudaMemcpyDeviceToHost));
+    *trace_len = out[0];
+    return B200_OK;
+}
+
+extern "C" int b200_get_unique_child_obs(int index, const int32_t *child, const float *score, const int32_t *n_to_o, int M,
+                                         int32_t *c_nodes, int32_t *c_obs, int32_t *k_out) {
+    if (!child || !score || !n_to_o || !c_nodes || !c_obs || !k_out || index < 0 || index >= M) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; Arena A;
+    TW(twin_arena(b, A));
+    TW(b.up(&b.child, child, (size_t)M * 7)); TW(b.up(&b.score, score, (size_t)M)); TW(b.up(&b.n2o, n_to_o, (size_t)M));
+    TW(b.up(&b.out, (const int32_t *)nullptr, 16));
+    TwinArgs t{b.child, nullptr, nullptr, nullptr, b.score, b.n2o, nullptr, nullptr, b.out};
+    k_twin_unique<<<1, 32>>>(A, t, index);
+    CK(cudaGetLastError());
+    int32_t out[16];
+    CK(cudaMemcpy(out, b.out, 64, cudaMemcpyDeviceToHost));
+    *k_out = out[0];
+    for (int i = 0; i < out[0]; ++i) { c_nodes[i] = out[1 + i]; c_obs[i] = out[8 + i]; }
+    return B200_OK;
+}
+
+static int twin_backup_common(TwinBufs &b, const int32_t *trace, int D, int32_t *visit, float *value, float *variance,
+                              const int32_t *n_to_o, const float *score, int M) {
+    if (b.up(&b.trace, trace, (size_t)D) || b.up(&b.visit, (const int32_t *)visit, (size_t)M) || b.up(&b.value, (const float *)value, (size_t)M) ||
+        b.up(&b.variance, (const float *)variance, (size_t)M) || b.up(&b.n2o, n_to_o, (size_t)M) || b.up(&b.score, score, (size_t)M)) return 1;
+    return 0;
+}
+static int twin_backup_fetch(TwinBufs &b, int32_t *visit, float *value, float *variance, int M) {
+    if (cudaMemcpy(visit, b.visit, (size_t)M * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    if (cudaMemcpy(value, b.value, (size_t)M * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    if (cudaMemcpy(variance, b.variance, (size_t)M * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return 0;
+}
+
+extern "C" int b200_backup_trace_obs(const int32_t *trace, int D, int32_t *visit, float *value, float *variance,
+                                     const int32_t *n_to_o, const float *score, int M, double v, double var, double gamma) {
+    if (!trace || D < 1 || !visit || !value || !variance || !n_to_o || !score) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; Arena A;
+    TW(twin_arena(b, A));
+    TW(twin_backup_common(b, trace, D, visit, value, variance, n_to_o, score, M));
+    TwinArgs t{nullptr, b.visit, b.value, b.variance, b.score, b.n2o, b.trace, nullptr, nullptr};
+    k_twin_backup<<<1, 1>>>(A, t, D, v, var, gamma, 0);
+    CK(cudaGetLastError());
+    TW(twin_backup_fetch(b, visit, value, variance, M));
+    return B200_OK;
+}
+
+extern "C" int b200_backup_trace_obs_LP(const int32_t *trace, int D, int32_t *visit, float *value, float *variance,
+                                        const int32_t *n_to_o, const float *score, const uint8_t *end, int M,
+                                        const int32_t *c_nodes, const int32_t *c_obs, int k, const float *v, const float *var,
+                                        double gamma, int mixture, int averaged) {
+    if (!trace || D < 1 || !visit || !value || !variance || !n_to_o || !score || !end || k < 0 || k > 7) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; Arena A;
+    TW(twin_arena(b, A));
+    TW(twin_backup_common(b, trace, D, visit, value, variance, n_to_o, score, M));
+    uint8_t *d_end = nullptr; int32_t *d_cn = nullptr, *d_co = nullptr; float *d_v = nullptr, *d_var = nullptr;
+    TW(b.up(&d_end, end, (size_t)M)); TW(b.up(&d_cn, c_nodes, (size_t)k)); TW(b.up(&d_co, c_obs, (size_t)k));
+    TW(b.up(&d_v, v, (size_t)k)); TW(b.up(&d_var, var, (size_t)k));
+    TwinArgs t{nullptr, b.visit, b.value, b.variance, b.score, b.n2o, b.trace, nullptr, nullptr};
+    k_twin_backup_lp<<<1, 1>>>(A, t, D, d_end, d_cn, d_co, k, d_v, d_var, gamma, mixture, averaged);
+    CK(cudaGetLastError());
+    TW(twin_backup_fetch(b, visit, value, variance, M));
+    return B200_OK;
+}
+
+extern "C" int b200_get_all_childs(int index, const int32_t *child, int M, uint8_t *mark) {
+    if (!child || !mark || index < 0 || index >= M) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b;
+    uint8_t *d_mark = nullptr; int32_t *d_q = nullptr;
+    TW(b.up(&b.child, child, (size_t)M * 7)); TW(b.up(&d_mark, (const uint8_t *)nullptr, (size_t)M)); TW(b.up(&d_q, (const int32_t *)nullptr, (size_t)M));
+    k_twin_all_childs<<<1, 32>>>(b.child, M, index, d_mark, d_q);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(mark, d_mark, (size_t)M, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- replay samples
+__global__ void k_collect_samples(Arena A, int min_visits, uint8_t *out, int capacity, int32_t *count) {
+    size_t n = (size_t)A.G * A.M;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int4 st = A.stat[i];
+        if (st.x < min_visits || st.w != 0 || st.x == 0) continue;      // ValueSim.py:143-144 (visit < min or end)
+        int slot = atomicAdd(count, 1);
+        if (slot >= capacity) continue;
+        uint8_t *dst = out + (size_t)slot * 212;
+        const uint32_t *k = A.key + i * KEY_WORDS;
+        for (int r = 0; r < 20; ++r) {
+            uint32_t row = (k[r >> 1] >> ((r & 1) * 16)) & 0x3ffu;
+            for (int c = 0; c < 10; ++c) dst[r * 10 + c] = (uint8_t)((row >> c) & 1u);
+        }
+        for (int j = 0; j < 4; ++j) dst[(k[10] >> (8 * j)) & 0xffu] = 0xff;    // int8 -1
+        float f[3] = {__int_as_float(st.y), __int_as_float(st.z), (float)st.x};
+        memcpy(dst + 200, f, 12);
+    }
+}
+
+extern "C" int b200_collect_samples_dev(b200_engine *e, int min_visits, void *out_dev, int capacity, int32_t *count_out) {
+    if (!e || !out_dev || capacity < 0 || !count_out) return fail(B200_ERR_BAD_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->d_sample_count) { if (dalloc(e, &e->d_sample_count, 1)) return B200_ERR_CUDA; }
+    CK(cudaMemsetAsync(e->d_sample_count, 0, 4, e->stream));
+    k_collect_samples<<<e->n_sm * 4, 256, 0, e->stream>>>(e->A, min_visits, (uint8_t *)out_dev, capacity, e->d_sample_count);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(count_out, e->d_sample_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (*count_out > capacity) *count_out = capacity;
+    return B200_OK;
+}

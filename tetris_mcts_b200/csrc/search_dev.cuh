@@ -1,0 +1,574 @@
+// search_dev.cuh — device side of the per-move MCTS simulation loop (sm_100a).
+//
+// One 8-lane group (quarter warp) owns one game's tree for the whole kernel; lane a (0..6) is child slot /
+// action a, lane 7 carries the node's own fields.  Trees never share memory between games, so there are no
+// inter-game races and no atomics on tree state.
+//
+// Reference functions restated here (file:line in /root/reference):
+//   get_unique_child_obs  agents/cppmodule/core.h:111-144        -> unique_children()
+//   check_low             core.h:65-77                            -> inside select_trace()
+//   policy_clt            core.h:83-105, special.h:26-33          -> clt_q(), select_trace()
+//   select_trace_obs      core.h:167-224                          -> select_trace()
+//   backup_trace_obs      core.h:226-260                          -> welford_level(), backup_trace()
+//   backup_trace_obs_LP   core.h:303-381 (averaged, non-mixture)  -> lp_init_and_average()
+//   new_node / expand     agents/agent.py:90-145                  -> new_node(), expand_leaf()
+//   remove_nodes          agents/agent.py:187-257, core.h:32-50   -> collect_garbage()
+//   compute_stats         agents/agent.py:153-185                 -> root_stats()
+//
+// Bit-exactness: every float/double operation that the reference evaluates (g++ -O3, x86-64, no FMA) is written
+// with explicit round-to-nearest intrinsics so that nvcc cannot contract it into an FMA.
+#pragma once
+#include <stdint.h>
+#include "tetris_dev.cuh"
+
+namespace b200 {
+
+constexpr int ROW_WORDS = 24;     // child row: c[8] | o[8] | s[8]
+constexpr int ZTABLE_N = 65536;   // z(n) table computed on the host with the reference's libm (special.h:26-33)
+
+enum : int { ST_OK = 0, ST_ARENA_FULL = 1, ST_TRACE_FULL = 2 };
+enum : int { LEAF_TERMINAL = 0, LEAF_EXPANDED = 1 };
+enum : int { MODE_LP = 0, MODE_SINGLE = 1, MODE_VANILLA = 2 };
+
+// HBM layout (all arrays are [game][...]; SoA across games, records kept 16-byte aligned):
+//   row      [G][M][24] i32/f32  node record: child ids c[0..6], c[7]=episode | child obs o[0..6], o[7]=own obs |
+//                                 child scores s[0..6], s[7]=own score.  One 96-B read gives select everything that
+//                                 the reference gathers from child[idx], n_to_o[c], score[c], score[idx].
+//   stat     [G][M]     int4     observation statistics {visit, value, variance, end}  (one 128-bit load/store)
+//   rec      [G][M][20] u32      packed game (SPEC §6), the node key
+//   key      [G][M][12] u32      observation key (SPEC §6), the statistics key
+//   ntab/otab[G][H]     uint2    open-addressing tables {hash32, index}; index 0 empty, 0xffffffff deleted
+//   nfree/ofree [G][M]  i32      free lists, popped from the back (agents/agent.py:72,99)
+struct Arena {
+    int G, M, H, trace_max;
+    int mode, low, lp_end_from_obs, lp_var_gamma2, stale_pop, eval_kind;
+    double gamma, rollout_variance;
+    int32_t *row; int4 *stat; uint32_t *rec; uint32_t *key;
+    uint2 *ntab, *otab;
+    int32_t *nfree, *ofree; int32_t *n_nfree, *n_ofree;
+    int32_t *root, *episode, *status; uint32_t *srng;
+    int32_t *trace, *trace_len, *leaf_kind;
+    uint8_t *nmark, *omark; int32_t *gc_queue;
+    uint32_t *cur;                 // [G][20] the live game of each tree (the object play.py owns)
+    const float *ztable;
+    uint2 *req; int32_t *n_req;    // evaluation requests {game, obs | slot<<28}
+    float2 *eval_out;              // [G][8] (value, variance) per child slot; slot 7 = the leaf itself
+    float *rollout_val;            // [G]
+    unsigned long long *counters;  // [8] 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels 5 rollout steps 6 new nodes
+};
+
+// ------------------------------------------------------------------ group helpers
+struct Grp {
+    unsigned mask; int lane;   // lane within the 8-lane group
+    __device__ __forceinline__ Grp() {
+        int l = threadIdx.x & 31;
+        lane = l & 7;
+        mask = 0xffu << (l & 24);
+    }
+    template <typename T> __device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(mask, v, src, 8); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> ((threadIdx.x & 31) & 24)) & 0xffu; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+__device__ __forceinline__ size_t node_at(const Arena &A, int g, int i) { return (size_t)g * A.M + i; }
+
+// ------------------------------------------------------------------ exact arithmetic (see header comment)
+__device__ __forceinline__ float ztab(const Arena &A, int n) {
+    if (n >= 0 && n < ZTABLE_N) return A.ztable[n];
+    double t = (double)n;                                   // special.h:26-33, evaluated in double
+    double alpha = __dsub_rn(1.0, __ddiv_rn(1.0, t));
+    double a = __ddiv_rn(-log(alpha), log(2.0));
+    double b = __dsub_rn(1.0, __ddiv_rn(log(a), log(22.0)));
+    return (float)__ddiv_rn(__dmul_rn(10.0, log(b)), log(41.0));   // core.h:93 narrows to float
+}
+
+// core.h:94 + core.h:213: q = (V[o] + score[c] - score[idx]) + z * sqrt(S2[o] / N[o]), all in float
+__device__ __forceinline__ float clt_q(float V, float sc, float sidx, float z, float S2, int N) {
+    float val = __fsub_rn(__fadd_rn(V, sc), sidx);
+    float root = __fsqrt_rn(__fdiv_rn(S2, (float)N));
+    return __fadd_rn(val, __fmul_rn(z, root));
+}
+
+// core.h:244-258, one trace level.  v is carried in double; stores narrow to float.
+__device__ __forceinline__ void welford_level(int4 &st, double &v, double var, float score_idx, double gamma) {
+    v = __dsub_rn(v, (double)score_idx);
+    int n = st.x;
+    float val = __int_as_float(st.y), s2 = __int_as_float(st.z);
+    if (n == 0) {
+        val = (float)v;
+        s2 = (float)var;
+    } else {
+        double delta = __dsub_rn(v, (double)val);
+        val = (float)__dadd_rn((double)val, __ddiv_rn(delta, (double)(n + 1)));
+        double delta2 = __dsub_rn(v, (double)val);
+        s2 = (float)__dadd_rn((double)s2, __ddiv_rn(__dsub_rn(__dmul_rn(delta, delta2), (double)s2), (double)(n + 1)));
+    }
+    st.x = n + 1; st.y = __float_as_int(val); st.z = __float_as_int(s2);
+    v = __dadd_rn(__dmul_rn(gamma, v), (double)score_idx);
+}
+
+// ------------------------------------------------------------------ unique children (core.h:111-144)
+// In: lane a (<7) holds child slot a as (c, o, s).  Out, per lane: is_first (this lane is the first occurrence of
+// its observation: the list position), rep_c / rep_s = the child that represents the observation (the one with the
+// strictly largest score, earliest on ties).
+struct Uniq { bool is_first; int rep_c; float rep_s; unsigned first_mask; };
+
+__device__ __forceinline__ Uniq unique_children(const Grp &gp, int c, int o, float s) {
+    bool valid = gp.lane < 7 && c != 0;
+    unsigned vmask = gp.ballot(valid);
+    int first = -1, rep_c = 0;
+    float best = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        int cj = gp.bcast(c, j), oj = gp.bcast(o, j);
+        float sj = gp.bcast(s, j);
+        if (((vmask >> j) & 1u) && oj == o) {
+            if (first < 0) { first = j; best = sj; rep_c = cj; }
+            else if (sj > best) { best = sj; rep_c = cj; }      // strict >, core.h:139
+        }
+    }
+    Uniq u;
+    u.is_first = valid && first == gp.lane;
+    u.rep_c = rep_c; u.rep_s = best;
+    u.first_mask = gp.ballot(u.is_first);
+    return u;
+}
+
+// ------------------------------------------------------------------ accessors
+// The engine keeps the packed arena above; the single-call twins of agents/cppmodule/core.cpp:20-26 work on the
+// reference's own array layout (agents/agent.py:58-88).  Both run the same select / backup code through these.
+struct ArenaAcc {
+    const Arena &A; int g;
+    __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
+        const int32_t *row = A.row + node_at(A, g, idx) * ROW_WORDS;
+        c = row[lane]; o = row[8 + lane]; s = __int_as_float(row[16 + lane]);   // lane 7: own episode / obs / score
+    }
+    __device__ __forceinline__ void meta(int idx, int &o, float &s) const {
+        const int32_t *row = A.row + node_at(A, g, idx) * ROW_WORDS;
+        o = row[15]; s = __int_as_float(row[23]);
+    }
+    __device__ __forceinline__ int4 stat(int o) const { return A.stat[node_at(A, g, o)]; }
+    __device__ __forceinline__ void set_stat(int o, int4 st) const { A.stat[node_at(A, g, o)] = st; }
+    __device__ __forceinline__ void put_trace(int d, int idx) const { A.trace[(size_t)g * A.trace_max + d] = idx; }
+    __device__ __forceinline__ int get_trace(int d) const { return A.trace[(size_t)g * A.trace_max + d]; }
+    __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
+    __device__ __forceinline__ float z(int n) const { return ztab(A, n); }
+};
+
+struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
+    const int32_t *child; int32_t *visit; float *value; float *variance; const float *score; const int32_t *n2o;
+    int32_t *trace; uint32_t *rng; const Arena *A;
+    __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
+        if (lane < 7) { c = child[(size_t)idx * 7 + lane]; o = n2o[c]; s = score[c]; }
+        else { c = 0; o = n2o[idx]; s = score[idx]; }
+    }
+    __device__ __forceinline__ void meta(int idx, int &o, float &s) const { o = n2o[idx]; s = score[idx]; }
+    __device__ __forceinline__ int4 stat(int o) const { return make_int4(visit[o], __float_as_int(value[o]), __float_as_int(variance[o]), 0); }
+    __device__ __forceinline__ void set_stat(int o, int4 st) const { visit[o] = st.x; value[o] = __int_as_float(st.y); variance[o] = __int_as_float(st.z); }
+    __device__ __forceinline__ void put_trace(int d, int idx) const { trace[d] = idx; }
+    __device__ __forceinline__ int get_trace(int d) const { return trace[d]; }
+    __device__ __forceinline__ uint32_t rand() const { uint32_t sr = *rng; uint32_t r = rng_next(sr); *rng = sr; return r; }
+    __device__ __forceinline__ float z(int n) const { return ztab(*A, n); }
+};
+
+// ------------------------------------------------------------------ select (core.h:167-224)
+// Returns the leaf; writes the trace.  All 8 lanes return the same values.
+template <typename Acc>
+__device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int root, int low, int trace_max, int &D_out, int &status) {
+    int idx = root, D = 0;
+    for (;;) {
+        if (D >= trace_max) { status = ST_TRACE_FULL; break; }
+        if (gp.lane == 0) acc.put_trace(D, idx);
+        ++D;
+        int c, o; float s;
+        acc.children(idx, gp.lane, c, o, s);
+        float s_idx = gp.bcast(s, 7);
+        Uniq u = unique_children(gp, c, o, s);
+        if (u.first_mask == 0) break;                                   // core.h:200 no children: leaf
+        int4 st = make_int4(0, 0, 0, 0);
+        if (u.is_first) st = acc.stat(o);
+        unsigned lowmask = gp.ballot(u.is_first && st.x < low);          // core.h:65-77
+        int pick;
+        if (lowmask) {
+            uint32_t r = 0;
+            if (gp.lane == 0) r = acc.rand();
+            r = gp.bcast(r, 0);
+            pick = (int)__fns(lowmask, 0, (int)(r % (uint32_t)__popc(lowmask)) + 1);
+        } else {
+            int n = u.is_first ? st.x : 0;                               // core.h:88 accumulate(visit)
+            n += __shfl_xor_sync(gp.mask, n, 1, 8);
+            n += __shfl_xor_sync(gp.mask, n, 2, 8);
+            n += __shfl_xor_sync(gp.mask, n, 4, 8);
+            float z = acc.z(n);
+            float q = u.is_first ? clt_q(__int_as_float(st.y), u.rep_s, s_idx, z, __int_as_float(st.z), st.x) : 0.f;
+            pick = -1;
+            float max_q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {                                // core.h:94-101 first strict max in list order
+                float qj = gp.bcast(q, j);
+                if ((u.first_mask >> j) & 1u) {
+                    if (pick < 0) { pick = j; max_q = qj; }
+                    else if (qj > max_q) { max_q = qj; pick = j; }
+                }
+            }
+        }
+        idx = gp.bcast(u.rep_c, pick);
+    }
+    D_out = D;
+    return idx;
+}
+
+// ------------------------------------------------------------------ hash tables
+__device__ __forceinline__ uint32_t fold32(uint64_t h) { uint32_t x = (uint32_t)(h ^ (h >> 32)); return x ? x : 1u; }
+
+// Find `words` (nw of them, held identically by every lane) in a table whose entries index `store` records.
+// Group-cooperative: lane j compares uint4 j of the candidate record.  Returns index or 0.
+template <int NW>
+__device__ __forceinline__ int table_find(const Grp &gp, const uint2 *tab, int H, const uint32_t *store, size_t base,
+                                          const uint32_t (&words)[NW], uint32_t h, int *slot_out = nullptr) {
+    uint32_t p = h & (uint32_t)(H - 1);
+    for (;;) {
+        uint2 e = tab[p];
+        if (e.y == 0u) return 0;
+        if (e.y != 0xffffffffu && e.x == h) {
+            bool eq = true;
+            if (gp.lane * 4 < NW) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(store + (base + e.y) * NW + gp.lane * 4);
+                int k = gp.lane * 4;
+                // words[] is indexed with a lane-dependent offset; unrolled selects keep it in registers
+                uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+                for (int q = 0; q < NW / 4; ++q)
+                    if (q * 4 == k) { a0 = words[q * 4]; a1 = words[q * 4 + 1]; a2 = words[q * 4 + 2]; a3 = words[q * 4 + 3]; }
+                eq = v.x == a0 && v.y == a1 && v.z == a2 && v.w == a3;
+            }
+            if (gp.ballot(eq) == 0xffu) { if (slot_out) *slot_out = (int)p; return (int)e.y; }
+        }
+        p = (p + 1) & (uint32_t)(H - 1);
+    }
+}
+
+__device__ __forceinline__ void table_insert(const Grp &gp, uint2 *tab, int H, uint32_t h, int idx) {
+    if (gp.lane == 0) {
+        uint32_t p = h & (uint32_t)(H - 1);
+        for (;;) {
+            uint32_t y = tab[p].y;
+            if (y == 0u || y == 0xffffffffu) break;
+            p = (p + 1) & (uint32_t)(H - 1);
+        }
+        tab[p] = make_uint2(h, (uint32_t)idx);
+    }
+    gp.sync();
+}
+
+// ------------------------------------------------------------------ garbage collection (agent.py:187-257)
+__device__ __noinline__ void collect_garbage(const Arena &A, const Grp &gp, int g) {
+    const int M = A.M, H = A.H;
+    uint8_t *nmark = A.nmark + (size_t)g * M, *omark = A.omark + (size_t)g * M;
+    int32_t *queue = A.gc_queue + (size_t)g * 2 * M;
+    int32_t *rowb = A.row + (size_t)g * M * ROW_WORDS;
+    uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
+    const int root = A.root[g];
+    for (int i = gp.lane; i < M; i += 8) { nmark[i] = 0; omark[i] = 0; }
+    gp.sync();
+    // get_all_childs (core.h:32-50): breadth-first over child[], the null node 0 included
+    if (gp.lane == 0) { nmark[root] = 1; nmark[0] = 1; queue[0] = root; }
+    gp.sync();
+    int head = 0, tail = 1;
+    while (head < tail) {
+        int n = queue[head++];
+        int c = (gp.lane < 7) ? rowb[(size_t)n * ROW_WORDS + gp.lane] : 0;
+        bool fresh = gp.lane < 7 && c != 0 && nmark[c] == 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {            // the same child may sit in two slots: the earliest lane pushes it
+            int cj = gp.bcast(c, j);
+            if (gp.lane > j && cj == c) fresh = false;
+        }
+        unsigned fm = gp.ballot(fresh);
+        if (fresh) { nmark[c] = 1; queue[tail + __popc(fm & ((1u << gp.lane) - 1u))] = c; }
+        tail += __popc(fm);
+        gp.sync();
+    }
+    // update_available (agent.py:187-204): ascending complements; observations of occupied nodes stay
+    for (int i = gp.lane; i < M; i += 8)
+        if (nmark[i]) omark[rowb[(size_t)i * ROW_WORDS + 15]] = 1;   // n_to_o[i] lives in o[7]; n_to_o[0] = 0
+    gp.sync();
+    int32_t *nfree = A.nfree + (size_t)g * M, *ofree = A.ofree + (size_t)g * M;
+    int nn = 0, no = 0;
+    for (int base = 0; base < M; base += 8) {
+        int i = base + gp.lane;
+        bool fn = i < M && !nmark[i], fo = i < M && !omark[i];
+        unsigned mn = gp.ballot(fn), mo = gp.ballot(fo);
+        unsigned below = (1u << gp.lane) - 1u;
+        if (fn) nfree[nn + __popc(mn & below)] = i;
+        if (fo) ofree[no + __popc(mo & below)] = i;
+        nn += __popc(mn); no += __popc(mo);
+    }
+    gp.sync();
+    // reset_arrays (agent.py:227-244).  Node table: the reference pops BY THE FREED SLOT'S CURRENT GAME
+    // (agent.py:229-232), which for a slot freed at an earlier collection is a stale state that may equal a live
+    // node's state; that live node then loses its entry.  stale_pop=1 reproduces this literally.
+    const uint32_t *recb = A.rec + (size_t)g * M * REC_WORDS;
+    if (A.stale_pop) {
+        for (int j = 0; j < nn; ++j) {
+            int i = nfree[j];
+            uint32_t w[REC_WORDS];
+#pragma unroll
+            for (int q = 0; q < REC_WORDS / 4; ++q) {
+                uint4 v = *reinterpret_cast<const uint4 *>(recb + (size_t)i * REC_WORDS + q * 4);
+                w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
+            }
+            int slot = -1;
+            int hit = table_find<REC_WORDS>(gp, ntab, H, A.rec, (size_t)g * M, w, fold32(hash_words(w, REC_WORDS)), &slot);
+            if (hit && gp.lane == 0) ntab[slot].y = 0xffffffffu;
+            gp.sync();
+        }
+    } else {
+        for (int p = gp.lane; p < H; p += 8) { uint32_t y = ntab[p].y; if (y != 0u && y != 0xffffffffu && !nmark[y]) ntab[p].y = 0xffffffffu; }
+        gp.sync();
+    }
+    for (int p = gp.lane; p < H; p += 8) { uint32_t y = otab[p].y; if (y != 0u && y != 0xffffffffu && !omark[y]) otab[p].y = 0xffffffffu; }
+    gp.sync();
+    // compact both tables (drop deleted entries): survivors -> queue (as hash,index pairs) -> cleared table
+    for (int t = 0; t < 2; ++t) {
+        uint2 *tab = t ? otab : ntab;
+        uint2 *list = reinterpret_cast<uint2 *>(queue);   // gc_queue holds 2M ints = M pairs >= any survivor count
+        {
+            int cnt = 0;
+            for (int base = 0; base < H; base += 8) {
+                uint2 e = tab[base + gp.lane];
+                bool live = e.y != 0u && e.y != 0xffffffffu;
+                unsigned m = gp.ballot(live);
+                if (live) list[cnt + __popc(m & ((1u << gp.lane) - 1u))] = e;
+                cnt += __popc(m);
+                tab[base + gp.lane] = make_uint2(0u, 0u);
+            }
+            gp.sync();
+            for (int j = gp.lane; j < cnt; j += 8) {      // lanes claim slots with CAS; keys are unique so order is free
+                uint2 e = list[j];
+                uint32_t p = e.x & (uint32_t)(H - 1);
+                while (atomicCAS(&tab[p].y, 0u, e.y) != 0u) p = (p + 1) & (uint32_t)(H - 1);
+                tab[p].x = e.x;
+            }
+            gp.sync();
+        }
+    }
+    // zero the freed rows / statistics / keys
+    for (int j = 0; j < nn; ++j) {
+        int i = nfree[j];
+        int4 *r = reinterpret_cast<int4 *>(rowb + (size_t)i * ROW_WORDS);
+        if (gp.lane < 6) r[gp.lane] = make_int4(0, 0, 0, 0);
+    }
+    int4 *statb = A.stat + (size_t)g * M;
+    uint32_t *keyb = A.key + (size_t)g * M * KEY_WORDS;
+    for (int j = 0; j < no; ++j) {
+        int i = ofree[j];
+        if (gp.lane == 0) statb[i] = make_int4(0, 0, 0, 0);
+        if (gp.lane >= 1 && gp.lane < 4) reinterpret_cast<uint4 *>(keyb + (size_t)i * KEY_WORDS)[gp.lane - 1] = make_uint4(0, 0, 0, 0);
+    }
+    if (gp.lane == 0) { A.n_nfree[g] = nn; A.n_ofree[g] = no; atomicAdd(&A.counters[3], 1ull); }
+    gp.sync();
+}
+
+// ------------------------------------------------------------------ new_node (agent.py:90-130)
+// `w` = packed game, held identically by all lanes.  Returns node index (0 on arena overflow); o_out/score_out are
+// the node's observation and score (what the parent's row caches for it).
+__device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, const uint32_t (&w)[REC_WORDS], int &o_out,
+                                        float &score_out, int &status) {
+    const int M = A.M, H = A.H;
+    uint2 *ntab = A.ntab + (size_t)g * H;
+    uint32_t h = fold32(hash_words(w, REC_WORDS));
+    int idx = table_find<REC_WORDS>(gp, ntab, H, A.rec, (size_t)g * M, w, h);
+    int32_t *rowb = A.row + (size_t)g * M * ROW_WORDS;
+    if (idx) {
+        o_out = rowb[(size_t)idx * ROW_WORDS + 15];
+        score_out = __int_as_float(rowb[(size_t)idx * ROW_WORDS + 23]);
+        return idx;
+    }
+    int nf = A.n_nfree[g];
+    if (nf == 0) { collect_garbage(A, gp, g); nf = A.n_nfree[g]; }        // agent.py:96-97
+    if (nf == 0) { status = ST_ARENA_FULL; o_out = 0; score_out = 0.f; return 0; }
+    idx = A.nfree[(size_t)g * M + nf - 1];                                  // agent.py:99 pop() from the right
+    gp.sync();
+    if (gp.lane == 0) A.n_nfree[g] = nf - 1;
+    if (gp.lane < 5) {
+        uint4 v;
+        int k = gp.lane * 4;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) if (q * 4 == k) { a0 = w[q * 4]; a1 = w[q * 4 + 1]; a2 = w[q * 4 + 2]; a3 = w[q * 4 + 3]; }
+        v = make_uint4(a0, a1, a2, a3);
+        *reinterpret_cast<uint4 *>(A.rec + ((size_t)g * M + idx) * REC_WORDS + k) = v;
+    }
+    gp.sync();
+    table_insert(gp, ntab, H, h, idx);
+    // observation (agent.py:114-128)
+    Game gm;
+    unpack(gm, w);
+    uint32_t key[KEY_WORDS];
+    obskey(gm, key);
+    uint32_t hk = fold32(hash_words(key, KEY_WORDS));
+    uint2 *otab = A.otab + (size_t)g * H;
+    int o = table_find<KEY_WORDS>(gp, otab, H, A.key, (size_t)g * M, key, hk);
+    if (!o) {
+        int nof = A.n_ofree[g];
+        o = A.ofree[(size_t)g * M + nof - 1];
+        gp.sync();
+        if (gp.lane == 0) {
+            A.n_ofree[g] = nof - 1;
+            A.stat[node_at(A, g, o)] = make_int4(0, 0, 0, gm.end);
+        }
+        if (gp.lane >= 1 && gp.lane < 4) {
+            int k = (gp.lane - 1) * 4;
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) if (q * 4 == k) { a0 = key[q * 4]; a1 = key[q * 4 + 1]; a2 = key[q * 4 + 2]; a3 = key[q * 4 + 3]; }
+            *reinterpret_cast<uint4 *>(A.key + ((size_t)g * M + o) * KEY_WORDS + k) = make_uint4(a0, a1, a2, a3);
+        }
+        gp.sync();
+        table_insert(gp, otab, H, hk, o);
+    }
+    float sc = (float)gm.score;                                             // agent.py:106 score[idx] = game.score
+    if (gp.lane == 7) {
+        int32_t *r = rowb + (size_t)idx * ROW_WORDS;
+        r[7] = A.episode[g]; r[15] = o; r[23] = __float_as_int(sc);
+    }
+    if (gp.lane == 0) atomicAdd(&A.counters[6], 1ull);
+    gp.sync();
+    o_out = o; score_out = sc;
+    return idx;
+}
+
+// ------------------------------------------------------------------ expand (agent.py:136-145)
+// lane a plays action a on the leaf's game; the seven results are then inserted in action order (first seen wins,
+// free-list order and a mid-expand garbage collection all as in the reference).  Leaves c/o/s of child a in lane a.
+__device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g, int leaf, const uint32_t (&leafrec)[REC_WORDS],
+                                            int &c, int &o, float &s, int &status) {
+    uint32_t mine[REC_WORDS];
+    {
+        Game gm;
+        unpack(gm, leafrec);
+        play(gm, gp.lane < 7 ? gp.lane : 0);
+        pack(gm, mine);
+    }
+    c = 0; o = 0; s = 0.f;
+    for (int a = 0; a < N_ACTIONS; ++a) {
+        uint32_t w[REC_WORDS];
+#pragma unroll
+        for (int q = 0; q < REC_WORDS; ++q) w[q] = gp.bcast(mine[q], a);
+        int oo; float ss;
+        int idx = new_node(A, gp, g, w, oo, ss, status);
+        if (gp.lane == a) { c = idx; o = oo; s = ss; }
+        // agent.py:145 writes child[i] as soon as new_node returns, so a collection triggered by a later
+        // sibling already sees this child as reachable
+        if (gp.lane == a) {
+            int32_t *r = A.row + node_at(A, g, leaf) * ROW_WORDS;
+            r[a] = idx; r[8 + a] = oo; r[16 + a] = __float_as_int(ss);
+        }
+        gp.sync();
+        if (status != ST_OK) break;
+    }
+    if (gp.lane == 0) atomicAdd(&A.counters[1], 1ull);
+}
+
+// ------------------------------------------------------------------ backup (core.h:226-260), one thread
+template <typename Acc>
+__device__ __forceinline__ void backup_trace(const Acc &acc, int D, double v, double var, double gamma) {
+    for (int i = D - 1; i >= 0; --i) {
+        int idx = acc.get_trace(i);
+        int o; float sc;
+        acc.meta(idx, o, sc);
+        int4 st = acc.stat(o);
+        welford_level(st, v, var, sc, gamma);
+        acc.set_stat(o, st);
+    }
+}
+
+// core.h:262-301 (the "mixture" update; not on the live path — ValueSimLP.py:29 passes mixture=False — kept for the
+// single-call twin of backup_trace_obs_LP)
+template <typename Acc>
+__device__ __forceinline__ void backup_trace_mixture(const Acc &acc, int D, double v, double var, double gamma) {
+    for (int i = D - 1; i >= 0; --i) {
+        int idx = acc.get_trace(i);
+        int o; float sc;
+        acc.meta(idx, o, sc);
+        int4 st = acc.stat(o);
+        v = __dsub_rn(v, (double)sc);
+        int n = st.x + 1;
+        float val = __int_as_float(st.y), s2 = __int_as_float(st.z);
+        double v_sq_diff = __dsub_rn(__dmul_rn(v, v), (double)__fmul_rn(val, val));
+        double v_tmp = (double)val;
+        double delta = __ddiv_rn(__dsub_rn(v, (double)val), (double)n);
+        val = (float)__dadd_rn((double)val, delta);
+        double var_diff = __dsub_rn(var, (double)s2);
+        double upd = __dsub_rn(__ddiv_rn(__dadd_rn(var_diff, v_sq_diff), (double)n), __dmul_rn(delta, __dadd_rn(v_tmp, (double)val)));
+        s2 = (float)__dadd_rn((double)s2, upd);
+        st.x = n; st.y = __float_as_int(val); st.z = __float_as_int(s2);
+        acc.set_stat(o, st);
+        v = __dadd_rn(__dmul_rn(gamma, v), (double)sc);
+        var = __dmul_rn(var, __dmul_rn(gamma, gamma));
+    }
+}
+
+// core.h:303-381 leaf-parallel initialise + (averaged | per-child) backup, one thread.
+//   c_nodes/c_obs: the unique children of the leaf (core.h:111-144 order); ev/evar: evaluator outputs per child;
+//   child_end[i]: the `end` flag the reference tests for child i (the Python path passes the never-written
+//   node array => all false; agent.cpp:538 tests the observation's flag).
+template <typename Acc>
+__device__ __forceinline__ void lp_backup(const Acc &acc, int D, int k, const int *c_obs, const float *c_score,
+                                          const float *ev, const float *evar, const bool *child_end, double gamma,
+                                          bool mixture, bool averaged, bool var_gamma2, float leaf_score) {
+    if (k > 0) {
+        double v_tmp = 0.0, var_tmp = 0.0;
+        for (int i = 0; i < k; ++i) {
+            int4 st = acc.stat(c_obs[i]);
+            if (st.x == 0) {                                               // core.h:344-353
+                st.x = 1;
+                if (child_end[i]) { st.y = __float_as_int(0.f); st.z = __float_as_int(0.f); }
+                else { st.y = __float_as_int(ev[i]); st.z = __float_as_int(evar[i]); }
+                acc.set_stat(c_obs[i], st);
+            }
+            float val = __int_as_float(st.y), s2 = __int_as_float(st.z);
+            if (averaged) {                                                // core.h:354-356
+                v_tmp = __dadd_rn(v_tmp, __dadd_rn((double)c_score[i], __dmul_rn(gamma, (double)val)));
+                var_tmp = __dadd_rn(var_tmp, (double)s2);
+            } else {                                                       // core.h:357-361 (value + gamma*score, as written)
+                double bv = __dadd_rn((double)val, __dmul_rn(gamma, (double)c_score[i]));
+                double bvar = __dmul_rn(__dmul_rn(gamma, gamma), (double)s2);
+                if (mixture) backup_trace_mixture(acc, D, bv, bvar, gamma);
+                else backup_trace(acc, D, bv, bvar, gamma);
+            }
+        }
+        if (averaged) {
+            v_tmp = __ddiv_rn(v_tmp, (double)k);                           // core.h:364
+            if (var_gamma2) var_tmp = __dmul_rn(var_tmp, __ddiv_rn(__dmul_rn(gamma, gamma), (double)k));   // core.h:365
+            else {                                                         // agent.cpp:557-562: /k, then float arguments
+                var_tmp = __ddiv_rn(var_tmp, (double)k);
+                v_tmp = (double)(float)v_tmp; var_tmp = (double)(float)var_tmp;
+            }
+            if (mixture) backup_trace_mixture(acc, D, v_tmp, var_tmp, gamma);
+            else backup_trace(acc, D, v_tmp, var_tmp, gamma);
+        }
+    } else {                                                               // core.h:368-371 terminal leaf
+        if (mixture) backup_trace_mixture(acc, D, (double)leaf_score, 0.0, gamma);
+        else backup_trace(acc, D, (double)leaf_score, 0.0, gamma);
+    }
+}
+
+// Scalar form of core.h:111-144 for one thread (backup side): fills c_obs / c_score(rep) / first-slot list.
+template <typename Acc>
+__device__ __forceinline__ int unique_scalar(const Acc &acc, int idx, int *c_nodes, int *c_obs, float *c_score, int *slot) {
+    int k = 0;
+    for (int a = 0; a < 7; ++a) {
+        int c, o; float s;
+        acc.children(idx, a, c, o, s);
+        if (c == 0) continue;
+        int j = 0;
+        while (j < k && c_obs[j] != o) ++j;
+        if (j == k) { c_nodes[k] = c; c_obs[k] = o; c_score[k] = s; slot[k] = a; ++k; }
+        else if (s > c_score[j]) { c_nodes[j] = c; c_score[j] = s; }
+    }
+    return k;
+}
+
+}  // namespace b200

@@ -1,0 +1,146 @@
+"""BatchedEngine — N independent game trees searched in lock-step on one B200.
+
+Host-side mirror of the reference's TreeAgent loop (agents/agent.py:147-151 play(), :296-301 update_root(),
+:153-185 compute_stats/get_action) for a batch of games; the compute is entirely in libb200_tetris_mcts.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class BatchedEngine:
+    def __init__(self, n_games, max_nodes=8192, mode="lp", gamma=None, low=None, eval_kind="net", weights=None,
+                 env_args=((20, 10), 1, 0, 0), seed=123, device=0, lp_end_from_obs=False, lp_var_gamma2=True,
+                 stale_pop=True, rollout_variance=1e3, trace_max=128):
+        mode_id = {"lp": L.MODE_LP, "single": L.MODE_SINGLE, "vanilla": L.MODE_VANILLA}[mode] if isinstance(mode, str) else int(mode)
+        eval_id = {"synthetic": L.EVAL_SYNTHETIC, "net": L.EVAL_NET, "net_tc": L.EVAL_NET_TC}[eval_kind] if isinstance(eval_kind, str) else int(eval_kind)
+        if tuple(env_args[0]) != (20, 10):
+            raise ValueError("only 20x10 boards (SPEC_PYTETRIS.md §1)")
+        cfg = L.Config()
+        cfg.n_games, cfg.max_nodes, cfg.mode = int(n_games), int(max_nodes), mode_id
+        # reference defaults: ValueSim.py:14 gamma=0.999, ValueSimLP.py:27 low=1; Vanilla.py:9 gamma=0.99, :27 low=5
+        cfg.gamma = float(gamma if gamma is not None else (0.99 if mode_id == L.MODE_VANILLA else 0.999))
+        cfg.low = int(low if low is not None else (5 if mode_id == L.MODE_VANILLA else 1))
+        cfg.lp_end_from_obs, cfg.lp_var_gamma2, cfg.stale_pop = int(lp_end_from_obs), int(lp_var_gamma2), int(stale_pop)
+        cfg.eval_kind, cfg.trace_max = eval_id, int(trace_max)
+        cfg.actions_per_drop, cfg.scoring, cfg.randomizer = int(env_args[1]), int(env_args[2]), int(env_args[3])
+        cfg.device, cfg.seed, cfg.rollout_variance = int(device), int(seed) & 0xffffffff, float(rollout_variance)
+        self.cfg = cfg
+        self.n_games, self.max_nodes, self.mode, self.eval_kind = int(n_games), int(max_nodes), mode_id, eval_id
+        self.h = L.P()
+        L.check(L.lib().b200_engine_create(C.byref(cfg), C.byref(self.h)))
+        if weights is not None:
+            self.load_weights(weights)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "h", None):
+            L.lib().b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights (model/model.py:163-174 Model.load)
+    def load_weights(self, weights):
+        w = np.ascontiguousarray(weights, np.float32).ravel()
+        if w.size != L.N_WEIGHTS:
+            raise ValueError("expected %d floats (state_dict order), got %d" % (L.N_WEIGHTS, w.size))
+        L.check(L.lib().b200_load_weights(self.h, L.ptr(w)))
+
+    # ------------------------------------------------------------------ games
+    def set_games(self, recs):
+        recs = np.ascontiguousarray(recs, np.uint32).reshape(self.n_games, L.REC_WORDS)
+        L.check(L.lib().b200_set_games(self.h, L.ptr(recs)))
+
+    def get_games(self):
+        recs = np.zeros((self.n_games, L.REC_WORDS), np.uint32)
+        L.check(L.lib().b200_get_games(self.h, L.ptr(recs)))
+        return recs
+
+    def update_root(self, auto_reset=False):
+        L.check(L.lib().b200_update_root(self.h, int(auto_reset)))
+
+    def run_sims(self, sims):
+        L.check(L.lib().b200_run_sims(self.h, int(sims)))
+
+    def get_stats(self):
+        stats = np.zeros((self.n_games, 3, L.N_ACTIONS), np.float32)
+        action = np.zeros(self.n_games, np.int32)
+        L.check(L.lib().b200_get_stats(self.h, L.ptr(stats), L.ptr(action)))
+        return stats, action
+
+    def env_step(self, actions=None):
+        a = None if actions is None else np.ascontiguousarray(actions, np.int32)
+        L.check(L.lib().b200_env_step(self.h, L.ptr(a)))
+
+    def play_move(self, sims, auto_reset=True, want_stats=True):
+        """One move of play.py:118-177 for every game. Returns (actions, stats)."""
+        actions = np.zeros(self.n_games, np.int32)
+        stats = np.zeros((self.n_games, 3, L.N_ACTIONS), np.float32) if want_stats else None
+        L.check(L.lib().b200_play_move(self.h, int(sims), int(auto_reset), L.ptr(actions), L.ptr(stats)))
+        return actions, stats
+
+    def sync(self):
+        L.check(L.lib().b200_sync(self.h))
+
+    def status(self):
+        st = np.zeros(self.n_games, np.int32)
+        L.check(L.lib().b200_status(self.h, L.ptr(st)))
+        return st
+
+    COUNTER_NAMES = ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "rollout_steps", "new_nodes", "_7",
+                     "games_finished", "score_sum", "lines_sum")
+
+    def counters(self):
+        c = np.zeros(16, np.uint64)
+        L.check(L.lib().b200_counters(self.h, L.ptr(c)))
+        return {n: int(c[i]) for i, n in enumerate(self.COUNTER_NAMES) if not n.startswith("_")}
+
+    PHASES = ("select_expand", "conv", "fc", "backup", "rollout", "synthetic", "misc", "_")
+
+    def set_timing(self, on=True):
+        L.check(L.lib().b200_set_timing(self.h, int(on)))
+
+    def phase_ms(self):
+        ms = np.zeros(8, np.float32)
+        n = np.zeros(8, np.uint64)
+        L.check(L.lib().b200_phase_ms(self.h, L.ptr(ms), L.ptr(n)))
+        return {p: (float(ms[i]), int(n[i])) for i, p in enumerate(self.PHASES) if not p.startswith("_")}
+
+    # ------------------------------------------------------------------ parity / introspection
+    def export_game(self, game):
+        """The arena of one game in the reference's array layout (agents/agent.py:58-88)."""
+        M = self.max_nodes
+        d = dict(child=np.zeros((M, 7), np.int32), score=np.zeros(M, np.float32), episode=np.zeros(M, np.int32),
+                 n2o=np.zeros(M, np.int32), visit=np.zeros(M, np.int32), value=np.zeros(M, np.float32),
+                 variance=np.zeros(M, np.float32), obs_end=np.zeros(M, np.uint8),
+                 game=np.zeros((M, L.REC_WORDS), np.uint32), obs_key=np.zeros((M, L.KEY_WORDS), np.uint32))
+        root = np.zeros(1, np.int32)
+        tr = np.zeros(int(self.cfg.trace_max) or 128, np.int32)
+        tl = np.zeros(1, np.int32)
+        L.check(L.lib().b200_export_game(self.h, int(game), L.ptr(d["child"]), L.ptr(d["score"]), L.ptr(d["episode"]),
+                                         L.ptr(d["n2o"]), L.ptr(d["visit"]), L.ptr(d["value"]), L.ptr(d["variance"]),
+                                         L.ptr(d["obs_end"]), L.ptr(d["game"]), L.ptr(d["obs_key"]), L.ptr(root),
+                                         L.ptr(tr), L.ptr(tl)))
+        d["root"] = int(root[0])
+        d["last_trace"] = tr[:int(tl[0])].copy()
+        return d
+
+    def valuenet(self, states):
+        """Model_VV.inference (model/model_vv.py:210-217): states (k,1,20,10) or (k,20,10) in {-1,0,1} -> (v, var)."""
+        s = np.ascontiguousarray(states, np.int8).reshape(-1, 200)
+        v = np.zeros(len(s), np.float32)
+        var = np.zeros(len(s), np.float32)
+        L.check(L.lib().b200_valuenet_forward(self.h, L.ptr(s), len(s), L.ptr(v), L.ptr(var)))
+        return v, var
+
+    def collect_samples_into(self, dev_ptr, capacity, min_visits):
+        """ValueSim.store_nodes-style samples (agents/ValueSim.py:122-159) written to a DEVICE buffer of 212-byte rows."""
+        cnt = np.zeros(1, np.int32)
+        L.check(L.lib().b200_collect_samples_dev(self.h, int(min_visits), C.c_void_p(int(dev_ptr)), int(capacity), L.ptr(cnt)))
+        return int(cnt[0])
