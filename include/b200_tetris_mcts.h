@@ -46,8 +46,10 @@ typedef struct {
     int32_t lp_end_from_obs;    /* 0: ValueSimLP.py:25 behaviour; 1: agent.cpp:538 */
     int32_t lp_var_gamma2;      /* 1: core.h:365; 0: agent.cpp:558 */
     int32_t stale_pop;          /* 1: reproduce agents/agent.py:229-232 literally */
+    int32_t overflow_reset;     /* 0: arena full after GC is an error (reference: IndexError agent.py:99 / UB agent.cpp:227-231);
+                                   1: drop that game's tree and re-root it at the live game (counter 7 counts these) */
     int32_t eval_kind;          /* B200_EVAL_* */
-    int32_t trace_max;          /* longest root-to-leaf path stored (0 -> 128) */
+    int32_t trace_max;          /* longest root-to-leaf path stored (0 -> 512) */
     int32_t actions_per_drop, scoring, randomizer;   /* play.py:75 env_args */
     int32_t device;             /* CUDA device ordinal */
     uint32_t seed;              /* search RNG stream base (replaces libc rand(), core.h:62,76, and random.randint, Vanilla.py:52) */
@@ -84,8 +86,10 @@ int b200_play_move(b200_engine *e, int sims, int auto_reset, int32_t *actions_ou
 
 int b200_status(b200_engine *e, int32_t *status);            /* per-game 0 ok / B200_ERR_ARENA_FULL / B200_ERR_TRACE_FULL */
 int b200_counters(b200_engine *e, uint64_t *out16);          /* 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels
-                                                                5 rollout steps 6 new nodes 8 games finished 9 score sum 10 lines sum */
+                                                                5 rollout steps 6 new nodes 7 tree resets 8 games finished 9 score sum 10 lines sum */
 int b200_sync(b200_engine *e);
+int b200_timer_start(b200_engine *e);                        /* CUDA-event stopwatch on the engine's stream (sync, then record) */
+int b200_timer_stop(b200_engine *e, float *ms);              /* record, wait, elapsed milliseconds since b200_timer_start */
 int b200_set_timing(b200_engine *e, int on);                 /* CUDA-event timing of each phase on the engine's stream */
 int b200_phase_ms(b200_engine *e, float *ms8, uint64_t *launches8);   /* 0 select+expand 1 conv 2 fc 3 backup 4 rollout 5 synth 6 stats/step/root */
 

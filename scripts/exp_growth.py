@@ -1,0 +1,25 @@
+"""Arena growth + first timings (development aid)."""
+import sys, time
+import numpy as np
+sys.path.insert(0, '.')
+from tetris_mcts_b200 import pyTetris as PT
+from tetris_mcts_b200.engine import BatchedEngine
+from tetris_mcts_b200.model.model_vv import init_weights
+G, M, sims = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+moves = int(sys.argv[4]); ev = sys.argv[5] if len(sys.argv) > 5 else 'net'
+eng = BatchedEngine(G, max_nodes=M, mode='lp', eval_kind=ev, weights=init_weights(0), overflow_reset=True)
+eng.set_games(PT.new_games(G, (1, 0, 0), np.arange(123, 123 + G, dtype=np.uint32)))
+eng.set_timing(True)
+prev = eng.counters()
+for mv in range(moves):
+    t = time.time()
+    try:
+        eng.play_move(sims, True, False)
+    except Exception as e:
+        print('move', mv, 'ERR', e); break
+    dt = time.time() - t
+    c = eng.counters()
+    d = {k: c[k] - prev[k] for k in c}; prev = c
+    print('move %2d %.3fs sims/s %.3g new_nodes/game %.0f evals/sim %.2f D %.2f gcs %d resets %d finished %d' % (
+        mv, dt, G * sims / dt, d['new_nodes'] / G, d['eval_requests'] / max(d['sims'], 1), d['trace_levels'] / max(d['sims'], 1), d['gcs'], d['tree_resets'], c['games_finished']), flush=True)
+print({k: (round(v[0], 2), v[1]) for k, v in eng.phase_ms().items()})

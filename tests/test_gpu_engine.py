@@ -71,7 +71,7 @@ def test_lp_synthetic_exact(gpu_lib, oracle):
 
 def test_lp_with_garbage_collection(gpu_lib, oracle):
     """Small arenas force remove_nodes (agents/agent.py:206-257) in the middle of expansions, several times per game."""
-    c = run_pair(oracle, "lp", n=12, M=2500, sims=40, moves=45)
+    c = run_pair(oracle, "lp", n=12, M=1500, sims=12, moves=100)
     assert c["gcs"] >= 12
 
 
@@ -98,7 +98,7 @@ def test_vanilla_rollouts_exact(gpu_lib, oracle):
 
 
 def test_no_stale_pop_variant(gpu_lib, oracle):
-    run_pair(oracle, "lp", n=8, M=2500, sims=40, moves=40, engine_kw=dict(stale_pop=False), agent_kw=dict(stale_pop=0))
+    run_pair(oracle, "lp", n=8, M=1500, sims=12, moves=100, engine_kw=dict(stale_pop=False), agent_kw=dict(stale_pop=0))
 
 
 def test_real_network_search_is_exact_given_the_same_evaluator(gpu_lib, oracle):

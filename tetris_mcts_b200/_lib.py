@@ -26,7 +26,7 @@ class B200Error(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("n_games", C.c_int32), ("max_nodes", C.c_int32), ("mode", C.c_int32), ("low", C.c_int32),
-                ("lp_end_from_obs", C.c_int32), ("lp_var_gamma2", C.c_int32), ("stale_pop", C.c_int32),
+                ("lp_end_from_obs", C.c_int32), ("lp_var_gamma2", C.c_int32), ("stale_pop", C.c_int32), ("overflow_reset", C.c_int32),
                 ("eval_kind", C.c_int32), ("trace_max", C.c_int32), ("actions_per_drop", C.c_int32),
                 ("scoring", C.c_int32), ("randomizer", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint32),
                 ("gamma", C.c_double), ("rollout_variance", C.c_double)]
@@ -59,6 +59,8 @@ def lib():
         L.b200_counters.argtypes = [P, P]
         L.b200_sync.argtypes = [P]
         L.b200_set_timing.argtypes = [P, C.c_int]
+        L.b200_timer_start.argtypes = [P]
+        L.b200_timer_stop.argtypes = [P, P]
         L.b200_phase_ms.argtypes = [P, P, P]
         L.b200_export_game.argtypes = [P, C.c_int] + [P] * 13
         L.b200_valuenet_forward.argtypes = [P, P, C.c_int, P, P]

@@ -56,6 +56,7 @@ struct b200_engine {
     std::vector<cudaEvent_t> ev; size_t ev_used = 0;
     std::vector<int> ev_phase;
     float phase_ms[PH_N] = {0}; uint64_t phase_launches[PH_N] = {0};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
     // sampling
     uint8_t *d_samples = nullptr; int sample_cap = 0; int32_t *d_sample_count = nullptr;
 };
@@ -143,9 +144,9 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     memset(&A, 0, sizeof(A));
     A.G = cfg->n_games; A.M = cfg->max_nodes;
     int H = 16; while (H < 2 * A.M) H <<= 1;
-    A.H = H; A.trace_max = cfg->trace_max > 0 ? cfg->trace_max : 128;
+    A.H = H; A.trace_max = cfg->trace_max > 0 ? cfg->trace_max : 512;
     A.mode = cfg->mode; A.low = cfg->low; A.lp_end_from_obs = cfg->lp_end_from_obs; A.lp_var_gamma2 = cfg->lp_var_gamma2;
-    A.stale_pop = cfg->stale_pop; A.eval_kind = cfg->eval_kind; A.gamma = cfg->gamma; A.rollout_variance = cfg->rollout_variance;
+    A.stale_pop = cfg->stale_pop; A.eval_kind = cfg->eval_kind; A.overflow_reset = cfg->overflow_reset; A.gamma = cfg->gamma; A.rollout_variance = cfg->rollout_variance;
     size_t GM = (size_t)A.G * A.M, G = (size_t)A.G;
     int rc = 0;
     rc |= dalloc(e, &A.row, GM * ROW_WORDS);
@@ -196,6 +197,7 @@ extern "C" int b200_engine_destroy(b200_engine *e) {
 #endif
     for (void *p : e->allocs) cudaFree(p);
     for (auto &ev : e->ev) cudaEventDestroy(ev);
+    if (e->t0) { cudaEventDestroy(e->t0); cudaEventDestroy(e->t1); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return B200_OK;
@@ -290,7 +292,7 @@ static int check_status(b200_engine *e) {   // cheap: max over the status array 
     CK(cudaMemcpyAsync(st.data(), e->A.status, st.size() * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     for (int g = 0; g < e->A.G; ++g)
-        if (st[g] != ST_OK) {
+        if (st[g] != ST_OK && !(st[g] == ST_ARENA_FULL && e->A.overflow_reset)) {
             int code = st[g] == ST_ARENA_FULL ? B200_ERR_ARENA_FULL : B200_ERR_TRACE_FULL;
             return fail(code, "game " + std::to_string(g) + (st[g] == ST_ARENA_FULL ? ": arena full after garbage collection (raise max_nodes)" : ": trace longer than trace_max"));
         }
@@ -417,6 +419,24 @@ extern "C" int b200_sync(b200_engine *e) {
     if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+// device-side stopwatch on the engine's own stream (torch.cuda.Event only sees torch's current stream)
+extern "C" int b200_timer_start(b200_engine *e) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->t0) { CK(cudaEventCreate(&e->t0)); CK(cudaEventCreate(&e->t1)); }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventRecord(e->t0, e->stream));
+    return B200_OK;
+}
+extern "C" int b200_timer_stop(b200_engine *e, float *ms) {
+    if (!e || !ms || !e->t0) return fail(B200_ERR_BAD_ARG, "timer not started");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventRecord(e->t1, e->stream));
+    CK(cudaEventSynchronize(e->t1));
+    CK(cudaEventElapsedTime(ms, e->t0, e->t1));
     return B200_OK;
 }
 

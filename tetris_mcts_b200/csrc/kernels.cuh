@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, un
     int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
     if (g >= A.G) return;
     int status = A.status[g];
+    if (status == ST_ARENA_FULL && A.overflow_reset) reset_tree(A, gp, g, status);   // re-roots at the live game
     if (status != ST_OK) return;
     uint32_t w[REC_WORDS];
     load_rec(A.cur + (size_t)g * REC_WORDS, w);
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(TPB) k_select_expand(Arena A) {
     int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
     if (g >= A.G) return;
     int status = A.status[g];
+    if (status == ST_ARENA_FULL && A.overflow_reset) reset_tree(A, gp, g, status);
     if (status != ST_OK) return;
     ArenaAcc acc{A, g};
     int D = 0;
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(TPB) k_select_expand(Arena A) {
     unsigned wm = __ballot_sync(0xffffffffu, mine);
     int lane32 = threadIdx.x & 31;
     int base = 0;
-    if (lane32 == 0 && wm) base = atomicAdd(A.n_req, __popc(wm));
+    if (lane32 == 0 && wm) { base = atomicAdd(A.n_req, __popc(wm)); atomicAdd(&A.counters[2], (unsigned long long)__popc(wm)); }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (mine) A.req[base + __popc(wm & ((1u << lane32) - 1u))] = make_uint2((uint32_t)g, (uint32_t)my_o | ((uint32_t)gp.lane << 28));
     if (gp.lane == 0) { atomicAdd(&A.counters[0], 1ull); atomicAdd(&A.counters[4], (unsigned long long)D); }

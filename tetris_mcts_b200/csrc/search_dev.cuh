@@ -41,7 +41,7 @@ enum : int { MODE_LP = 0, MODE_SINGLE = 1, MODE_VANILLA = 2 };
 //   nfree/ofree [G][M]  i32      free lists, popped from the back (agents/agent.py:72,99)
 struct Arena {
     int G, M, H, trace_max;
-    int mode, low, lp_end_from_obs, lp_var_gamma2, stale_pop, eval_kind;
+    int mode, low, lp_end_from_obs, lp_var_gamma2, stale_pop, eval_kind, overflow_reset;
     double gamma, rollout_variance;
     int32_t *row; int4 *stat; uint32_t *rec; uint32_t *key;
     uint2 *ntab, *otab;
@@ -357,7 +357,8 @@ __device__ __noinline__ void collect_garbage(const Arena &A, const Grp &gp, int 
     for (int j = 0; j < nn; ++j) {
         int i = nfree[j];
         int4 *r = reinterpret_cast<int4 *>(rowb + (size_t)i * ROW_WORDS);
-        if (gp.lane < 6) r[gp.lane] = make_int4(0, 0, 0, 0);
+        // agent.py:234-235 zeroes self.arrays (child, episode, score, ...) but node_to_obs is not among them: keep o[7]
+        if (gp.lane < 6) r[gp.lane] = make_int4(0, 0, 0, gp.lane == 3 ? r[3].w : 0);
     }
     int4 *statb = A.stat + (size_t)g * M;
     uint32_t *keyb = A.key + (size_t)g * M * KEY_WORDS;
@@ -437,6 +438,37 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
     gp.sync();
     o_out = o; score_out = sc;
     return idx;
+}
+
+// ------------------------------------------------------------------ overflow policy (beyond the reference)
+// When the reachable set alone fills the arena the reference dies (IndexError at agent.py:99 / UB at agent.cpp:227-231).
+// With overflow_reset the tree of that game is dropped and re-rooted at the live game: statistics restart as at the
+// first move of an episode.  Never taken when the arena is sized like the reference's (tests run with it off).
+__device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, int &status) {
+    const int M = A.M, H = A.H;
+    int4 *rows = reinterpret_cast<int4 *>(A.row + (size_t)g * M * ROW_WORDS);
+    for (int i = gp.lane; i < M * 6; i += 8) rows[i] = make_int4(0, 0, 0, 0);
+    int4 *statb = A.stat + (size_t)g * M;
+    for (int i = gp.lane; i < M; i += 8) statb[i] = make_int4(0, 0, 0, 0);
+    uint4 *keyb = reinterpret_cast<uint4 *>(A.key + (size_t)g * M * KEY_WORDS);
+    for (int i = gp.lane; i < M * 3; i += 8) keyb[i] = make_uint4(0, 0, 0, 0);
+    uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
+    for (int i = gp.lane; i < H; i += 8) { ntab[i] = make_uint2(0, 0); otab[i] = make_uint2(0, 0); }
+    int32_t *nfree = A.nfree + (size_t)g * M, *ofree = A.ofree + (size_t)g * M;
+    for (int i = gp.lane; i < M - 1; i += 8) { nfree[i] = i + 1; ofree[i] = i + 1; }
+    if (gp.lane == 0) { A.n_nfree[g] = M - 1; A.n_ofree[g] = M - 1; atomicAdd(&A.counters[7], 1ull); }
+    gp.sync();
+    status = ST_OK;
+    uint32_t w[REC_WORDS];
+#pragma unroll
+    for (int q = 0; q < REC_WORDS / 4; ++q) {
+        uint4 v = *reinterpret_cast<const uint4 *>(A.cur + (size_t)g * REC_WORDS + q * 4);
+        w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
+    }
+    int o; float sc;
+    int idx = new_node(A, gp, g, w, o, sc, status);
+    if (gp.lane == 0) { A.root[g] = idx; A.status[g] = status; }
+    gp.sync();
 }
 
 // ------------------------------------------------------------------ expand (agent.py:136-145)

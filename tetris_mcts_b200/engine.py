@@ -12,7 +12,7 @@ from . import _lib as L
 class BatchedEngine:
     def __init__(self, n_games, max_nodes=8192, mode="lp", gamma=None, low=None, eval_kind="net", weights=None,
                  env_args=((20, 10), 1, 0, 0), seed=123, device=0, lp_end_from_obs=False, lp_var_gamma2=True,
-                 stale_pop=True, rollout_variance=1e3, trace_max=128):
+                 stale_pop=True, rollout_variance=1e3, trace_max=512, overflow_reset=False):
         mode_id = {"lp": L.MODE_LP, "single": L.MODE_SINGLE, "vanilla": L.MODE_VANILLA}[mode] if isinstance(mode, str) else int(mode)
         eval_id = {"synthetic": L.EVAL_SYNTHETIC, "net": L.EVAL_NET, "net_tc": L.EVAL_NET_TC}[eval_kind] if isinstance(eval_kind, str) else int(eval_kind)
         if tuple(env_args[0]) != (20, 10):
@@ -23,7 +23,7 @@ class BatchedEngine:
         cfg.gamma = float(gamma if gamma is not None else (0.99 if mode_id == L.MODE_VANILLA else 0.999))
         cfg.low = int(low if low is not None else (5 if mode_id == L.MODE_VANILLA else 1))
         cfg.lp_end_from_obs, cfg.lp_var_gamma2, cfg.stale_pop = int(lp_end_from_obs), int(lp_var_gamma2), int(stale_pop)
-        cfg.eval_kind, cfg.trace_max = eval_id, int(trace_max)
+        cfg.eval_kind, cfg.trace_max, cfg.overflow_reset = eval_id, int(trace_max), int(overflow_reset)
         cfg.actions_per_drop, cfg.scoring, cfg.randomizer = int(env_args[1]), int(env_args[2]), int(env_args[3])
         cfg.device, cfg.seed, cfg.rollout_variance = int(device), int(seed) & 0xffffffff, float(rollout_variance)
         self.cfg = cfg
@@ -93,7 +93,7 @@ class BatchedEngine:
         L.check(L.lib().b200_status(self.h, L.ptr(st)))
         return st
 
-    COUNTER_NAMES = ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "rollout_steps", "new_nodes", "_7",
+    COUNTER_NAMES = ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "rollout_steps", "new_nodes", "tree_resets",
                      "games_finished", "score_sum", "lines_sum")
 
     def counters(self):
@@ -102,6 +102,14 @@ class BatchedEngine:
         return {n: int(c[i]) for i, n in enumerate(self.COUNTER_NAMES) if not n.startswith("_")}
 
     PHASES = ("select_expand", "conv", "fc", "backup", "rollout", "synthetic", "misc", "_")
+
+    def timer_start(self):
+        L.check(L.lib().b200_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = np.zeros(1, np.float32)
+        L.check(L.lib().b200_timer_stop(self.h, L.ptr(ms)))
+        return float(ms[0])
 
     def set_timing(self, on=True):
         L.check(L.lib().b200_set_timing(self.h, int(on)))
@@ -121,7 +129,7 @@ class BatchedEngine:
                  variance=np.zeros(M, np.float32), obs_end=np.zeros(M, np.uint8),
                  game=np.zeros((M, L.REC_WORDS), np.uint32), obs_key=np.zeros((M, L.KEY_WORDS), np.uint32))
         root = np.zeros(1, np.int32)
-        tr = np.zeros(int(self.cfg.trace_max) or 128, np.int32)
+        tr = np.zeros(int(self.cfg.trace_max) or 512, np.int32)
         tl = np.zeros(1, np.int32)
         L.check(L.lib().b200_export_game(self.h, int(game), L.ptr(d["child"]), L.ptr(d["score"]), L.ptr(d["episode"]),
                                          L.ptr(d["n2o"]), L.ptr(d["visit"]), L.ptr(d["value"]), L.ptr(d["variance"]),
