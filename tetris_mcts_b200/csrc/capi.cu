@@ -34,7 +34,7 @@ extern "C" int b200_device_count(void) {
     return n;
 }
 
-enum { PH_SELECT = 0, PH_CONV, PH_FC, PH_BACKUP, PH_ROLLOUT, PH_SYNTH, PH_MISC, PH_N = 8 };
+enum { PH_SELECT = 0, PH_CONV, PH_FC, PH_BACKUP, PH_ROLLOUT, PH_SYNTH, PH_MISC, PH_GC, PH_N = 8 };
 
 struct b200_engine {
     b200_config cfg;
@@ -129,7 +129,8 @@ static void flush_timing(b200_engine *e) {
 
 extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     if (!cfg || !out) return fail(B200_ERR_BAD_ARG, "null argument");
-    if (cfg->n_games < 1 || cfg->max_nodes < 16 || cfg->max_nodes >= (1 << 28)) return fail(B200_ERR_BAD_ARG, "n_games >= 1, 16 <= max_nodes < 2^28");
+    if (cfg->n_games < 1 || cfg->max_nodes < 16 || cfg->max_nodes >= (1 << 28) || (cfg->max_nodes & 3))
+        return fail(B200_ERR_BAD_ARG, "n_games >= 1, 16 <= max_nodes < 2^28, max_nodes % 4 == 0");
     if (cfg->mode < 0 || cfg->mode > 2) return fail(B200_ERR_BAD_ARG, "mode");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
@@ -161,7 +162,8 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     rc |= dalloc(e, &A.trace, G * A.trace_max); rc |= dalloc(e, &A.trace_len, G); rc |= dalloc(e, &A.leaf_kind, G);
     rc |= dalloc(e, &A.nmark, GM); rc |= dalloc(e, &A.omark, GM); rc |= dalloc(e, &A.gc_queue, GM * 2);
     rc |= dalloc(e, &A.cur, G * REC_WORDS);
-    rc |= dalloc(e, &A.req, G * 8); rc |= dalloc(e, &A.n_req, 1);
+    rc |= dalloc(e, &A.req, G * 8); rc |= dalloc(e, &A.n_req, 2);
+    rc |= dalloc(e, &A.gc_list, G); rc |= dalloc(e, &A.pending, G); rc |= dalloc(e, &A.resume_a, G);
     rc |= dalloc(e, &A.eval_out, G * 8); rc |= dalloc(e, &A.rollout_val, G);
     rc |= dalloc(e, &A.counters, 16);
     rc |= dalloc(e, &e->d_default_rec, REC_WORDS);
@@ -286,6 +288,7 @@ static int launch_net(b200_engine *e, const uint2 *req, const int32_t *n_req, co
 
 // ---------------------------------------------------------------------------------------------------- games / roots
 static inline int blocks_groups(int G) { return (G + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK; }
+static inline int gc_blocks(b200_engine *e) { int b = e->n_sm * 4; return e->A.G < b ? e->A.G : b; }
 
 static int check_status(b200_engine *e) {   // cheap: max over the status array computed on the host after a small copy
     std::vector<int32_t> st(e->A.G);
@@ -304,7 +307,10 @@ extern "C" int b200_update_root(b200_engine *e, int auto_reset) {
     CK(cudaSetDevice(e->cfg.device));
     {
         PhaseTimer t(e, PH_MISC);
-        k_update_root<<<blocks_groups(e->A.G), TPB, 0, e->stream>>>(e->A, auto_reset, e->d_game_stats);
+        CK(cudaMemsetAsync(e->A.n_req + 1, 0, sizeof(int32_t), e->stream));
+        k_update_root<<<blocks_groups(e->A.G), TPB, 0, e->stream>>>(e->A, auto_reset, e->d_game_stats, 0);
+        k_gc<<<gc_blocks(e), GC_THREADS, 0, e->stream>>>(e->A);                 // games whose free list ran dry (usually none)
+        k_update_root<<<blocks_groups(e->A.G), TPB, 0, e->stream>>>(e->A, auto_reset, e->d_game_stats, 1);
     }
     CK(cudaGetLastError());
     return B200_OK;
@@ -336,10 +342,15 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
     const bool need_net = A.mode != MODE_VANILLA && e->cfg.eval_kind != B200_EVAL_SYNTHETIC;
     if (need_net && !e->have_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
     for (int s = 0; s < sims; ++s) {
-        CK(cudaMemsetAsync(A.n_req, 0, sizeof(int32_t), e->stream));
+        CK(cudaMemsetAsync(A.n_req, 0, 2 * sizeof(int32_t), e->stream));
         {
             PhaseTimer t(e, PH_SELECT);
             k_select_expand<<<blocks_groups(G), TPB, 0, e->stream>>>(A);
+        }
+        {   // remove_nodes for the games that ran out of free slots in this step, then the rest of their expansion
+            PhaseTimer t(e, PH_GC);
+            k_gc<<<gc_blocks(e), GC_THREADS, 0, e->stream>>>(A);
+            k_expand_resume<<<blocks_groups(G), TPB, 0, e->stream>>>(A);
         }
         if (A.mode == MODE_VANILLA) {
             PhaseTimer t(e, PH_ROLLOUT);

@@ -81,21 +81,49 @@ __device__ __forceinline__ void reset_game(Game &g) {   // SPEC §4 reset(): kee
     spawn(g);
 }
 
+// ---------------------------------------------------------------- suspension for garbage collection
+// A group that finds its free list empty queues its game for k_gc and records what to redo afterwards.
+__device__ __forceinline__ void suspend_for_gc(const Arena &A, const Grp &gp, int g, int what, int a) {
+    if (gp.lane == 0) {
+        A.pending[g] = what; A.resume_a[g] = a;
+        A.gc_list[atomicAdd(A.n_req + 1, 1)] = g;
+    }
+}
+
+// queue the evaluation requests of one group: lanes whose bit is set in `need` ask for observation my_o, slot = lane
+__device__ __forceinline__ void emit_requests(const Arena &A, const Grp &gp, int g, unsigned need, int my_o) {
+    if (need == 0) return;
+    int base = 0;
+    if (gp.lane == 0) { base = atomicAdd(A.n_req, __popc(need)); atomicAdd(&A.counters[2], (unsigned long long)__popc(need)); }
+    base = gp.bcast(base, 0);
+    if ((need >> gp.lane) & 1u)
+        A.req[base + __popc(need & ((1u << gp.lane) - 1u))] = make_uint2((uint32_t)g, (uint32_t)my_o | ((uint32_t)gp.lane << 28));
+}
+
 // ---------------------------------------------------------------- update_root (agent.py:296-301)
-// auto_reset reproduces play.py:161-177: a finished game is counted, reset and re-rooted.
-__global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, unsigned long long *game_stats) {
+// auto_reset reproduces play.py:161-177: a finished game is counted, reset and re-rooted.  only_pending: second pass
+// after k_gc for the games that had to suspend (the pass is idempotent: see the comments at the two new_node calls).
+__global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, unsigned long long *game_stats, int only_pending) {
     Grp gp;
     int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
     if (g >= A.G) return;
     int status = A.status[g];
-    if (status == ST_ARENA_FULL && A.overflow_reset) reset_tree(A, gp, g, status);   // re-roots at the live game
+    if (only_pending) {
+        if (A.pending[g] != PEND_ROOT) return;
+        gp.sync();
+        if (gp.lane == 0) A.pending[g] = PEND_NONE;
+    } else if (status == ST_ARENA_FULL && A.overflow_reset) {
+        reset_tree(A, gp, g, status);   // re-roots at the live game
+    }
     if (status != ST_OK) return;
+    const bool may_suspend = !only_pending;
     uint32_t w[REC_WORDS];
     load_rec(A.cur + (size_t)g * REC_WORDS, w);
     int o; float s;
-    int idx = new_node(A, gp, g, w, o, s, status);
+    int idx = new_node(A, gp, g, w, o, s, status, may_suspend);
+    if (status == ST_NEED_GC) { suspend_for_gc(A, gp, g, PEND_ROOT, 0); return; }   // nothing was changed yet: redo all
     bool ended = (w[10] >> 21) & 1u;
-    if (gp.lane == 0) { A.root[g] = idx; if (ended) A.episode[g] += 1; }
+    if (gp.lane == 0 && status == ST_OK) { A.root[g] = idx; if (ended) A.episode[g] += 1; }
     gp.sync();
     if (ended && auto_reset && status == ST_OK) {
         Game gm;
@@ -109,10 +137,20 @@ __global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, un
         pack(gm, w);
         if (gp.lane == 0) store_rec(A.cur + (size_t)g * REC_WORDS, w);
         gp.sync();
-        idx = new_node(A, gp, g, w, o, s, status);
-        if (gp.lane == 0) A.root[g] = idx;
+        idx = new_node(A, gp, g, w, o, s, status, may_suspend);
+        // suspended here: the live game is already the fresh one, so the redo pass only re-roots (no second episode++)
+        if (status == ST_NEED_GC) { suspend_for_gc(A, gp, g, PEND_ROOT, 0); return; }
+        if (gp.lane == 0 && status == ST_OK) A.root[g] = idx;
     }
     if (gp.lane == 0 && status != ST_OK) A.status[g] = status;
+}
+
+// After an expansion is complete: which unique children need the network (ValueSimLP.py:55-60 evaluates every unique
+// child; core.h:344 only uses results where visit == 0, so only those boards are queued).
+__device__ __forceinline__ void request_lp_evals(const Arena &A, const Grp &gp, int g, int c, int o, float s) {
+    Uniq u = unique_children(gp, c, o, s);
+    bool ask = u.is_first && A.stat[node_at(A, g, o)].x == 0;
+    emit_requests(A, gp, g, gp.ballot(ask), o);
 }
 
 // ---------------------------------------------------------------- select + expand (ValueSimLP.py:45-57 etc.)
@@ -131,37 +169,200 @@ __global__ void __launch_bounds__(TPB) k_select_expand(Arena A) {
     load_rec(A.rec + node_at(A, g, leaf) * REC_WORDS, w);
     bool ended = (w[10] >> 21) & 1u;
     int kind = ended ? LEAF_TERMINAL : LEAF_EXPANDED;
-    unsigned need = 0;   // lanes that ask for an evaluation
-    int my_o = 0;
     if (!ended) {
-        if (A.mode == MODE_SINGLE) {          // ValueSim.py:83-88 evaluates the leaf itself, before expanding
-            my_o = A.row[node_at(A, g, leaf) * ROW_WORDS + 15];
-            need = 1u << 7;
-        }
-        int c, o; float s;
-        expand_leaf(A, gp, g, leaf, w, c, o, s, status);
-        if (status == ST_OK && A.mode == MODE_LP) {
-            Uniq u = unique_children(gp, c, o, s);
-            // ValueSimLP.py:55-60 evaluates every unique child; core.h:344 only uses results where visit == 0,
-            // so only those boards are sent to the network
-            bool ask = u.is_first && A.stat[node_at(A, g, o)].x == 0;
-            need = gp.ballot(ask);
-            my_o = o;
+        if (A.mode == MODE_SINGLE)            // ValueSim.py:83-88 evaluates the leaf itself, before expanding
+            emit_requests(A, gp, g, 1u << 7, A.row[node_at(A, g, leaf) * ROW_WORDS + 15]);
+        int c, o, a_stop; float s;
+        expand_leaf(A, gp, g, leaf, w, c, o, s, status, 0, true, a_stop);
+        if (status == ST_NEED_GC) {
+            suspend_for_gc(A, gp, g, PEND_EXPAND, a_stop);
+            kind = LEAF_SUSPENDED; status = ST_OK;
+        } else if (status == ST_OK && A.mode == MODE_LP) {
+            request_lp_evals(A, gp, g, c, o, s);
         }
     }
     if (gp.lane == 0) {
         A.trace_len[g] = D; A.leaf_kind[g] = kind;
         if (status != ST_OK) A.status[g] = status;
+        atomicAdd(&A.counters[0], 1ull); atomicAdd(&A.counters[4], (unsigned long long)D);
     }
-    // compact the evaluation requests: one atomic per warp
-    bool mine = status == ST_OK && ((need >> gp.lane) & 1u);
-    unsigned wm = __ballot_sync(0xffffffffu, mine);
-    int lane32 = threadIdx.x & 31;
-    int base = 0;
-    if (lane32 == 0 && wm) { base = atomicAdd(A.n_req, __popc(wm)); atomicAdd(&A.counters[2], (unsigned long long)__popc(wm)); }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (mine) A.req[base + __popc(wm & ((1u << lane32) - 1u))] = make_uint2((uint32_t)g, (uint32_t)my_o | ((uint32_t)gp.lane << 28));
-    if (gp.lane == 0) { atomicAdd(&A.counters[0], 1ull); atomicAdd(&A.counters[4], (unsigned long long)D); }
+}
+
+// continue the expansions that had to wait for k_gc (children resume_a..6), then queue their evaluations
+__global__ void __launch_bounds__(TPB) k_expand_resume(Arena A) {
+    Grp gp;
+    int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
+    if (g >= A.G) return;
+    if (A.pending[g] != PEND_EXPAND) return;
+    gp.sync();
+    if (gp.lane == 0) A.pending[g] = PEND_NONE;
+    int status = A.status[g];
+    if (status != ST_OK) return;                         // k_gc found the arena full: the reference dies here
+    int D = A.trace_len[g];
+    int leaf = A.trace[(size_t)g * A.trace_max + D - 1];
+    uint32_t w[REC_WORDS];
+    load_rec(A.rec + node_at(A, g, leaf) * REC_WORDS, w);
+    int c, o, a_stop; float s;
+    expand_leaf(A, gp, g, leaf, w, c, o, s, status, A.resume_a[g], false, a_stop);
+    if (status == ST_OK) {
+        ArenaAcc acc{A, g};
+        acc.children(leaf, gp.lane, c, o, s);            // children 0..resume_a-1 were linked before the collection
+        if (A.mode == MODE_LP) request_lp_evals(A, gp, g, c, o, s);
+        if (gp.lane == 0) A.leaf_kind[g] = LEAF_EXPANDED;
+    } else if (gp.lane == 0) {
+        A.status[g] = status;
+    }
+}
+
+// ---------------------------------------------------------------- remove_nodes (agent.py:187-257), one CTA per game
+// get_all_childs (core.h:32-50) as a level-synchronous parallel BFS, update_available (agent.py:187-204) as ordered
+// compaction (ascending free lists, popped from the back), reset_arrays (agent.py:227-244) including its pop-by-stale-game
+// behaviour (see stale_pop), then both hash tables are rebuilt from their surviving entries.
+constexpr int GC_THREADS = 256;
+
+__device__ __forceinline__ bool test_and_set_mark(uint8_t *mark, int i) {
+    unsigned *wp = reinterpret_cast<unsigned *>(mark + (i & ~3));
+    unsigned bit = 1u << (8 * (i & 3));
+    return (atomicOr(wp, bit) & bit) == 0u;
+}
+
+__device__ __forceinline__ int block_excl_scan(int flag, int *s_warp, int &total) {   // 256 threads; returns rank of this thread
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    int rank = __popc(m & ((1u << lane) - 1u));
+    __syncthreads();
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < GC_THREADS / 32; ++i) { int v = s_warp[i]; if (i < wid) off += v; tot += v; }
+    total = tot;
+    return off + rank;
+}
+
+__global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
+    __shared__ int s_n[2];
+    __shared__ int s_warp[GC_THREADS / 32];
+    const int n_items = A.n_req[1];
+    const int t = threadIdx.x;
+    const int M = A.M, H = A.H;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int g = A.gc_list[item];
+        uint8_t *nmark = A.nmark + (size_t)g * M, *omark = A.omark + (size_t)g * M;
+        int32_t *q0 = A.gc_queue + (size_t)g * 2 * M, *q1 = q0 + M;
+        int32_t *rowb = A.row + (size_t)g * M * ROW_WORDS;
+        uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
+        const uint32_t *recb = A.rec + (size_t)g * M * REC_WORDS;
+        const int root = A.root[g];
+        __syncthreads();
+        for (int i = t; i < M / 4; i += GC_THREADS) { reinterpret_cast<unsigned *>(nmark)[i] = 0u; reinterpret_cast<unsigned *>(omark)[i] = 0u; }
+        for (int i = (M / 4) * 4 + t; i < M; i += GC_THREADS) { nmark[i] = 0; omark[i] = 0; }
+        __syncthreads();
+        if (t == 0) {                                        // core.h:32-50: the null node 0 is always traversed
+            nmark[0] = 1;
+            int n = 0;
+            if (root != 0) { nmark[root] = 1; q0[n++] = root; }
+            s_n[0] = n; s_n[1] = 0;
+        }
+        __syncthreads();
+        int32_t *cur = q0, *nxt = q1;
+        for (;;) {
+            const int nc = s_n[0];
+            if (nc == 0) break;
+            for (int i = t; i < nc * 7; i += GC_THREADS) {
+                int c = rowb[(size_t)cur[i / 7] * ROW_WORDS + (i % 7)];
+                if (c != 0 && test_and_set_mark(nmark, c)) nxt[atomicAdd(&s_n[1], 1)] = c;
+            }
+            __syncthreads();
+            if (t == 0) { s_n[0] = s_n[1]; s_n[1] = 0; }
+            int32_t *tmp = cur; cur = nxt; nxt = tmp;
+            __syncthreads();
+        }
+        // observations of occupied nodes stay (agent.py:198); n_to_o[i] lives in o[7]
+        for (int i = t; i < M; i += GC_THREADS)
+            if (nmark[i]) omark[rowb[(size_t)i * ROW_WORDS + 15]] = 1;
+        __syncthreads();
+        // ascending complements (agent.py:192,201)
+        int32_t *nfree = A.nfree + (size_t)g * M, *ofree = A.ofree + (size_t)g * M;
+        int nn = 0, no = 0;
+        for (int base = 0; base < M; base += GC_THREADS) {
+            int i = base + t, tot;
+            int fn = i < M && !nmark[i], fo = i < M && !omark[i];
+            int r = block_excl_scan(fn, s_warp, tot);
+            if (fn) nfree[nn + r] = i;
+            nn += tot;
+            r = block_excl_scan(fo, s_warp, tot);
+            if (fo) ofree[no + r] = i;
+            no += tot;
+        }
+        __syncthreads();
+        // reset_arrays: node table.  stale_pop: erase BY THE FREED SLOT'S CURRENT GAME (agent.py:229-232); a slot freed
+        // at an earlier collection still holds its old state, which may equal a live node's: that node loses its entry.
+        if (A.stale_pop) {
+            for (int j = t; j < nn; j += GC_THREADS) {
+                const uint4 *mine = reinterpret_cast<const uint4 *>(recb + (size_t)nfree[j] * REC_WORDS);
+                uint4 m0 = mine[0], m1 = mine[1], m2 = mine[2], m3 = mine[3], m4 = mine[4];
+                uint32_t w[REC_WORDS] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w,
+                                         m3.x, m3.y, m3.z, m3.w, m4.x, m4.y, m4.z, m4.w};
+                uint32_t h = fold32(hash_words(w, REC_WORDS));
+                uint32_t p = h & (uint32_t)(H - 1);
+                for (;;) {
+                    uint2 e = ntab[p];
+                    if (e.y == 0u) break;
+                    if (e.y != 0xffffffffu && e.x == h) {
+                        const uint4 *c = reinterpret_cast<const uint4 *>(recb + (size_t)e.y * REC_WORDS);
+                        uint4 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+                        bool eq = c0.x == m0.x && c0.y == m0.y && c0.z == m0.z && c0.w == m0.w && c1.x == m1.x && c1.y == m1.y &&
+                                  c1.z == m1.z && c1.w == m1.w && c2.x == m2.x && c2.y == m2.y && c2.z == m2.z && c2.w == m2.w &&
+                                  c3.x == m3.x && c3.y == m3.y && c3.z == m3.z && c3.w == m3.w && c4.x == m4.x && c4.y == m4.y &&
+                                  c4.z == m4.z && c4.w == m4.w;
+                        if (eq) { ntab[p].y = 0xffffffffu; break; }
+                    }
+                    p = (p + 1) & (uint32_t)(H - 1);
+                }
+            }
+        } else {
+            for (int p = t; p < H; p += GC_THREADS) { uint32_t y = ntab[p].y; if (y != 0u && y != 0xffffffffu && !nmark[y]) ntab[p].y = 0xffffffffu; }
+        }
+        for (int p = t; p < H; p += GC_THREADS) { uint32_t y = otab[p].y; if (y != 0u && y != 0xffffffffu && !omark[y]) otab[p].y = 0xffffffffu; }
+        __syncthreads();
+        // rebuild both tables from their surviving entries (the BFS queues are free again: 2M ints = M pairs)
+        for (int tb = 0; tb < 2; ++tb) {
+            uint2 *tab = tb ? otab : ntab;
+            uint2 *list = reinterpret_cast<uint2 *>(q0);
+            if (t == 0) s_n[0] = 0;
+            __syncthreads();
+            for (int p = t; p < H; p += GC_THREADS) {
+                uint2 e = tab[p];
+                if (e.y != 0u && e.y != 0xffffffffu) list[atomicAdd(&s_n[0], 1)] = e;
+                tab[p] = make_uint2(0u, 0u);
+            }
+            __syncthreads();
+            const int cnt = s_n[0];
+            for (int j = t; j < cnt; j += GC_THREADS) {      // keys are unique, so the claim order is free
+                uint2 e = list[j];
+                uint32_t p = e.x & (uint32_t)(H - 1);
+                while (atomicCAS(&tab[p].y, 0u, e.y) != 0u) p = (p + 1) & (uint32_t)(H - 1);
+                tab[p].x = e.x;
+            }
+            __syncthreads();
+        }
+        // zero the freed rows (agent.py:234-235; node_to_obs is not in self.arrays: o[7] stays), statistics and keys
+        for (int i = t; i < nn * 6; i += GC_THREADS) {
+            int4 *r = reinterpret_cast<int4 *>(rowb + (size_t)nfree[i / 6] * ROW_WORDS) + (i % 6);
+            *r = make_int4(0, 0, 0, (i % 6) == 3 ? r->w : 0);
+        }
+        int4 *statb = A.stat + (size_t)g * M;
+        uint4 *keyb = reinterpret_cast<uint4 *>(A.key + (size_t)g * M * KEY_WORDS);
+        for (int i = t; i < no; i += GC_THREADS) statb[ofree[i]] = make_int4(0, 0, 0, 0);
+        for (int i = t; i < no * 3; i += GC_THREADS) keyb[(size_t)ofree[i / 3] * 3 + (i % 3)] = make_uint4(0, 0, 0, 0);
+        if (t == 0) {
+            A.n_nfree[g] = nn; A.n_ofree[g] = no;
+            atomicAdd(&A.counters[3], 1ull);
+            if (nn == 0) A.status[g] = ST_ARENA_FULL;        // reference: IndexError at agent.py:99 / UB at agent.cpp:227-231
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------- test evaluator (shared definition with oracle/mcts_oracle.c)

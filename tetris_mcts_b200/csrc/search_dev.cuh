@@ -26,8 +26,9 @@ namespace b200 {
 constexpr int ROW_WORDS = 24;     // child row: c[8] | o[8] | s[8]
 constexpr int ZTABLE_N = 65536;   // z(n) table computed on the host with the reference's libm (special.h:26-33)
 
-enum : int { ST_OK = 0, ST_ARENA_FULL = 1, ST_TRACE_FULL = 2 };
-enum : int { LEAF_TERMINAL = 0, LEAF_EXPANDED = 1 };
+enum : int { ST_OK = 0, ST_ARENA_FULL = 1, ST_TRACE_FULL = 2, ST_NEED_GC = 3 };
+enum : int { LEAF_TERMINAL = 0, LEAF_EXPANDED = 1, LEAF_SUSPENDED = 2 };
+enum : int { PEND_NONE = 0, PEND_EXPAND = 1, PEND_ROOT = 2 };
 enum : int { MODE_LP = 0, MODE_SINGLE = 1, MODE_VANILLA = 2 };
 
 // HBM layout (all arrays are [game][...]; SoA across games, records kept 16-byte aligned):
@@ -51,7 +52,8 @@ struct Arena {
     uint8_t *nmark, *omark; int32_t *gc_queue;
     uint32_t *cur;                 // [G][20] the live game of each tree (the object play.py owns)
     const float *ztable;
-    uint2 *req; int32_t *n_req;    // evaluation requests {game, obs | slot<<28}
+    uint2 *req; int32_t *n_req;    // evaluation requests {game, obs | slot<<28}; n_req[0] = count, n_req[1] = games queued for k_gc
+    int32_t *gc_list, *pending, *resume_a;   // [G] games waiting for a collection, what to resume, and at which child
     float2 *eval_out;              // [G][8] (value, variance) per child slot; slot 7 = the leaf itself
     float *rollout_val;            // [G]
     unsigned long long *counters;  // [8] 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels 5 rollout steps 6 new nodes
@@ -262,120 +264,15 @@ __device__ __forceinline__ void table_insert(const Grp &gp, uint2 *tab, int H, u
 }
 
 // ------------------------------------------------------------------ garbage collection (agent.py:187-257)
-__device__ __noinline__ void collect_garbage(const Arena &A, const Grp &gp, int g) {
-    const int M = A.M, H = A.H;
-    uint8_t *nmark = A.nmark + (size_t)g * M, *omark = A.omark + (size_t)g * M;
-    int32_t *queue = A.gc_queue + (size_t)g * 2 * M;
-    int32_t *rowb = A.row + (size_t)g * M * ROW_WORDS;
-    uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
-    const int root = A.root[g];
-    for (int i = gp.lane; i < M; i += 8) { nmark[i] = 0; omark[i] = 0; }
-    gp.sync();
-    // get_all_childs (core.h:32-50): breadth-first over child[], the null node 0 included
-    if (gp.lane == 0) { nmark[root] = 1; nmark[0] = 1; queue[0] = root; }
-    gp.sync();
-    int head = 0, tail = 1;
-    while (head < tail) {
-        int n = queue[head++];
-        int c = (gp.lane < 7) ? rowb[(size_t)n * ROW_WORDS + gp.lane] : 0;
-        bool fresh = gp.lane < 7 && c != 0 && nmark[c] == 0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {            // the same child may sit in two slots: the earliest lane pushes it
-            int cj = gp.bcast(c, j);
-            if (gp.lane > j && cj == c) fresh = false;
-        }
-        unsigned fm = gp.ballot(fresh);
-        if (fresh) { nmark[c] = 1; queue[tail + __popc(fm & ((1u << gp.lane) - 1u))] = c; }
-        tail += __popc(fm);
-        gp.sync();
-    }
-    // update_available (agent.py:187-204): ascending complements; observations of occupied nodes stay
-    for (int i = gp.lane; i < M; i += 8)
-        if (nmark[i]) omark[rowb[(size_t)i * ROW_WORDS + 15]] = 1;   // n_to_o[i] lives in o[7]; n_to_o[0] = 0
-    gp.sync();
-    int32_t *nfree = A.nfree + (size_t)g * M, *ofree = A.ofree + (size_t)g * M;
-    int nn = 0, no = 0;
-    for (int base = 0; base < M; base += 8) {
-        int i = base + gp.lane;
-        bool fn = i < M && !nmark[i], fo = i < M && !omark[i];
-        unsigned mn = gp.ballot(fn), mo = gp.ballot(fo);
-        unsigned below = (1u << gp.lane) - 1u;
-        if (fn) nfree[nn + __popc(mn & below)] = i;
-        if (fo) ofree[no + __popc(mo & below)] = i;
-        nn += __popc(mn); no += __popc(mo);
-    }
-    gp.sync();
-    // reset_arrays (agent.py:227-244).  Node table: the reference pops BY THE FREED SLOT'S CURRENT GAME
-    // (agent.py:229-232), which for a slot freed at an earlier collection is a stale state that may equal a live
-    // node's state; that live node then loses its entry.  stale_pop=1 reproduces this literally.
-    const uint32_t *recb = A.rec + (size_t)g * M * REC_WORDS;
-    if (A.stale_pop) {
-        for (int j = 0; j < nn; ++j) {
-            int i = nfree[j];
-            uint32_t w[REC_WORDS];
-#pragma unroll
-            for (int q = 0; q < REC_WORDS / 4; ++q) {
-                uint4 v = *reinterpret_cast<const uint4 *>(recb + (size_t)i * REC_WORDS + q * 4);
-                w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
-            }
-            int slot = -1;
-            int hit = table_find<REC_WORDS>(gp, ntab, H, A.rec, (size_t)g * M, w, fold32(hash_words(w, REC_WORDS)), &slot);
-            if (hit && gp.lane == 0) ntab[slot].y = 0xffffffffu;
-            gp.sync();
-        }
-    } else {
-        for (int p = gp.lane; p < H; p += 8) { uint32_t y = ntab[p].y; if (y != 0u && y != 0xffffffffu && !nmark[y]) ntab[p].y = 0xffffffffu; }
-        gp.sync();
-    }
-    for (int p = gp.lane; p < H; p += 8) { uint32_t y = otab[p].y; if (y != 0u && y != 0xffffffffu && !omark[y]) otab[p].y = 0xffffffffu; }
-    gp.sync();
-    // compact both tables (drop deleted entries): survivors -> queue (as hash,index pairs) -> cleared table
-    for (int t = 0; t < 2; ++t) {
-        uint2 *tab = t ? otab : ntab;
-        uint2 *list = reinterpret_cast<uint2 *>(queue);   // gc_queue holds 2M ints = M pairs >= any survivor count
-        {
-            int cnt = 0;
-            for (int base = 0; base < H; base += 8) {
-                uint2 e = tab[base + gp.lane];
-                bool live = e.y != 0u && e.y != 0xffffffffu;
-                unsigned m = gp.ballot(live);
-                if (live) list[cnt + __popc(m & ((1u << gp.lane) - 1u))] = e;
-                cnt += __popc(m);
-                tab[base + gp.lane] = make_uint2(0u, 0u);
-            }
-            gp.sync();
-            for (int j = gp.lane; j < cnt; j += 8) {      // lanes claim slots with CAS; keys are unique so order is free
-                uint2 e = list[j];
-                uint32_t p = e.x & (uint32_t)(H - 1);
-                while (atomicCAS(&tab[p].y, 0u, e.y) != 0u) p = (p + 1) & (uint32_t)(H - 1);
-                tab[p].x = e.x;
-            }
-            gp.sync();
-        }
-    }
-    // zero the freed rows / statistics / keys
-    for (int j = 0; j < nn; ++j) {
-        int i = nfree[j];
-        int4 *r = reinterpret_cast<int4 *>(rowb + (size_t)i * ROW_WORDS);
-        // agent.py:234-235 zeroes self.arrays (child, episode, score, ...) but node_to_obs is not among them: keep o[7]
-        if (gp.lane < 6) r[gp.lane] = make_int4(0, 0, 0, gp.lane == 3 ? r[3].w : 0);
-    }
-    int4 *statb = A.stat + (size_t)g * M;
-    uint32_t *keyb = A.key + (size_t)g * M * KEY_WORDS;
-    for (int j = 0; j < no; ++j) {
-        int i = ofree[j];
-        if (gp.lane == 0) statb[i] = make_int4(0, 0, 0, 0);
-        if (gp.lane >= 1 && gp.lane < 4) reinterpret_cast<uint4 *>(keyb + (size_t)i * KEY_WORDS)[gp.lane - 1] = make_uint4(0, 0, 0, 0);
-    }
-    if (gp.lane == 0) { A.n_nfree[g] = nn; A.n_ofree[g] = no; atomicAdd(&A.counters[3], 1ull); }
-    gp.sync();
-}
+// remove_nodes runs as its own CTA-per-game kernel (kernels.cuh: k_gc): a game whose free list runs dry suspends
+// its expansion at exactly the child where the reference would call remove_nodes (agent.py:96-97), the collection
+// runs with a whole thread block, and k_expand_resume continues with the remaining children.
 
 // ------------------------------------------------------------------ new_node (agent.py:90-130)
 // `w` = packed game, held identically by all lanes.  Returns node index (0 on arena overflow); o_out/score_out are
 // the node's observation and score (what the parent's row caches for it).
 __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, const uint32_t (&w)[REC_WORDS], int &o_out,
-                                        float &score_out, int &status) {
+                                        float &score_out, int &status, bool may_suspend) {
     const int M = A.M, H = A.H;
     uint2 *ntab = A.ntab + (size_t)g * H;
     uint32_t h = fold32(hash_words(w, REC_WORDS));
@@ -387,8 +284,9 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
         return idx;
     }
     int nf = A.n_nfree[g];
-    if (nf == 0) { collect_garbage(A, gp, g); nf = A.n_nfree[g]; }        // agent.py:96-97
-    if (nf == 0) { status = ST_ARENA_FULL; o_out = 0; score_out = 0.f; return 0; }
+    if (nf == 0) {      // agent.py:96-97: remove_nodes() is due here.  First time: suspend for k_gc; after it: the arena is full.
+        status = may_suspend ? ST_NEED_GC : ST_ARENA_FULL; o_out = 0; score_out = 0.f; return 0;
+    }
     idx = A.nfree[(size_t)g * M + nf - 1];                                  // agent.py:99 pop() from the right
     gp.sync();
     if (gp.lane == 0) A.n_nfree[g] = nf - 1;
@@ -466,7 +364,7 @@ __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, in
         w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
     }
     int o; float sc;
-    int idx = new_node(A, gp, g, w, o, sc, status);
+    int idx = new_node(A, gp, g, w, o, sc, status, false);
     if (gp.lane == 0) { A.root[g] = idx; A.status[g] = status; }
     gp.sync();
 }
@@ -475,7 +373,7 @@ __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, in
 // lane a plays action a on the leaf's game; the seven results are then inserted in action order (first seen wins,
 // free-list order and a mid-expand garbage collection all as in the reference).  Leaves c/o/s of child a in lane a.
 __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g, int leaf, const uint32_t (&leafrec)[REC_WORDS],
-                                            int &c, int &o, float &s, int &status) {
+                                            int &c, int &o, float &s, int &status, int a_begin, bool may_suspend, int &a_stop) {
     uint32_t mine[REC_WORDS];
     {
         Game gm;
@@ -484,12 +382,14 @@ __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g
         pack(gm, mine);
     }
     c = 0; o = 0; s = 0.f;
-    for (int a = 0; a < N_ACTIONS; ++a) {
+    a_stop = N_ACTIONS;
+    for (int a = a_begin; a < N_ACTIONS; ++a) {
         uint32_t w[REC_WORDS];
 #pragma unroll
         for (int q = 0; q < REC_WORDS; ++q) w[q] = gp.bcast(mine[q], a);
         int oo; float ss;
-        int idx = new_node(A, gp, g, w, oo, ss, status);
+        int idx = new_node(A, gp, g, w, oo, ss, status, may_suspend);
+        if (status == ST_NEED_GC) { a_stop = a; break; }     // resume at this child after k_gc
         if (gp.lane == a) { c = idx; o = oo; s = ss; }
         // agent.py:145 writes child[i] as soon as new_node returns, so a collection triggered by a later
         // sibling already sees this child as reachable
@@ -500,7 +400,7 @@ __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g
         gp.sync();
         if (status != ST_OK) break;
     }
-    if (gp.lane == 0) atomicAdd(&A.counters[1], 1ull);
+    if (gp.lane == 0 && status == ST_OK) atomicAdd(&A.counters[1], 1ull);
 }
 
 // ------------------------------------------------------------------ backup (core.h:226-260), one thread

@@ -101,7 +101,7 @@ class BatchedEngine:
         L.check(L.lib().b200_counters(self.h, L.ptr(c)))
         return {n: int(c[i]) for i, n in enumerate(self.COUNTER_NAMES) if not n.startswith("_")}
 
-    PHASES = ("select_expand", "conv", "fc", "backup", "rollout", "synthetic", "misc", "_")
+    PHASES = ("select_expand", "conv", "fc", "backup", "rollout", "synthetic", "misc", "gc")
 
     def timer_start(self):
         L.check(L.lib().b200_timer_start(self.h))
