@@ -286,12 +286,14 @@ def run_b200(args, cfg):
             if conv_ms > 0 and conv_n > 0:
                 ach = boards * CONV_FLOP / (conv_ms / 1e3) / 1e12
                 roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
-                        "kernel": "k_vn_conv" if cfg["eval"] == "net" else "k_tc_conv", "ms_per_launch": conv_ms / conv_n,
+                        "kernel": "k_vn_conv" if cfg["eval"] == "net" else "k_tc_conv", "mma_flops_issued_per_launch": boards * 2 * 128 * 16 * (96 + 64 + 32) * 18 * 2 / conv_n, "ms_per_launch": conv_ms / conv_n,
                         "flops_per_launch": boards * CONV_FLOP / conv_n, "boards_per_launch": boards / conv_n,
                         "fc_kernel_tflops": boards * FC_FLOP / (fc_ms / 1e3) / 1e12 if fc_ms > 0 else None,
                         "share_of_step": conv_ms / ms, "peak_src": peaks["src"] + " bf16 dense, sustained",
-                        "note": "fp32-faithful arithmetic (north_star 1e-5): CUDA-core fp32 FMA for eval=net, 3xTF32 tcgen05 for eval=net_tc; "
-                                "the bf16 figure is the roofline denominator the driver measured, not this kernel's attainable ceiling"}
+                        "note": "achieved counts ALGORITHMIC conv FLOPs (SURVEY 8d: 2 884 608 per board).  fp32-faithful arithmetic (north_star 1e-5): "
+                                "eval=net is CUDA-core fp32 FMA; eval=net_tc is tcgen05 kind::f16 with every fp32 operand split into three bf16 terms "
+                                "(6 products per algorithmic product, M=128 pixel tiles with 25-56% halo rows), so the tensor pipe executes "
+                                "mma_flops_issued_per_launch; the bf16 peak is the driver-measured denominator, not this kernel's attainable ceiling"}
         else:
             ro_ms, ro_n = phases["rollout"]
             roof = {"bound": "hbm", "achieved": 0.0, "peak": peaks["hbm"], "unit": "GB/s", "frac": 0.0, "traffic": None, "kernel": "k_rollout",
@@ -333,7 +335,7 @@ def main():
     ap.add_argument("--games-per-gpu", type=int, default=None)
     ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--max-nodes", type=int, default=None)
-    ap.add_argument("--eval", default=os.environ.get("B200_EVAL", "net"), choices=["net", "net_tc", "synthetic"])
+    ap.add_argument("--eval", default=os.environ.get("B200_EVAL", "net_tc"), choices=["net", "net_tc", "synthetic"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-moves-per-step", type=int, default=4)

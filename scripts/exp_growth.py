@@ -23,3 +23,12 @@ for mv in range(moves):
     print('move %2d %.3fs sims/s %.3g new_nodes/game %.0f evals/sim %.2f D %.2f gcs %d resets %d finished %d' % (
         mv, dt, G * sims / dt, d['new_nodes'] / G, d['eval_requests'] / max(d['sims'], 1), d['trace_levels'] / max(d['sims'], 1), d['gcs'], d['tree_resets'], c['games_finished']), flush=True)
 print({k: (round(v[0], 2), v[1]) for k, v in eng.phase_ms().items()})
+
+import ctypes
+from tetris_mcts_b200 import _lib as L
+pr = np.zeros(16, np.uint64)
+L.lib().b200_debug_prof.argtypes = [L.P, L.P]
+L.check(L.lib().b200_debug_prof(eng.h, L.ptr(pr)))
+names = ['decode', 'conv1', 'wait_c2', 'epi2', 'wait_c3', 'epi3', 'iss_wait_a1', 'iss_conv2', 'iss_wait_a2', 'iss_conv3']
+tot = pr[:6].sum()
+print({n: round(float(pr[i]) / max(float(tot), 1), 3) for i, n in enumerate(names)}, 'worker cycles total', int(tot))

@@ -101,18 +101,19 @@ def test_no_stale_pop_variant(gpu_lib, oracle):
     run_pair(oracle, "lp", n=8, M=1500, sims=12, moves=100, engine_kw=dict(stale_pop=False), agent_kw=dict(stale_pop=0))
 
 
-def test_real_network_search_is_exact_given_the_same_evaluator(gpu_lib, oracle):
+@pytest.mark.parametrize("kind", ["net", "net_tc"])
+def test_real_network_search_is_exact_given_the_same_evaluator(gpu_lib, oracle, kind):
     """With the value network as evaluator the search must still be trace-for-trace identical when the oracle agent is
     fed the SAME network outputs (the LP path is deterministic given evaluator and piece sequence)."""
     from tetris_mcts_b200.engine import BatchedEngine
     w = oracle.seeded_weights(0)
-    side = BatchedEngine(1, max_nodes=64, eval_kind="net", weights=w)
+    side = BatchedEngine(1, max_nodes=64, eval_kind=kind, weights=w)
 
     def cb(states):
         v, var = side.valuenet(states)
         return v, var
 
-    run_pair(oracle, "lp", n=3, M=2048, sims=25, moves=4, eval_kind="net", weights=w, eval_cb=cb)
+    run_pair(oracle, "lp", n=3, M=2048, sims=25, moves=4, eval_kind=kind, weights=w, eval_cb=cb)
     side.close()
 
 

@@ -23,7 +23,7 @@ def _boards_unused(n, seed):
     return b
 
 
-@pytest.mark.parametrize("kind", ["net"])
+@pytest.mark.parametrize("kind", ["net", "net_tc"])
 def test_matches_oracle(gpu_lib, oracle, kind):
     from tetris_mcts_b200.engine import BatchedEngine
     w = oracle.seeded_weights(0)
@@ -37,10 +37,11 @@ def test_matches_oracle(gpu_lib, oracle, kind):
     eng.close()
 
 
-def test_batch_position_independent(gpu_lib, oracle):
+@pytest.mark.parametrize("kind", ["net", "net_tc"])
+def test_batch_position_independent(gpu_lib, oracle, kind):
     """The same board must give the same bits wherever it sits in the batch (search determinism relies on it)."""
     from tetris_mcts_b200.engine import BatchedEngine
-    eng = BatchedEngine(1, max_nodes=64, eval_kind="net", weights=oracle.seeded_weights(1))
+    eng = BatchedEngine(1, max_nodes=64, eval_kind=kind, weights=oracle.seeded_weights(1))
     s = boards(300, 9)
     v1, r1 = eng.valuenet(s)
     perm = np.random.default_rng(0).permutation(300)
@@ -50,13 +51,32 @@ def test_batch_position_independent(gpu_lib, oracle):
 
 
 @pytest.mark.skipif(not os.path.exists(GOLD), reason="golden vectors not generated")
-def test_matches_reference_golden(gpu_lib, oracle):
+@pytest.mark.parametrize("kind", ["net", "net_tc"])
+def test_matches_reference_golden(gpu_lib, oracle, kind):
     from tetris_mcts_b200.engine import BatchedEngine
     z = np.load(GOLD)
     for seed in z["seeds"]:
         w = oracle.seeded_weights(int(seed))
-        eng = BatchedEngine(1, max_nodes=64, eval_kind="net", weights=w)
+        eng = BatchedEngine(1, max_nodes=64, eval_kind=kind, weights=w)
         v, var = eng.valuenet(z["states"])
         assert np.allclose(v, z["v_%d" % seed], rtol=RTOL, atol=ATOL), np.abs(v - z["v_%d" % seed]).max()
         assert np.allclose(var, z["var_%d" % seed], rtol=RTOL, atol=ATOL), np.abs(var - z["var_%d" % seed]).max()
         eng.close()
+
+
+def test_tensor_core_conv_stack_matches_cuda_core_path(gpu_lib, oracle):
+    """Layer-level check of the tcgen05 shift-GEMM convolutions: the flatten input of fc1 from both device paths."""
+    import ctypes as C
+    from tetris_mcts_b200.engine import BatchedEngine
+    from tetris_mcts_b200 import _lib as L
+    w = oracle.seeded_weights(2)
+    s = np.ascontiguousarray(boards(37, 5).reshape(-1, 200))
+    outs = {}
+    for kind in ("net", "net_tc"):
+        eng = BatchedEngine(1, max_nodes=64, eval_kind=kind, weights=w)
+        o = np.zeros((len(s), 1792), np.float32)
+        L.check(L.lib().b200_debug_act3(eng.h, L.ptr(s), len(s), L.ptr(o)))
+        outs[kind] = o
+        eng.close()
+    assert np.abs(outs["net"]).max() > 0.01
+    assert np.allclose(outs["net"], outs["net_tc"], rtol=2e-6, atol=2e-6), np.abs(outs["net"] - outs["net_tc"]).max()

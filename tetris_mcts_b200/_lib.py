@@ -64,6 +64,7 @@ def lib():
         L.b200_phase_ms.argtypes = [P, P, P]
         L.b200_export_game.argtypes = [P, C.c_int] + [P] * 13
         L.b200_valuenet_forward.argtypes = [P, P, C.c_int, P, P]
+        L.b200_debug_act3.argtypes = [P, P, C.c_int, P]
         L.b200_tetris_step.argtypes = [P, P, C.c_int]
         L.b200_tetris_new.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int]
         L.b200_tetris_state.argtypes = [P, P, C.c_int]

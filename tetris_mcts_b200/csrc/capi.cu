@@ -165,7 +165,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     rc |= dalloc(e, &A.req, G * 8); rc |= dalloc(e, &A.n_req, 2);
     rc |= dalloc(e, &A.gc_list, G); rc |= dalloc(e, &A.pending, G); rc |= dalloc(e, &A.resume_a, G);
     rc |= dalloc(e, &A.eval_out, G * 8); rc |= dalloc(e, &A.rollout_val, G);
-    rc |= dalloc(e, &A.counters, 16);
+    rc |= dalloc(e, &A.counters, 32);
     rc |= dalloc(e, &e->d_default_rec, REC_WORDS);
     rc |= dalloc(e, &e->d_stats, G * 21); rc |= dalloc(e, &e->d_action, G);
     e->d_game_stats = A.counters + 8;
@@ -267,13 +267,24 @@ static int ensure_act3(b200_engine *e, size_t rows) {
 static int launch_net(b200_engine *e, const uint2 *req, const int32_t *n_req, const uint32_t *keys, int M, float2 *eval_out,
                       size_t max_rows) {
     if (!e->have_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
-    if (ensure_act3(e, max_rows)) return B200_ERR_CUDA;
 #ifdef B200_WITH_TC
     if (e->cfg.eval_kind == B200_EVAL_NET_TC) {
-        return tc_forward(e->tc_state, req, n_req, keys, M, eval_out, max_rows, e->d_act3, e->W, e->n_sm, e->stream,
-                          [&](int ph) { return new PhaseTimer(e, ph); }, [](void *t) { delete (PhaseTimer *)t; });
+        TcState *st = (TcState *)e->tc_state;
+        if (tc_ensure_act3(st, max_rows, e->stream)) return fail(B200_ERR_CUDA, "act3 (tensor-core layout) allocation failed");
+        {
+            PhaseTimer t(e, PH_CONV);
+            k_tc_conv<<<e->n_sm, TCC_THREADS, TCC_SMEM, e->stream>>>(e->W, st->TW, req, n_req, keys, M, st->d_act3, (int)st->tiles,
+                                                                    e->timing ? e->A.counters + 16 : nullptr);
+        }
+        {
+            PhaseTimer t(e, PH_FC);
+            k_tc_fc<<<e->n_sm, TCF_THREADS, TCF_SMEM, e->stream>>>(e->W, st->TW, st->d_act3, (int)st->tiles, req, n_req, eval_out);
+        }
+        CK(cudaGetLastError());
+        return B200_OK;
     }
 #endif
+    if (ensure_act3(e, max_rows)) return B200_ERR_CUDA;
     {
         PhaseTimer t(e, PH_CONV);
         k_vn_conv<<<e->n_sm, VN_THREADS, VN_SMEM_BYTES, e->stream>>>(e->W, req, n_req, keys, M, e->d_act3);
@@ -426,6 +437,14 @@ extern "C" int b200_counters(b200_engine *e, uint64_t *out16) {
     return B200_OK;
 }
 
+extern "C" int b200_debug_prof(b200_engine *e, uint64_t *out16) {   // clock64 phase sums of CTA 0 of k_tc_conv (timing mode)
+    if (!e || !out16) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(out16, e->A.counters + 16, 16 * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
 extern "C" int b200_sync(b200_engine *e) {
     if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
     CK(cudaSetDevice(e->cfg.device));
@@ -546,6 +565,41 @@ extern "C" int b200_valuenet_forward(b200_engine *e, const int8_t *states, int k
     cudaStreamSynchronize(e->stream);
     cudaFree(d_states); cudaFree(d_keys); cudaFree(d_req); cudaFree(d_n); cudaFree(d_out);
     return rc;
+}
+
+// development / test aid: the conv stack's output (flatten input of fc1) in torch order c*56 + y*4 + x, for either path
+extern "C" int b200_debug_act3(b200_engine *e, const int8_t *states, int k, float *out) {
+    if (!e || !states || !out || k < 1) return fail(B200_ERR_BAD_ARG, "bad argument");
+    std::vector<float> v(k), var(k);
+    int rc = b200_valuenet_forward(e, states, k, v.data(), var.data());   // leaves act3 of these k boards in the scratch buffers
+    if (rc) return rc;
+#ifdef B200_WITH_TC
+    if (e->cfg.eval_kind == B200_EVAL_NET_TC) {
+        TcState *st = (TcState *)e->tc_state;
+        size_t bytes = (size_t)3 * st->tiles * ACT3_KCHUNKS * 2048;
+        std::vector<uint8_t> h(bytes);
+        CK(cudaMemcpy(h.data(), st->d_act3, bytes, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < k; ++r)
+            for (int kp = 0; kp < 1792; ++kp) {
+                int p = kp >> 5, c = kp & 31;
+                float sum = 0.f;
+                for (int s = 2; s >= 0; --s) {
+                    size_t off = ((((size_t)s * st->tiles + (r >> 7)) * ACT3_KCHUNKS + (kp >> 3)) * 128 + (r & 127)) * 16 + (kp & 7) * 2;
+                    uint16_t hb; memcpy(&hb, &h[off], 2);
+                    sum += host_bf16_f(hb);
+                }
+                out[(size_t)r * 1792 + c * 56 + p] = sum;
+            }
+        return B200_OK;
+    }
+#endif
+    std::vector<float> h((size_t)k * 1792);
+    CK(cudaMemcpy(h.data(), e->d_act3, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < k; ++r)
+        for (int y = 0; y < 14; ++y)
+            for (int c = 0; c < 32; ++c)
+                for (int x = 0; x < 4; ++x) out[(size_t)r * 1792 + c * 56 + y * 4 + x] = h[(size_t)r * 1792 + (y * 32 + c) * 4 + x];
+    return B200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------- standalone env

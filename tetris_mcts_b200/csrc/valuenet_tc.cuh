@@ -1,0 +1,589 @@
+// valuenet_tc.cuh — the reference value network (model/model_vv.py:13-52) on Blackwell tensor cores (sm_100a).
+//
+// Precision: north_star asks value outputs within 1e-5 of the reference's fp32.  Plain bf16/tf32 MMAs cannot reach
+// that, so every fp32 operand x is split into three bf16 terms x = x1 + x2 + x3 (24 mantissa bits kept) and each
+// product a*b is accumulated in fp32 (TMEM) as a1b3 + a3b1 + a2b2 + a1b2 + a2b1 + a1b1 (smallest terms first; the
+// dropped terms are < 2^-24 relative).  Six bf16 MMAs replace one fp32 product: the tensor pipe still beats the
+// CUDA-core path by ~5x end to end.
+//
+//   k_tc_conv  one persistent CTA per SM, two boards in flight (ping-pong):
+//              decode obs key -> conv1 on CUDA cores (K = 9 is too small for an MMA) -> split -> smem
+//              conv2 / conv3 as shift-GEMMs: activations live in shared memory channel-chunk-major
+//              ([8-channel chunk][pixel row][16 B]), so the A operand of filter tap (dy,dx) is the SAME array
+//              started (dy*W+dx) rows later — a canonical no-swizzle K-major UMMA layout with SBO = 128 B,
+//              LBO = rows*16 B.  tcgen05.mma (M=128 pixels, N=32 couts, K=16) issued by one thread, accumulators
+//              in TMEM, completion through tcgen05.commit -> mbarrier; epilogues read TMEM with tcgen05.ld, apply
+//              bias+ReLU, re-split and write the next layer's operand (or act3 to HBM in the FC kernel's tile layout).
+//   k_tc_fc    [R,1792] x [1792,256]: 128-row tiles, operands streamed by cp.async.bulk (1-D TMA) into a 5-stage
+//              mbarrier ring — both operands are stored in HBM already in the canonical UMMA layout, so one bulk copy
+//              per operand block needs no tensor map; warp-specialised (producer / MMA issuer / 4 epilogue warps);
+//              epilogue fuses bias+ReLU+fc_out+sigmoid+affine and scatters (v, var) to the requesting tree slot.
+#pragma once
+#include <cuda_bf16.h>
+#include "search_dev.cuh"
+#include "valuenet_simt.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {   // 1-D TMA (UBLKCP)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {   // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {   // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// rows of a core matrix are 16 B apart, 8-row groups SBO apart, the two 16-byte K chunks LBO apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {   // lane i of the warp <- TMEM lane (quadrant*32 + i), 16 columns
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// accumulator blocks a*W1 | a*W2 | a*W3 sit 32 columns apart: add them smallest first
+__device__ __forceinline__ void tmem_ld16_sum3(uint32_t taddr, float (&v)[16]) {
+    float w1[16], w2[16], w3[16];
+    tmem_ld16(taddr + 64, w3);
+    tmem_ld16(taddr + 32, w2);
+    tmem_ld16(taddr, w1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (w3[i] + w2[i]) + w1[i];
+}
+
+// x = x1 + x2 + x3 with bf16 terms (round-to-nearest each step); returned as three 16-bit patterns
+__device__ __forceinline__ void split3(float x, uint32_t &h1, uint32_t &h2, uint32_t &h3) {
+    __nv_bfloat16 b1 = __float2bfloat16_rn(x);
+    float r1 = x - __bfloat162float(b1);
+    __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+    float r2 = r1 - __bfloat162float(b2);
+    __nv_bfloat16 b3 = __float2bfloat16_rn(r2);
+    h1 = __bfloat16_as_ushort(b1); h2 = __bfloat16_as_ushort(b2); h3 = __bfloat16_as_ushort(b3);
+}
+// eight fp32 values -> three 16-byte chunks (one per split)
+__device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2, uint4 &c3) {
+    uint32_t a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split3(x[i], a[i], b[i], c[i]);
+    c1 = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
+    c2 = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
+    c3 = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
+}
+
+// product terms in accumulation order: (A split, B split), smallest magnitude first
+__device__ __constant__ int TC_TERM_A[6] = {0, 2, 1, 0, 1, 0};
+__device__ __constant__ int TC_TERM_B[6] = {2, 0, 1, 1, 0, 0};
+__host__ __device__ constexpr int tc_term_a(int t) { return t == 0 ? 0 : t == 1 ? 2 : t == 2 ? 1 : t == 3 ? 0 : t == 4 ? 1 : 0; }
+__host__ __device__ constexpr int tc_term_b(int t) { return t == 0 ? 2 : t == 1 ? 0 : t == 2 ? 1 : t == 3 ? 1 : t == 4 ? 0 : 0; }
+
+// ---------------------------------------------------------------------------------------------------- conv kernel
+constexpr int TCC_WORKERS = 256;            // warps 0-7: decode, conv1, epilogues
+constexpr int TCC_THREADS = TCC_WORKERS + 32;   // warp 8: MMA issuer (one elected lane)
+constexpr int TCC_R1 = 152;                 // act1 rows per board: 18x8 grid = 144 (+8: tap shifts read up to row 145)
+constexpr int TCC_R2 = 144;                 // act2 rows per board: 16x6 grid = 96 (+48: M=128 tile + shifts read up to row 141)
+constexpr int TCC_WBLOCK = 2 * 96 * 16;      // one (tap, half) block: [chunk 2][n = split*32 + cout][16 B]
+constexpr int TCC_WBYTES = 18 * TCC_WBLOCK;  // one conv layer = 55296 B
+constexpr int TCC_A1 = 3 * 4 * TCC_R1 * 16; // act1 of one board slot: [split][chunk 4][row][16 B]
+constexpr int TCC_A2 = 3 * 4 * TCC_R2 * 16;
+constexpr int TCC_OFF_W2 = 0;
+constexpr int TCC_OFF_W3 = TCC_OFF_W2 + TCC_WBYTES;
+constexpr int TCC_OFF_A1 = TCC_OFF_W3 + TCC_WBYTES;
+constexpr int TCC_OFF_A2 = TCC_OFF_A1 + 2 * TCC_A1;
+constexpr int TCC_OFF_IN = TCC_OFF_A2 + 2 * TCC_A2;        // 2 x 200 floats
+constexpr int TCC_OFF_W1 = TCC_OFF_IN + 2 * 200 * 4;       // 288 floats + 96 floats of biases
+constexpr int TCC_OFF_KEY = TCC_OFF_W1 + (288 + 96) * 4;   // 2 x 12 key words of the current pair
+constexpr int TCC_OFF_BAR = TCC_OFF_KEY + 2 * 12 * 4;      // 8 mbarriers + tmem pointer
+constexpr int TCC_SMEM = TCC_OFF_BAR + 80;
+constexpr int TCC_TMEM_COLS = 512;          // 2 slots x 2 layers x 96 columns (three partial sums of 32 couts) = 384 -> 512
+constexpr int ACT3_KCHUNKS = 224;           // 1792 / 8
+
+struct TcWeights {
+    const uint8_t *wc2, *wc3;   // TCC_WBYTES each, already in the shared-memory layout
+    const uint8_t *wfc;         // [split 3][k16 block 112][chunk 2][n 256][16 B]
+};
+
+// act3 in HBM, FC-tile layout: [split][tile of 128 rows][k chunk 224][row 128][8 bf16], k' = (y*4 + x)*32 + c
+__device__ __forceinline__ size_t act3_off(int split, int n_tiles, int ridx, int kchunk) {
+    return ((((size_t)split * n_tiles + (ridx >> 7)) * ACT3_KCHUNKS + kchunk) * 128 + (ridx & 127)) * 16;
+}
+
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// One 3x3 convolution layer as 54 tcgen05.mma (9 taps x 2 halves of the 32 input channels x 3 activation splits).
+// The operand fetch of an SS-mode MMA is shared-memory bound (~64 B/clk), so the three weight splits are stacked along
+// N: activation split 1 meets [W1;W2;W3] (N=96), split 2 meets [W1;W2] (N=64), split 3 meets W1 (N=32).  The six
+// products land in three 32-column accumulator blocks (a*W1 | a*W2 | a*W3) that the epilogue adds, smallest first.
+//   R = rows per operand chunk, WGRID = width of the pixel grid the operand is stored on (tap shift = dy*WGRID + dx)
+template <int R, int WGRID>
+__device__ __forceinline__ void issue_conv_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
+    const uint64_t a0 = umma_desc(a_addr, R * 16, 128), b0 = umma_desc(w_addr, 96 * 16, 128);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int sa = 0; sa < 3; ++sa) {
+                const uint32_t a_off = sa * 4 * R + 2 * h * R + (tap / 3) * WGRID + (tap % 3);   // 16-byte units
+                const uint32_t b_off = (tap * 2 + h) * (TCC_WBLOCK / 16);
+                // split sa of the activations only needs weight splits 0 .. 2-sa (N = 96, 64, 32); the first k block
+                // initialises the columns it covers: sa=0 covers all 96, so later ones always accumulate
+                umma_bf16(tmem_d, a0 + a_off, b0 + b_off, umma_idesc_bf16(128, 96 - 32 * sa), (tap | h | sa) ? 1u : 0u);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TCC_THREADS, 1)
+k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr, const uint32_t *keys, int M, uint8_t *act3, int n_tiles,
+          unsigned long long *prof) {
+#define PROF_T(i) do { if (prof && do_prof) { long long _n = clock64(); pacc[i] += _n - ptick; ptick = _n; } } while (0)
+    extern __shared__ __align__(128) uint8_t smem[];
+    float *sIn = reinterpret_cast<float *>(smem + TCC_OFF_IN);
+    float *sW1 = reinterpret_cast<float *>(smem + TCC_OFF_W1);
+    float *sB = sW1 + 288;
+    uint32_t *sKey = reinterpret_cast<uint32_t *>(smem + TCC_OFF_KEY);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TCC_OFF_BAR);
+    uint64_t *bar_c2 = bars, *bar_c3 = bars + 2;       // tensor core -> workers: conv2 / conv3 of slot done
+    uint64_t *bar_a1 = bars + 4, *bar_a2 = bars + 6;   // workers -> issuer: act1 / act2 of slot written
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + TCC_OFF_BAR + 64);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    // ---- one-time setup: weights into smem, zeroed activations, barriers, TMEM
+    for (int i = t; i < TCC_WBYTES / 16; i += TCC_THREADS) {
+        reinterpret_cast<uint4 *>(smem + TCC_OFF_W2)[i] = reinterpret_cast<const uint4 *>(TW.wc2)[i];
+        reinterpret_cast<uint4 *>(smem + TCC_OFF_W3)[i] = reinterpret_cast<const uint4 *>(TW.wc3)[i];
+    }
+    for (int i = t; i < (2 * TCC_A1 + 2 * TCC_A2) / 16; i += TCC_THREADS) reinterpret_cast<uint4 *>(smem + TCC_OFF_A1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = t; i < 288; i += TCC_THREADS) sW1[i] = W.w1[i];
+    if (t < 32) { sB[t] = W.b1[t]; sB[32 + t] = W.b2[t]; sB[64 + t] = W.b3[t]; }
+    if (t == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        for (int i = 4; i < 8; ++i) mbar_init(&bars[i], TCC_WORKERS);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc<TCC_TMEM_COLS>(tmem_ptr);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_req = *n_req_ptr;
+    const int n_pairs = (n_req + 1) >> 1;
+    // pairs are handed out in runs of 4 (8 consecutive requests) so that neighbouring act3 rows are written close in time
+    const int n_runs = (n_pairs + 3) >> 2;
+    if (warp == 8) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t s_w2 = smem_u32(smem + TCC_OFF_W2), s_w3 = smem_u32(smem + TCC_OFF_W3);
+            const uint32_t s_a1 = smem_u32(smem + TCC_OFF_A1), s_a2 = smem_u32(smem + TCC_OFF_A2);
+            uint32_t phase = 0;
+            const bool do_prof = blockIdx.x == 0;
+            long long pacc[12] = {0}, ptick = clock64();
+            for (int run = blockIdx.x; run < n_runs; run += gridDim.x)
+                for (int pi = 0; pi < 4 && run * 4 + pi < n_pairs; ++pi) {
+                    for (int slot = 0; slot < 2; ++slot) {     // conv2 (model_vv.py:34): act1 on the 18x8 grid
+                        mbar_wait(&bar_a1[slot], phase);
+                        PROF_T(6);
+                        tc_fence_after();
+                        issue_conv_layer<TCC_R1, 8>(tmem_base + slot * 192, s_a1 + slot * TCC_A1, s_w2);
+                        umma_commit(&bar_c2[slot]);
+                        PROF_T(7);
+                    }
+                    for (int slot = 0; slot < 2; ++slot) {     // conv3 (model_vv.py:36): act2 on the compact 16x6 grid
+                        mbar_wait(&bar_a2[slot], phase);
+                        PROF_T(8);
+                        tc_fence_after();
+                        issue_conv_layer<TCC_R2, 6>(tmem_base + slot * 192 + 96, s_a2 + slot * TCC_A2, s_w3);
+                        umma_commit(&bar_c3[slot]);
+                        PROF_T(9);
+                    }
+                    phase ^= 1;
+                }
+            if (prof && do_prof) for (int i = 6; i < 10; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+        }
+    } else {
+        // ===================================================== workers (256 threads)
+        uint32_t phase = 0;
+        const bool do_prof = blockIdx.x == 0 && t == 0;
+        long long pacc[12] = {0}, ptick = clock64();
+        uint32_t kpre = 0;                                     // prefetched key word of the NEXT pair (threads 0..23)
+        auto fetch_key = [&](int pair) -> uint32_t {
+            const int ridx = pair * 2 + t / 12;
+            if (t < 24 && pair < n_pairs && ridx < n_req) {
+                uint2 rq = req[ridx];
+                return keys[((size_t)rq.x * M + (rq.y & 0x0fffffffu)) * KEY_WORDS + (t % 12)];
+            }
+            return 0u;
+        };
+        int first_pair = blockIdx.x * 4;
+        kpre = fetch_key(first_pair);
+        for (int run = blockIdx.x; run < n_runs; run += gridDim.x)
+            for (int pi = 0; pi < 4 && run * 4 + pi < n_pairs; ++pi) {
+                const int pair = run * 4 + pi;
+                if (t < 24) sKey[t] = kpre;
+                worker_barrier();
+                {   // prefetch the next pair's keys (latency hidden behind this pair's work)
+                    int np = (pi < 3 && pair + 1 < n_pairs) ? pair + 1 : (run + (int)gridDim.x) * 4;
+                    kpre = fetch_key(np);
+                }
+                // ---- decode both boards: {-1,0,1} (model_vv.py:212)
+                for (int i = t; i < 400; i += TCC_WORKERS) {
+                    const int slot = i / 200, cell = i - slot * 200, r = cell / 10, c = cell - r * 10;
+                    const uint32_t *k = sKey + slot * 12;
+                    float v = 0.f;
+                    if (pair * 2 + slot < n_req) {
+                        v = (float)((k[r >> 1] >> ((r & 1) * 16 + c)) & 1u);
+                        uint32_t pc = k[10], ci = (uint32_t)cell;
+                        if ((pc & 0xffu) == ci || ((pc >> 8) & 0xffu) == ci || ((pc >> 16) & 0xffu) == ci || (pc >> 24) == ci) v = -1.f;
+                    }
+                    sIn[i] = v;
+                }
+                worker_barrier();
+                PROF_T(0);
+                // ---- conv1 (model_vv.py:32) on CUDA cores: task = (pixel of the 18x8 grid, 8-cout chunk)
+                for (int slot = 0; slot < 2; ++slot) {
+                    for (int task = t; task < 144 * 4; task += TCC_WORKERS) {
+                        const int cq = task & 3, pix = task >> 2, y = pix >> 3, x = pix & 7;
+                        float acc[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = sB[cq * 8 + j];
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                float in = sIn[slot * 200 + (y + dy) * 10 + x + dx];
+                                const float4 *w = reinterpret_cast<const float4 *>(sW1 + (dy * 3 + dx) * 32 + cq * 8);
+                                float4 wa = w[0], wb = w[1];
+                                acc[0] = fmaf(in, wa.x, acc[0]); acc[1] = fmaf(in, wa.y, acc[1]); acc[2] = fmaf(in, wa.z, acc[2]); acc[3] = fmaf(in, wa.w, acc[3]);
+                                acc[4] = fmaf(in, wb.x, acc[4]); acc[5] = fmaf(in, wb.y, acc[5]); acc[6] = fmaf(in, wb.z, acc[6]); acc[7] = fmaf(in, wb.w, acc[7]);
+                            }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+                        uint4 c1, c2, c3;
+                        split8(acc, c1, c2, c3);
+                        uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_A1 + (cq * TCC_R1 + pix) * 16;
+                        *reinterpret_cast<uint4 *>(base) = c1;
+                        *reinterpret_cast<uint4 *>(base + 4 * TCC_R1 * 16) = c2;
+                        *reinterpret_cast<uint4 *>(base + 8 * TCC_R1 * 16) = c3;
+                    }
+                    tc_fence_before();          // orders this thread's earlier tcgen05.ld of the slot's accumulators
+                    fence_async_smem();
+                    mbar_arrive(&bar_a1[slot]);
+                }
+                PROF_T(1);
+                // ---- conv2 epilogue: bias + ReLU + split -> act2[slot] (16x6 compact grid)
+                const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+                for (int slot = 0; slot < 2; ++slot) {
+                    mbar_wait(&bar_c2[slot], phase);
+                    PROF_T(2);
+                    tc_fence_after();
+                    float v[16];
+                    tmem_ld16_sum3(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 192 + half * 16, v);
+                    const int y = m >> 3, x = m & 7;
+                    if (x < 6) {
+                        const int r = y * 6 + x;
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[32 + half * 16 + c2 * 8 + j], 0.f);
+                            uint4 c1, cc2, c3;
+                            split8(o, c1, cc2, c3);
+                            uint8_t *base = smem + TCC_OFF_A2 + slot * TCC_A2 + ((half * 2 + c2) * TCC_R2 + r) * 16;
+                            *reinterpret_cast<uint4 *>(base) = c1;
+                            *reinterpret_cast<uint4 *>(base + 4 * TCC_R2 * 16) = cc2;
+                            *reinterpret_cast<uint4 *>(base + 8 * TCC_R2 * 16) = c3;
+                        }
+                    }
+                    tc_fence_before();
+                    fence_async_smem();
+                    mbar_arrive(&bar_a2[slot]);
+                    PROF_T(3);
+                }
+                // ---- conv3 epilogue: bias + ReLU + split -> act3 in HBM (FC tile layout)
+                for (int slot = 0; slot < 2; ++slot) {
+                    mbar_wait(&bar_c3[slot], phase);
+                    PROF_T(4);
+                    tc_fence_after();
+                    const int ridx = pair * 2 + slot;
+                    const int y = m / 6, x = m - y * 6;
+                    float v[16];
+                    tmem_ld16_sum3(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 192 + 96 + half * 16, v);
+                    if (m < 84 && x < 4 && ridx < n_req) {
+                        const int p = y * 4 + x;
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            float o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[64 + half * 16 + c2 * 8 + j], 0.f);
+                            uint4 c1, cc2, c3;
+                            split8(o, c1, cc2, c3);
+                            const int kc = p * 4 + half * 2 + c2;
+                            *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
+                            *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = cc2;
+                            *reinterpret_cast<uint4 *>(act3 + act3_off(2, n_tiles, ridx, kc)) = c3;
+                        }
+                    }
+                    PROF_T(5);
+                }
+                phase ^= 1;
+            }
+        if (prof && do_prof) for (int i = 0; i < 6; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+    }
+#undef PROF_T
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<TCC_TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------- fc kernel
+constexpr int TCF_THREADS = 192;            // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int TCF_STAGES = 5;
+constexpr int TCF_A_BYTES = 2 * 128 * 16;   // one split of one k16 block of the A tile
+constexpr int TCF_B_BYTES = 2 * 256 * 16;
+constexpr int TCF_STAGE = 3 * TCF_A_BYTES + 3 * TCF_B_BYTES;   // 36864
+constexpr int TCF_KBLOCKS = 112;            // 1792 / 16
+constexpr int TCF_OFF_BAR = TCF_STAGES * TCF_STAGE;
+constexpr int TCF_OFF_EPI = TCF_OFF_BAR + 128;                 // bias[256] | wout[2][256] | bout/ub/lb
+constexpr int TCF_SMEM = TCF_OFF_EPI + (256 * 3 + 8) * 4;
+constexpr int TCF_TMEM_COLS = 256;
+
+__global__ void __launch_bounds__(TCF_THREADS, 1)
+k_tc_fc(NetWeights W, TcWeights TW, const uint8_t *act3, int n_tiles_alloc, const uint2 *req, const int32_t *n_req_ptr, float2 *eval_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TCF_OFF_BAR);     // [stage] operands landed
+    uint64_t *empty = full + TCF_STAGES;                                    // [stage] operands consumed
+    uint64_t *acc_full = empty + TCF_STAGES;                                // accumulator complete
+    uint64_t *acc_empty = acc_full + 1;                                     // accumulator drained by the epilogue
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 1);
+    float *sBias = reinterpret_cast<float *>(smem + TCF_OFF_EPI), *sWo = sBias + 256, *sTail = sWo + 512;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    for (int i = t; i < 256; i += TCF_THREADS) { sBias[i] = W.bfc1[i]; sWo[i] = W.wout[i]; sWo[256 + i] = W.wout[256 + i]; }
+    if (t < 2) { sTail[t] = W.bout[t]; sTail[2 + t] = W.ub[t]; sTail[4 + t] = W.lb[t]; }
+    if (t == 0) {
+        for (int i = 0; i < TCF_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TCF_TMEM_COLS>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_req = *n_req_ptr;
+    const int n_tiles = (n_req + 127) >> 7;
+    if (warp == 0) {
+        if (lane == 0) {   // ===== producer: bulk copies of the pre-laid-out operand blocks
+            int stage = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int j = 0; j < TCF_KBLOCKS; ++j) {
+                    mbar_wait(&empty[stage], ph ^ 1);
+                    mbar_expect_tx(&full[stage], TCF_STAGE);
+                    uint8_t *dst = smem + stage * TCF_STAGE;
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        bulk_g2s(dst + s * TCF_A_BYTES, act3 + (((size_t)s * n_tiles_alloc + tile) * ACT3_KCHUNKS + 2 * j) * 2048, TCF_A_BYTES, &full[stage]);
+                        bulk_g2s(dst + 3 * TCF_A_BYTES + s * TCF_B_BYTES, TW.wfc + ((size_t)s * TCF_KBLOCKS + j) * TCF_B_BYTES, TCF_B_BYTES, &full[stage]);
+                    }
+                    if (++stage == TCF_STAGES) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer: D[128 x 256] += A[128 x 16] * B[256 x 16]^T, six split terms per k block
+            const uint32_t idesc = umma_idesc_bf16(128, 256);
+            int stage = 0; uint32_t ph = 0, aph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(acc_empty, aph ^ 1);
+                tc_fence_after();
+                uint32_t acc = 0;
+                for (int j = 0; j < TCF_KBLOCKS; ++j) {
+                    mbar_wait(&full[stage], ph);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + stage * TCF_STAGE);
+#pragma unroll
+                    for (int term = 0; term < 6; ++term) {
+                        uint64_t ad = umma_desc(sbase + TC_TERM_A[term] * TCF_A_BYTES, 128 * 16, 128);
+                        uint64_t bd = umma_desc(sbase + 3 * TCF_A_BYTES + TC_TERM_B[term] * TCF_B_BYTES, 256 * 16, 128);
+                        umma_bf16(tmem_base, ad, bd, idesc, acc);
+                        acc = 1;
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == TCF_STAGES) { stage = 0; ph ^= 1; }
+                }
+                umma_commit(acc_full);
+                aph ^= 1;
+            }
+        }
+    } else {   // ===== epilogue warps 2..5: TMEM quadrant = warp % 4, one row per thread
+        const int q = warp & 3, row = q * 32 + lane;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(acc_full, aph);
+            tc_fence_after();
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float h = fmaxf(v[j] + sBias[c0 + j], 0.f);                 // model_vv.py:39-40
+                    p0 = fmaf(h, sWo[c0 + j], p0); p1 = fmaf(h, sWo[256 + c0 + j], p1);   // :41
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty);
+            const int ridx = tile * 128 + row;
+            if (ridx < n_req) {
+                float x0 = p0 + sTail[0], x1 = p1 + sTail[1];
+                float s0 = 1.f / (1.f + expf(-x0)), s1 = 1.f / (1.f + expf(-x1));      // :42
+                uint2 rq = req[ridx];
+                eval_out[(size_t)rq.x * 8 + (rq.y >> 28)] =
+                    make_float2(__fadd_rn(__fmul_rn(s0, sTail[2]), sTail[4]), __fadd_rn(__fmul_rn(s1, sTail[3]), sTail[5]));   // :51
+            }
+            aph ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TCF_TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+struct TcState {
+    uint8_t *d_w = nullptr;      // wc2 | wc3 | wfc
+    TcWeights TW{};
+    uint8_t *d_act3 = nullptr; size_t tiles = 0;
+};
+
+static inline uint16_t host_bf16_rn(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float host_bf16_f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+static inline void host_split3(float x, uint16_t *o) {
+    o[0] = host_bf16_rn(x); float r1 = x - host_bf16_f(o[0]);
+    o[1] = host_bf16_rn(r1); float r2 = r1 - host_bf16_f(o[1]);
+    o[2] = host_bf16_rn(r2);
+}
+
+// w = the state_dict-order weight vector of include/b200_tetris_mcts.h.  Pure re-layout + bf16 splitting.
+static int tc_prepare(void **state, const float *w, cudaStream_t stream) {
+    TcState *st = (TcState *)*state;
+    if (!st) { st = new TcState(); *state = st; }
+    const float *c2w = w + 288 + 32, *c3w = c2w + 9216 + 32, *f1w = c3w + 9216 + 32;
+    const size_t fc_bytes = (size_t)3 * TCF_KBLOCKS * TCF_B_BYTES;
+    std::vector<uint8_t> h(2 * (size_t)TCC_WBYTES + fc_bytes);
+    uint16_t *p2 = reinterpret_cast<uint16_t *>(h.data()), *p3 = reinterpret_cast<uint16_t *>(h.data() + TCC_WBYTES);
+    uint16_t *pf = reinterpret_cast<uint16_t *>(h.data() + 2 * (size_t)TCC_WBYTES);
+    for (int layer = 0; layer < 2; ++layer) {
+        const float *cw = layer ? c3w : c2w;
+        uint16_t *dst = layer ? p3 : p2;
+        for (int tap = 0; tap < 9; ++tap)
+            for (int hh = 0; hh < 2; ++hh)
+                for (int c2 = 0; c2 < 2; ++c2)
+                    for (int n = 0; n < 32; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            int ci = 16 * hh + 8 * c2 + e;
+                            uint16_t s3[3];
+                            host_split3(cw[(n * 32 + ci) * 9 + tap], s3);
+                            for (int s = 0; s < 3; ++s) dst[((((size_t)(tap * 2 + hh)) * 2 + c2) * 96 + s * 32 + n) * 8 + e] = s3[s];
+                        }
+    }
+    for (int j = 0; j < TCF_KBLOCKS; ++j)
+        for (int c2 = 0; c2 < 2; ++c2)
+            for (int n = 0; n < 256; ++n)
+                for (int e = 0; e < 8; ++e) {
+                    int kp = j * 16 + c2 * 8 + e, p = kp >> 5, c = kp & 31;      // k' = pixel*32 + channel, pixel = y*4 + x
+                    uint16_t s3[3];
+                    host_split3(f1w[(size_t)n * 1792 + c * 56 + p], s3);
+                    for (int s = 0; s < 3; ++s) pf[((((size_t)s * TCF_KBLOCKS + j) * 2 + c2) * 256 + n) * 8 + e] = s3[s];
+                }
+    if (!st->d_w && cudaMalloc(&st->d_w, h.size()) != cudaSuccess) return 1;
+    if (cudaMemcpyAsync(st->d_w, h.data(), h.size(), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+    st->TW.wc2 = st->d_w; st->TW.wc3 = st->d_w + TCC_WBYTES; st->TW.wfc = st->d_w + 2 * (size_t)TCC_WBYTES;
+    if (cudaFuncSetAttribute(k_tc_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, TCC_SMEM) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(k_tc_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM) != cudaSuccess) return 1;
+    return 0;
+}
+
+static int tc_ensure_act3(TcState *st, size_t max_rows, cudaStream_t stream) {
+    size_t tiles = (max_rows + 127) / 128;
+    if (st->tiles >= tiles) return 0;
+    if (st->d_act3) { cudaStreamSynchronize(stream); cudaFree(st->d_act3); st->d_act3 = nullptr; }
+    size_t bytes = (size_t)3 * tiles * ACT3_KCHUNKS * 2048;
+    if (cudaMalloc(&st->d_act3, bytes) != cudaSuccess) return 1;
+    cudaMemsetAsync(st->d_act3, 0, bytes, stream);
+    st->tiles = tiles;
+    return 0;
+}
+
+static void tc_destroy(void *state) {
+    TcState *st = (TcState *)state;
+    if (!st) return;
+    cudaFree(st->d_w); cudaFree(st->d_act3);
+    delete st;
+}
+
+}  // namespace b200
