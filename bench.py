@@ -263,6 +263,18 @@ def run_b200(args, cfg):
     D.barrier()
     e1 = eng.counters()
     e2e_sims = D.sum_over_ranks({"sims": e1["sims"] - e0["sims"]}, dev)["sims"]
+    # ---- the one exchange step: all-gather of fixed-size replay-sample blocks (212-byte rows), outside the timed regions
+    cap = 65536
+    block = torch.zeros((cap, D.SAMPLE_BYTES), dtype=torch.uint8, device=dev)
+    n_local = eng.collect_samples_into(block.data_ptr(), cap, 25)          # ValueSimLP.py:11 min_visits_to_store=25
+    torch.cuda.synchronize()
+    D.barrier()
+    tg = time.perf_counter()
+    rows, counts = D.allgather_samples(block, n_local)
+    torch.cuda.synchronize()
+    tg = D.max_over_ranks(time.perf_counter() - tg, dev)
+    traj = {"samples_total": int(rows.shape[0]), "samples_per_rank": counts, "block_bytes_per_rank": cap * D.SAMPLE_BYTES,
+            "ms": tg * 1e3, "backend": "nccl" if world > 1 else "none"}
     launches = sum(n for _, n in phases.values())
     peaks = measured_peaks()
     out = None
@@ -313,7 +325,7 @@ def run_b200(args, cfg):
                "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": config, "roofline": roof, "roofline_select_backup": roof_tree, "cpu_baseline": cpu,
                "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": G * 80 * world, "d2h_bytes_per_step": G * (4 + 84 + 80) * world},
-               "gpu_launches": int(launches), "clocks": clk.summary(),
+               "gpu_launches": int(launches), "clocks": clk.summary(), "trajectory_allgather": traj,
                "phases_ms_per_step": {k: v[0] / steps for k, v in phases.items()},
                "counters_per_step": {k: v / steps for k, v in delta.items()}}
     eng.close()

@@ -1,5 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_valuenet.py -x -q -m gpu 2>&1 | tail -12
-timeout 600 python scripts/exp_growth.py 16384 16384 500 4 net_tc 2>&1 | tail -6
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_tc.json 2> gpurun_out/bench_r1_tc.err; tail -c 3500 gpurun_out/bench_r1_tc.json; tail -5 gpurun_out/bench_r1_tc.err
