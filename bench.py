@@ -31,6 +31,15 @@ ENV_ARGS = ((20, 10), 1, 0, 0)                   # play.py:75 defaults
 BASE_SEED = 123                                  # SURVEY §8d (echoes agent.cpp:23)
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -288,7 +297,9 @@ def run_b200(args, cfg):
         tree_s = (sel_ms + bk_ms) / 1e3
         if tree_s > 0:
             ach = tree_bytes / tree_s / 1e9
-            roof_tree = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+            tr_s, tr_b = ncu_traffic("k_select_expand"), ncu_traffic("k_backup")
+            roof_tree = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                         "traffic": (tr_s + tr_b) if tr_s and tr_b else None, "algorithmic_bytes_per_launch_pair": tree_bytes / max(sel_n, 1),
                          "kernels": "k_select_expand + k_backup", "mean_trace_len": D_mean, "ms_per_launch_pair": (sel_ms + bk_ms) / max(sel_n, 1),
                          "peak_src": peaks["src"]}
         if cfg["mode"] != "vanilla":
@@ -297,8 +308,9 @@ def run_b200(args, cfg):
             boards = delta["eval_requests"]
             if conv_ms > 0 and conv_n > 0:
                 ach = boards * CONV_FLOP / (conv_ms / 1e3) / 1e12
-                roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
-                        "kernel": "k_vn_conv" if cfg["eval"] == "net" else "k_tc_conv", "mma_flops_issued_per_launch": boards * 2 * 128 * 16 * (96 + 64 + 32) * 18 * 2 / conv_n, "ms_per_launch": conv_ms / conv_n,
+                kname = "k_vn_conv" if cfg["eval"] == "net" else "k_tc_conv"
+                roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
+                        "traffic": ncu_traffic(kname), "kernel": kname, "mma_flops_issued_per_launch": boards * 2 * 128 * 16 * (96 + 64 + 32) * 18 * 2 / conv_n, "ms_per_launch": conv_ms / conv_n,
                         "flops_per_launch": boards * CONV_FLOP / conv_n, "boards_per_launch": boards / conv_n,
                         "fc_kernel_tflops": boards * FC_FLOP / (fc_ms / 1e3) / 1e12 if fc_ms > 0 else None,
                         "share_of_step": conv_ms / ms, "peak_src": peaks["src"] + " bf16 dense, sustained",
