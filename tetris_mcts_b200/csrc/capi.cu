@@ -375,7 +375,7 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
         }
         {
             PhaseTimer t(e, PH_BACKUP);
-            k_backup<<<(G + 127) / 128, 128, 0, e->stream>>>(A);
+            k_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
         }
     }
     CK(cudaGetLastError());

@@ -403,40 +403,99 @@ __global__ void k_rollout(Arena A) {
     atomicAdd(&A.counters[5], (unsigned long long)steps);
 }
 
-// ---------------------------------------------------------------- backup (core.h:226-381), one thread per game
-__global__ void k_backup(Arena A) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
+// ---------------------------------------------------------------- backup (core.h:226-381), one warp per game
+// The reference walks the trace leaf -> root with two dependent gathers per level.  Here the 32 lanes of a warp fetch
+// 32 levels at once (node meta, then statistics: three memory latencies per 32 levels instead of per level), the
+// Welford recurrence then runs lane to lane in registers in exactly the reference's order (same welford_level code,
+// v carried in double), and the statistics are written back in parallel.  If an observation occurs twice among the
+// levels in flight (statistics are shared between nodes, agent.py:116-128) the warp falls back to the scalar walk.
+__global__ void __launch_bounds__(128) k_backup(Arena A) {
+    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (g >= A.G || A.status[g] != ST_OK) return;
     ArenaAcc acc{A, g};
-    int D = A.trace_len[g];
-    int leaf = acc.get_trace(D - 1);
-    int kind = A.leaf_kind[g];
+    const int D = A.trace_len[g];
+    const int kind = A.leaf_kind[g];
+    if (kind == LEAF_SUSPENDED || D <= 0) return;
+    const int leaf = acc.get_trace(D - 1);
     int lo; float leaf_score;
     acc.meta(leaf, lo, leaf_score);
+    double v = (double)leaf_score, var = 0.0;
     if (A.mode == MODE_LP) {
-        int c_nodes[7], c_obs[7], slot[7]; float c_score[7], ev[7], evar[7]; bool cend[7];
-        int k = 0;
         if (kind == LEAF_EXPANDED) {
-            k = unique_scalar(acc, leaf, c_nodes, c_obs, c_score, slot);
-            for (int i = 0; i < k; ++i) {
-                float2 e = A.eval_out[(size_t)g * 8 + slot[i]];
-                ev[i] = e.x; evar[i] = e.y;
-                cend[i] = A.lp_end_from_obs ? (A.stat[node_at(A, g, c_obs[i])].w != 0) : false;
+            // core.h:340-366: initialise unvisited unique children, then average score + gamma*value and the variances
+            Grp gp;                                   // lanes 0-7 of the warp form the group that holds the 7 child slots
+            int c = 0, o = 0; float s = 0.f;
+            if (lane < 8) acc.children(leaf, lane, c, o, s);
+            double v_tmp = 0.0, var_tmp = 0.0;
+            int k = 0;
+            if (lane < 8) {
+                Uniq u = unique_children(gp, c, o, s);
+                int4 st = make_int4(0, 0, 0, 0);
+                if (u.is_first) {
+                    st = acc.stat(o);
+                    if (st.x == 0) {                                           // core.h:344-353
+                        float2 e = A.eval_out[(size_t)g * 8 + lane];
+                        bool cend = A.lp_end_from_obs ? (st.w != 0) : false;
+                        st.x = 1; st.y = __float_as_int(cend ? 0.f : e.x); st.z = __float_as_int(cend ? 0.f : e.y);
+                        acc.set_stat(o, st);
+                    }
+                }
+                k = __popc(u.first_mask);
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {                                  // list order = slot order of first occurrences
+                    float sj = gp.bcast(u.rep_s, j), valj = gp.bcast(__int_as_float(st.y), j), s2j = gp.bcast(__int_as_float(st.z), j);
+                    if ((u.first_mask >> j) & 1u) {
+                        v_tmp = __dadd_rn(v_tmp, __dadd_rn((double)sj, __dmul_rn(A.gamma, (double)valj)));   // core.h:355
+                        var_tmp = __dadd_rn(var_tmp, (double)s2j);
+                    }
+                }
             }
+            k = __shfl_sync(0xffffffffu, k, 0);
+            v_tmp = __shfl_sync(0xffffffffu, v_tmp, 0);
+            var_tmp = __shfl_sync(0xffffffffu, var_tmp, 0);
+            v = __ddiv_rn(v_tmp, (double)k);                                   // core.h:364
+            if (A.lp_var_gamma2) var = __dmul_rn(var_tmp, __ddiv_rn(__dmul_rn(A.gamma, A.gamma), (double)k));   // core.h:365
+            else { var = __ddiv_rn(var_tmp, (double)k); v = (double)(float)v; var = (double)(float)var; }        // agent.cpp:557-562
+            __syncwarp();
         }
-        lp_backup(acc, D, k, c_obs, c_score, ev, evar, cend, A.gamma, false, true, A.lp_var_gamma2 != 0, leaf_score);
     } else if (A.mode == MODE_SINGLE) {
-        double v = (double)leaf_score, var = 0.0;
         if (kind == LEAF_EXPANDED) {
             float2 e = A.eval_out[(size_t)g * 8 + 7];
             v = (double)__fadd_rn(leaf_score, e.x);      // ValueSim.py:86 int + np.float32 -> float32 (numpy >= 2)
             var = (double)e.y;
         }
-        backup_trace(acc, D, v, var, A.gamma);
-    } else {
-        double v = (double)leaf_score, var = 0.0;
-        if (kind == LEAF_EXPANDED) { v = (double)A.rollout_val[g]; var = A.rollout_variance; }   // Vanilla.py:53-54
-        backup_trace(acc, D, v, var, A.gamma);
+    } else if (kind == LEAF_EXPANDED) {
+        v = (double)A.rollout_val[g]; var = A.rollout_variance;                // Vanilla.py:53-54
+    }
+    // ---- core.h:244-259 along the trace, 32 levels per round
+    for (int top = D - 1; top >= 0; top -= 32) {
+        const int n = top + 1 < 32 ? top + 1 : 32;      // levels top, top-1, ..., top-n+1 -> lanes 0..n-1
+        int o = -1 - lane; float sc = 0.f; int4 st = make_int4(0, 0, 0, 0);
+        if (lane < n) { acc.meta(acc.get_trace(top - lane), o, sc); }
+        bool dup = __popc(__match_any_sync(0xffffffffu, o)) > 1;
+        if (__any_sync(0xffffffffu, dup)) {             // shared observation inside the window: scalar walk for this window
+            if (lane == 0) {
+                for (int i = top; i > top - n; --i) {
+                    int oo; float ss;
+                    acc.meta(acc.get_trace(i), oo, ss);
+                    int4 s2 = acc.stat(oo);
+                    welford_level(s2, v, var, ss, A.gamma);
+                    acc.set_stat(oo, s2);
+                }
+            }
+            v = __shfl_sync(0xffffffffu, v, 0);
+            __syncwarp();
+            continue;
+        }
+        if (lane < n) st = acc.stat(o);
+        for (int j = 0; j < n; ++j) {
+            double vin = __shfl_sync(0xffffffffu, v, j == 0 ? 0 : j - 1);     // v after level j-1 lives in lane j-1 (lane 0 initially)
+            if (lane == j) { if (j > 0) v = vin; welford_level(st, v, var, sc, A.gamma); }
+        }
+        if (lane < n) acc.set_stat(o, st);
+        v = __shfl_sync(0xffffffffu, v, n - 1);
+        __syncwarp();
     }
 }
 
