@@ -576,19 +576,19 @@ extern "C" int b200_debug_act3(b200_engine *e, const int8_t *states, int k, floa
 #ifdef B200_WITH_TC
     if (e->cfg.eval_kind == B200_EVAL_NET_TC) {
         TcState *st = (TcState *)e->tc_state;
-        size_t bytes = (size_t)3 * st->tiles * ACT3_KCHUNKS * 2048;
+        size_t bytes = (size_t)2 * st->tiles * ACT3_KCHUNKS * 2048;
         std::vector<uint8_t> h(bytes);
         CK(cudaMemcpy(h.data(), st->d_act3, bytes, cudaMemcpyDeviceToHost));
         for (int r = 0; r < k; ++r)
             for (int kp = 0; kp < 1792; ++kp) {
                 int p = kp >> 5, c = kp & 31;
                 float sum = 0.f;
-                for (int s = 2; s >= 0; --s) {
+                for (int s = 1; s >= 0; --s) {
                     size_t off = ((((size_t)s * st->tiles + (r >> 7)) * ACT3_KCHUNKS + (kp >> 3)) * 128 + (r & 127)) * 16 + (kp & 7) * 2;
                     uint16_t hb; memcpy(&hb, &h[off], 2);
-                    sum += host_bf16_f(hb);
+                    sum += host_half_f(hb);
                 }
-                out[(size_t)r * 1792 + c * 56 + p] = sum;
+                out[(size_t)r * 1792 + c * 56 + p] = sum / TC_SCALE_A;
             }
         return B200_OK;
     }

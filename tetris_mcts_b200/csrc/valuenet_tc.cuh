@@ -1,10 +1,10 @@
 // valuenet_tc.cuh — the reference value network (model/model_vv.py:13-52) on Blackwell tensor cores (sm_100a).
 //
-// Precision: north_star asks value outputs within 1e-5 of the reference's fp32.  Plain bf16/tf32 MMAs cannot reach
-// that, so every fp32 operand x is split into three bf16 terms x = x1 + x2 + x3 (24 mantissa bits kept) and each
-// product a*b is accumulated in fp32 (TMEM) as a1b3 + a3b1 + a2b2 + a1b2 + a2b1 + a1b1 (smallest terms first; the
-// dropped terms are < 2^-24 relative).  Six bf16 MMAs replace one fp32 product: the tensor pipe still beats the
-// CUDA-core path by ~5x end to end.
+// Precision: north_star asks value outputs within 1e-5 of the reference's fp32.  Plain bf16/tf32/fp16 MMAs cannot
+// reach that, so every fp32 operand x is split into two fp16 terms x = x1 + x2 (11 + 11 = 22 mantissa bits, the
+// precision class of 3xTF32) and each product a*b is accumulated in fp32 (TMEM) as a1*b2 + a2*b1 + a1*b1 (the dropped
+// a2*b2 is < 2^-22 relative).  Operands are pre-scaled by exact powers of two (activations x16, weights x64) so that the
+// low terms stay in fp16's normal range; the epilogues undo the 2^10.  Three fp16 MMAs replace one fp32 product.
 //
 //   k_tc_conv  one persistent CTA per SM, two boards in flight (ping-pong):
 //              decode obs key -> conv1 on CUDA cores (K = 9 is too small for an MMA) -> split -> smem
@@ -13,13 +13,13 @@
 //              started (dy*W+dx) rows later — a canonical no-swizzle K-major UMMA layout with SBO = 128 B,
 //              LBO = rows*16 B.  tcgen05.mma (M=128 pixels, N=32 couts, K=16) issued by one thread, accumulators
 //              in TMEM, completion through tcgen05.commit -> mbarrier; epilogues read TMEM with tcgen05.ld, apply
-//              bias+ReLU, re-split and write the next layer's operand (or act3 to HBM in the FC kernel's tile layout).
+//              bias+ReLU, re-split (fp16 x2) and write the next layer's operand (or act3 to HBM in the FC kernel's tile layout).
 //   k_tc_fc    [R,1792] x [1792,256]: 128-row tiles, operands streamed by cp.async.bulk (1-D TMA) into a 5-stage
 //              mbarrier ring — both operands are stored in HBM already in the canonical UMMA layout, so one bulk copy
 //              per operand block needs no tensor map; warp-specialised (producer / MMA issuer / 4 epilogue warps);
 //              epilogue fuses bias+ReLU+fc_out+sigmoid+affine and scatters (v, var) to the requesting tree slot.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "search_dev.cuh"
 #include "valuenet_simt.cuh"
 
@@ -72,11 +72,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {   // whole warp
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=fp16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+constexpr float TC_SCALE_A = 16.f, TC_SCALE_W = 64.f, TC_UNSCALE = 1.f / 1024.f;
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -98,50 +99,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {   //
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// accumulator blocks a*W1 | a*W2 | a*W3 sit 32 columns apart: add them smallest first
-__device__ __forceinline__ void tmem_ld16_sum3(uint32_t taddr, float (&v)[16]) {
-    float w1[16], w2[16], w3[16];
-    tmem_ld16(taddr + 64, w3);
+// accumulator blocks a*W1 | a*W2 sit 32 columns apart: add the small one first, undo the operand scaling
+__device__ __forceinline__ void tmem_ld16_sum2(uint32_t taddr, float (&v)[16]) {
+    float w1[16], w2[16];
     tmem_ld16(taddr + 32, w2);
     tmem_ld16(taddr, w1);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = (w3[i] + w2[i]) + w1[i];
+    for (int i = 0; i < 16; ++i) v[i] = (w2[i] + w1[i]) * TC_UNSCALE;
 }
 
-// x = x1 + x2 + x3 with bf16 terms (round-to-nearest each step); returned as three 16-bit patterns
-__device__ __forceinline__ void split3(float x, uint32_t &h1, uint32_t &h2, uint32_t &h3) {
-    __nv_bfloat16 b1 = __float2bfloat16_rn(x);
-    float r1 = x - __bfloat162float(b1);
-    __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
-    float r2 = r1 - __bfloat162float(b2);
-    __nv_bfloat16 b3 = __float2bfloat16_rn(r2);
-    h1 = __bfloat16_as_ushort(b1); h2 = __bfloat16_as_ushort(b2); h3 = __bfloat16_as_ushort(b3);
-}
-// eight fp32 values -> three 16-byte chunks (one per split)
-__device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2, uint4 &c3) {
-    uint32_t a[8], b[8], c[8];
+// x = x1 + x2 with fp16 terms (round-to-nearest each step); eight fp32 values -> two 16-byte chunks (one per split)
+__device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2) {
+    uint32_t a[8], b[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split3(x[i], a[i], b[i], c[i]);
+    for (int i = 0; i < 8; ++i) {
+        __half h1 = __float2half_rn(x[i]);
+        __half h2 = __float2half_rn(x[i] - __half2float(h1));
+        a[i] = __half_as_ushort(h1); b[i] = __half_as_ushort(h2);
+    }
     c1 = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
     c2 = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
-    c3 = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
 }
-
-// product terms in accumulation order: (A split, B split), smallest magnitude first
-__device__ __constant__ int TC_TERM_A[6] = {0, 2, 1, 0, 1, 0};
-__device__ __constant__ int TC_TERM_B[6] = {2, 0, 1, 1, 0, 0};
-__host__ __device__ constexpr int tc_term_a(int t) { return t == 0 ? 0 : t == 1 ? 2 : t == 2 ? 1 : t == 3 ? 0 : t == 4 ? 1 : 0; }
-__host__ __device__ constexpr int tc_term_b(int t) { return t == 0 ? 2 : t == 1 ? 0 : t == 2 ? 1 : t == 3 ? 1 : t == 4 ? 0 : 0; }
 
 // ---------------------------------------------------------------------------------------------------- conv kernel
 constexpr int TCC_WORKERS = 256;            // warps 0-7: decode, conv1, epilogues
 constexpr int TCC_THREADS = TCC_WORKERS + 32;   // warp 8: MMA issuer (one elected lane)
 constexpr int TCC_R1 = 152;                 // act1 rows per board: 18x8 grid = 144 (+8: tap shifts read up to row 145)
 constexpr int TCC_R2 = 144;                 // act2 rows per board: 16x6 grid = 96 (+48: M=128 tile + shifts read up to row 141)
-constexpr int TCC_WBLOCK = 2 * 96 * 16;      // one (tap, half) block: [chunk 2][n = split*32 + cout][16 B]
-constexpr int TCC_WBYTES = 18 * TCC_WBLOCK;  // one conv layer = 55296 B
-constexpr int TCC_A1 = 3 * 4 * TCC_R1 * 16; // act1 of one board slot: [split][chunk 4][row][16 B]
-constexpr int TCC_A2 = 3 * 4 * TCC_R2 * 16;
+constexpr int TCC_WBLOCK = 2 * 64 * 16;      // one (tap, half) block: [chunk 2][n = split*32 + cout][16 B]
+constexpr int TCC_WBYTES = 18 * TCC_WBLOCK;  // one conv layer = 36864 B
+constexpr int TCC_A1 = 2 * 4 * TCC_R1 * 16; // act1 of one board slot: [split][chunk 4][row][16 B]
+constexpr int TCC_A2 = 2 * 4 * TCC_R2 * 16;
 constexpr int TCC_OFF_W2 = 0;
 constexpr int TCC_OFF_W3 = TCC_OFF_W2 + TCC_WBYTES;
 constexpr int TCC_OFF_A1 = TCC_OFF_W3 + TCC_WBYTES;
@@ -151,7 +139,7 @@ constexpr int TCC_OFF_W1 = TCC_OFF_IN + 2 * 200 * 4;       // 288 floats + 96 fl
 constexpr int TCC_OFF_KEY = TCC_OFF_W1 + (288 + 96) * 4;   // 2 x 12 key words of the current pair
 constexpr int TCC_OFF_BAR = TCC_OFF_KEY + 2 * 12 * 4;      // 8 mbarriers + tmem pointer
 constexpr int TCC_SMEM = TCC_OFF_BAR + 80;
-constexpr int TCC_TMEM_COLS = 512;          // 2 slots x 2 layers x 96 columns (three partial sums of 32 couts) = 384 -> 512
+constexpr int TCC_TMEM_COLS = 256;          // 2 slots x 2 layers x 64 columns (two partial sums of 32 couts)
 constexpr int ACT3_KCHUNKS = 224;           // 1792 / 8
 
 struct TcWeights {
@@ -166,25 +154,24 @@ __device__ __forceinline__ size_t act3_off(int split, int n_tiles, int ridx, int
 
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// One 3x3 convolution layer as 54 tcgen05.mma (9 taps x 2 halves of the 32 input channels x 3 activation splits).
-// The operand fetch of an SS-mode MMA is shared-memory bound (~64 B/clk), so the three weight splits are stacked along
-// N: activation split 1 meets [W1;W2;W3] (N=96), split 2 meets [W1;W2] (N=64), split 3 meets W1 (N=32).  The six
-// products land in three 32-column accumulator blocks (a*W1 | a*W2 | a*W3) that the epilogue adds, smallest first.
+// One 3x3 convolution layer as 36 tcgen05.mma (9 taps x 2 halves of the 32 input channels x 2 activation splits).
+// The operand fetch of an SS-mode MMA is shared-memory bound (~64 B/clk measured), so the two weight splits are stacked
+// along N: activation split 1 meets [W1;W2] (N=64), split 2 meets W1 (N=32).  The three products land in two 32-column
+// accumulator blocks (a*W1 | a*W2) that the epilogue adds.
 //   R = rows per operand chunk, WGRID = width of the pixel grid the operand is stored on (tap shift = dy*WGRID + dx)
 template <int R, int WGRID>
 __device__ __forceinline__ void issue_conv_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
-    const uint64_t a0 = umma_desc(a_addr, R * 16, 128), b0 = umma_desc(w_addr, 96 * 16, 128);
+    const uint64_t a0 = umma_desc(a_addr, R * 16, 128), b0 = umma_desc(w_addr, 64 * 16, 128);
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int sa = 0; sa < 3; ++sa) {
+            for (int sa = 0; sa < 2; ++sa) {
                 const uint32_t a_off = sa * 4 * R + 2 * h * R + (tap / 3) * WGRID + (tap % 3);   // 16-byte units
                 const uint32_t b_off = (tap * 2 + h) * (TCC_WBLOCK / 16);
-                // split sa of the activations only needs weight splits 0 .. 2-sa (N = 96, 64, 32); the first k block
-                // initialises the columns it covers: sa=0 covers all 96, so later ones always accumulate
-                umma_bf16(tmem_d, a0 + a_off, b0 + b_off, umma_idesc_bf16(128, 96 - 32 * sa), (tap | h | sa) ? 1u : 0u);
+                // the first MMA (sa = 0, N = 64) initialises both accumulator blocks; everything after accumulates
+                umma_f16(tmem_d, a0 + a_off, b0 + b_off, umma_idesc_f16(128, 64 - 32 * sa), (tap | h | sa) ? 1u : 0u);
             }
         }
     }
@@ -241,7 +228,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                         mbar_wait(&bar_a1[slot], phase);
                         PROF_T(6);
                         tc_fence_after();
-                        issue_conv_layer<TCC_R1, 8>(tmem_base + slot * 192, s_a1 + slot * TCC_A1, s_w2);
+                        issue_conv_layer<TCC_R1, 8>(tmem_base + slot * 128, s_a1 + slot * TCC_A1, s_w2);
                         umma_commit(&bar_c2[slot]);
                         PROF_T(7);
                     }
@@ -249,7 +236,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                         mbar_wait(&bar_a2[slot], phase);
                         PROF_T(8);
                         tc_fence_after();
-                        issue_conv_layer<TCC_R2, 6>(tmem_base + slot * 192 + 96, s_a2 + slot * TCC_A2, s_w3);
+                        issue_conv_layer<TCC_R2, 6>(tmem_base + slot * 128 + 64, s_a2 + slot * TCC_A2, s_w3);
                         umma_commit(&bar_c3[slot]);
                         PROF_T(9);
                     }
@@ -314,13 +301,12 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                                 acc[4] = fmaf(in, wb.x, acc[4]); acc[5] = fmaf(in, wb.y, acc[5]); acc[6] = fmaf(in, wb.z, acc[6]); acc[7] = fmaf(in, wb.w, acc[7]);
                             }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-                        uint4 c1, c2, c3;
-                        split8(acc, c1, c2, c3);
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f) * TC_SCALE_A;
+                        uint4 c1, c2;
+                        split8(acc, c1, c2);
                         uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_A1 + (cq * TCC_R1 + pix) * 16;
                         *reinterpret_cast<uint4 *>(base) = c1;
                         *reinterpret_cast<uint4 *>(base + 4 * TCC_R1 * 16) = c2;
-                        *reinterpret_cast<uint4 *>(base + 8 * TCC_R1 * 16) = c3;
                     }
                     tc_fence_before();          // orders this thread's earlier tcgen05.ld of the slot's accumulators
                     fence_async_smem();
@@ -334,7 +320,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     PROF_T(2);
                     tc_fence_after();
                     float v[16];
-                    tmem_ld16_sum3(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 192 + half * 16, v);
+                    tmem_ld16_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + half * 16, v);
                     const int y = m >> 3, x = m & 7;
                     if (x < 6) {
                         const int r = y * 6 + x;
@@ -342,13 +328,12 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                         for (int c2 = 0; c2 < 2; ++c2) {
                             float o[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[32 + half * 16 + c2 * 8 + j], 0.f);
-                            uint4 c1, cc2, c3;
-                            split8(o, c1, cc2, c3);
+                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[32 + half * 16 + c2 * 8 + j], 0.f) * TC_SCALE_A;
+                            uint4 c1, cc2;
+                            split8(o, c1, cc2);
                             uint8_t *base = smem + TCC_OFF_A2 + slot * TCC_A2 + ((half * 2 + c2) * TCC_R2 + r) * 16;
                             *reinterpret_cast<uint4 *>(base) = c1;
                             *reinterpret_cast<uint4 *>(base + 4 * TCC_R2 * 16) = cc2;
-                            *reinterpret_cast<uint4 *>(base + 8 * TCC_R2 * 16) = c3;
                         }
                     }
                     tc_fence_before();
@@ -364,20 +349,19 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     const int ridx = pair * 2 + slot;
                     const int y = m / 6, x = m - y * 6;
                     float v[16];
-                    tmem_ld16_sum3(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 192 + 96 + half * 16, v);
+                    tmem_ld16_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + 64 + half * 16, v);
                     if (m < 84 && x < 4 && ridx < n_req) {
                         const int p = y * 4 + x;
 #pragma unroll
                         for (int c2 = 0; c2 < 2; ++c2) {
                             float o[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[64 + half * 16 + c2 * 8 + j], 0.f);
-                            uint4 c1, cc2, c3;
-                            split8(o, c1, cc2, c3);
+                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[64 + half * 16 + c2 * 8 + j], 0.f) * TC_SCALE_A;
+                            uint4 c1, cc2;
+                            split8(o, c1, cc2);
                             const int kc = p * 4 + half * 2 + c2;
                             *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
                             *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = cc2;
-                            *reinterpret_cast<uint4 *>(act3 + act3_off(2, n_tiles, ridx, kc)) = c3;
                         }
                     }
                     PROF_T(5);
@@ -394,13 +378,14 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
 
 // ---------------------------------------------------------------------------------------------------- fc kernel
 constexpr int TCF_THREADS = 192;            // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
-constexpr int TCF_STAGES = 5;
+constexpr int TCF_STAGES = 8;
 constexpr int TCF_A_BYTES = 2 * 128 * 16;   // one split of one k16 block of the A tile
 constexpr int TCF_B_BYTES = 2 * 256 * 16;
-constexpr int TCF_STAGE = 3 * TCF_A_BYTES + 3 * TCF_B_BYTES;   // 36864
+constexpr int TCF_STAGE = 2 * TCF_A_BYTES + 2 * TCF_B_BYTES;   // 24576
 constexpr int TCF_KBLOCKS = 112;            // 1792 / 16
 constexpr int TCF_OFF_BAR = TCF_STAGES * TCF_STAGE;
-constexpr int TCF_OFF_EPI = TCF_OFF_BAR + 128;                 // bias[256] | wout[2][256] | bout/ub/lb
+constexpr int TCF_OFF_EPI = TCF_OFF_BAR + 256;                 // (2*stages + 2 mbarriers + tmem ptr fit in 256 B) bias[256] | wout[2][256] | bout/ub/lb
+static_assert((2 * TCF_STAGES + 2) * 8 + 4 <= 256, "barrier block overflows into the epilogue constants");
 constexpr int TCF_SMEM = TCF_OFF_EPI + (256 * 3 + 8) * 4;
 constexpr int TCF_TMEM_COLS = 256;
 
@@ -438,9 +423,9 @@ k_tc_fc(NetWeights W, TcWeights TW, const uint8_t *act3, int n_tiles_alloc, cons
                     mbar_expect_tx(&full[stage], TCF_STAGE);
                     uint8_t *dst = smem + stage * TCF_STAGE;
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) {
+                    for (int s = 0; s < 2; ++s) {
                         bulk_g2s(dst + s * TCF_A_BYTES, act3 + (((size_t)s * n_tiles_alloc + tile) * ACT3_KCHUNKS + 2 * j) * 2048, TCF_A_BYTES, &full[stage]);
-                        bulk_g2s(dst + 3 * TCF_A_BYTES + s * TCF_B_BYTES, TW.wfc + ((size_t)s * TCF_KBLOCKS + j) * TCF_B_BYTES, TCF_B_BYTES, &full[stage]);
+                        bulk_g2s(dst + 2 * TCF_A_BYTES + s * TCF_B_BYTES, TW.wfc + ((size_t)s * TCF_KBLOCKS + j) * TCF_B_BYTES, TCF_B_BYTES, &full[stage]);
                     }
                     if (++stage == TCF_STAGES) { stage = 0; ph ^= 1; }
                 }
@@ -448,7 +433,7 @@ k_tc_fc(NetWeights W, TcWeights TW, const uint8_t *act3, int n_tiles_alloc, cons
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ===== MMA issuer: D[128 x 256] += A[128 x 16] * B[256 x 16]^T, six split terms per k block
-            const uint32_t idesc = umma_idesc_bf16(128, 256);
+            const uint32_t idesc = umma_idesc_f16(128, 256);
             int stage = 0; uint32_t ph = 0, aph = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 mbar_wait(acc_empty, aph ^ 1);
@@ -459,10 +444,11 @@ k_tc_fc(NetWeights W, TcWeights TW, const uint8_t *act3, int n_tiles_alloc, cons
                     tc_fence_after();
                     const uint32_t sbase = smem_u32(smem + stage * TCF_STAGE);
 #pragma unroll
-                    for (int term = 0; term < 6; ++term) {
-                        uint64_t ad = umma_desc(sbase + TC_TERM_A[term] * TCF_A_BYTES, 128 * 16, 128);
-                        uint64_t bd = umma_desc(sbase + 3 * TCF_A_BYTES + TC_TERM_B[term] * TCF_B_BYTES, 256 * 16, 128);
-                        umma_bf16(tmem_base, ad, bd, idesc, acc);
+                    for (int term = 0; term < 3; ++term) {   // a1*b2, a2*b1, a1*b1 (small terms first)
+                        const int sa = term == 1 ? 1 : 0, sb = term == 0 ? 1 : 0;
+                        uint64_t ad = umma_desc(sbase + sa * TCF_A_BYTES, 128 * 16, 128);
+                        uint64_t bd = umma_desc(sbase + 2 * TCF_A_BYTES + sb * TCF_B_BYTES, 256 * 16, 128);
+                        umma_f16(tmem_base, ad, bd, idesc, acc);
                         acc = 1;
                     }
                     umma_commit(&empty[stage]);
@@ -485,7 +471,7 @@ k_tc_fc(NetWeights W, TcWeights TW, const uint8_t *act3, int n_tiles_alloc, cons
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float h = fmaxf(v[j] + sBias[c0 + j], 0.f);                 // model_vv.py:39-40
+                    float h = fmaxf(v[j] * TC_UNSCALE + sBias[c0 + j], 0.f);   // model_vv.py:39-40
                     p0 = fmaf(h, sWo[c0 + j], p0); p1 = fmaf(h, sWo[256 + c0 + j], p1);   // :41
                 }
             }
@@ -514,25 +500,19 @@ struct TcState {
     uint8_t *d_act3 = nullptr; size_t tiles = 0;
 };
 
-static inline uint16_t host_bf16_rn(float x) {
-    uint32_t u; memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
+static inline void host_split2(float x, uint16_t *o) {   // x*scale = h1 + h2 in fp16
+    __half h1 = __float2half_rn(x);
+    __half h2 = __float2half_rn(x - __half2float(h1));
+    memcpy(&o[0], &h1, 2); memcpy(&o[1], &h2, 2);
 }
-static inline float host_bf16_f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
-static inline void host_split3(float x, uint16_t *o) {
-    o[0] = host_bf16_rn(x); float r1 = x - host_bf16_f(o[0]);
-    o[1] = host_bf16_rn(r1); float r2 = r1 - host_bf16_f(o[1]);
-    o[2] = host_bf16_rn(r2);
-}
+static inline float host_half_f(uint16_t h) { __half x; memcpy(&x, &h, 2); return __half2float(x); }
 
 // w = the state_dict-order weight vector of include/b200_tetris_mcts.h.  Pure re-layout + bf16 splitting.
 static int tc_prepare(void **state, const float *w, cudaStream_t stream) {
     TcState *st = (TcState *)*state;
     if (!st) { st = new TcState(); *state = st; }
     const float *c2w = w + 288 + 32, *c3w = c2w + 9216 + 32, *f1w = c3w + 9216 + 32;
-    const size_t fc_bytes = (size_t)3 * TCF_KBLOCKS * TCF_B_BYTES;
+    const size_t fc_bytes = (size_t)2 * TCF_KBLOCKS * TCF_B_BYTES;
     std::vector<uint8_t> h(2 * (size_t)TCC_WBYTES + fc_bytes);
     uint16_t *p2 = reinterpret_cast<uint16_t *>(h.data()), *p3 = reinterpret_cast<uint16_t *>(h.data() + TCC_WBYTES);
     uint16_t *pf = reinterpret_cast<uint16_t *>(h.data() + 2 * (size_t)TCC_WBYTES);
@@ -545,9 +525,9 @@ static int tc_prepare(void **state, const float *w, cudaStream_t stream) {
                     for (int n = 0; n < 32; ++n)
                         for (int e = 0; e < 8; ++e) {
                             int ci = 16 * hh + 8 * c2 + e;
-                            uint16_t s3[3];
-                            host_split3(cw[(n * 32 + ci) * 9 + tap], s3);
-                            for (int s = 0; s < 3; ++s) dst[((((size_t)(tap * 2 + hh)) * 2 + c2) * 96 + s * 32 + n) * 8 + e] = s3[s];
+                            uint16_t s2[2];
+                            host_split2(cw[(n * 32 + ci) * 9 + tap] * TC_SCALE_W, s2);
+                            for (int s = 0; s < 2; ++s) dst[((((size_t)(tap * 2 + hh)) * 2 + c2) * 64 + s * 32 + n) * 8 + e] = s2[s];
                         }
     }
     for (int j = 0; j < TCF_KBLOCKS; ++j)
@@ -555,9 +535,9 @@ static int tc_prepare(void **state, const float *w, cudaStream_t stream) {
             for (int n = 0; n < 256; ++n)
                 for (int e = 0; e < 8; ++e) {
                     int kp = j * 16 + c2 * 8 + e, p = kp >> 5, c = kp & 31;      // k' = pixel*32 + channel, pixel = y*4 + x
-                    uint16_t s3[3];
-                    host_split3(f1w[(size_t)n * 1792 + c * 56 + p], s3);
-                    for (int s = 0; s < 3; ++s) pf[((((size_t)s * TCF_KBLOCKS + j) * 2 + c2) * 256 + n) * 8 + e] = s3[s];
+                    uint16_t s2[2];
+                    host_split2(f1w[(size_t)n * 1792 + c * 56 + p] * TC_SCALE_W, s2);
+                    for (int s = 0; s < 2; ++s) pf[((((size_t)s * TCF_KBLOCKS + j) * 2 + c2) * 256 + n) * 8 + e] = s2[s];
                 }
     if (!st->d_w && cudaMalloc(&st->d_w, h.size()) != cudaSuccess) return 1;
     if (cudaMemcpyAsync(st->d_w, h.data(), h.size(), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
@@ -572,7 +552,7 @@ static int tc_ensure_act3(TcState *st, size_t max_rows, cudaStream_t stream) {
     size_t tiles = (max_rows + 127) / 128;
     if (st->tiles >= tiles) return 0;
     if (st->d_act3) { cudaStreamSynchronize(stream); cudaFree(st->d_act3); st->d_act3 = nullptr; }
-    size_t bytes = (size_t)3 * tiles * ACT3_KCHUNKS * 2048;
+    size_t bytes = (size_t)2 * tiles * ACT3_KCHUNKS * 2048;
     if (cudaMalloc(&st->d_act3, bytes) != cudaSuccess) return 1;
     cudaMemsetAsync(st->d_act3, 0, bytes, stream);
     st->tiles = tiles;
