@@ -99,6 +99,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {   //
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8_sum2(uint32_t taddr, float (&v)[8]) {
+    float w1[8], w2[8];
+    tmem_ld8(taddr + 32, w2);
+    tmem_ld8(taddr, w1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (w2[i] + w1[i]) * TC_UNSCALE;
+}
+
 // accumulator blocks a*W1 | a*W2 sit 32 columns apart: add the small one first, undo the operand scaling
 __device__ __forceinline__ void tmem_ld16_sum2(uint32_t taddr, float (&v)[16]) {
     float w1[16], w2[16];
@@ -122,24 +138,25 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2
 }
 
 // ---------------------------------------------------------------------------------------------------- conv kernel
-constexpr int TCC_WORKERS = 256;            // warps 0-7: decode, conv1, epilogues
-constexpr int TCC_THREADS = TCC_WORKERS + 32;   // warp 8: MMA issuer (one elected lane)
+constexpr int TCC_WORKERS = 512;            // warps 0-15: decode, conv1, epilogues
+constexpr int TCC_ISSUER = TCC_WORKERS / 32; // warp 16: MMA issuer (one elected lane)
+constexpr int TCC_THREADS = TCC_WORKERS + 32;
 constexpr int TCC_R1 = 152;                 // act1 rows per board: 18x8 grid = 144 (+8: tap shifts read up to row 145)
 constexpr int TCC_R2 = 144;                 // act2 rows per board: 16x6 grid = 96 (+48: M=128 tile + shifts read up to row 141)
 constexpr int TCC_WBLOCK = 2 * 64 * 16;      // one (tap, half) block: [chunk 2][n = split*32 + cout][16 B]
 constexpr int TCC_WBYTES = 18 * TCC_WBLOCK;  // one conv layer = 36864 B
-constexpr int TCC_A1 = 2 * 4 * TCC_R1 * 16; // act1 of one board slot: [split][chunk 4][row][16 B]
-constexpr int TCC_A2 = 2 * 4 * TCC_R2 * 16;
+constexpr int TCC_SLOTS = 3;                // boards in flight
+constexpr int TCC_ASLOT = 2 * 4 * TCC_R1 * 16;   // operand buffer of one slot: act1 [split][chunk 4][152 rows][16 B], later overwritten
+                                                 // in place by act2 [split][chunk 4][144 rows][16 B] (conv2 has finished reading by then)
 constexpr int TCC_OFF_W2 = 0;
 constexpr int TCC_OFF_W3 = TCC_OFF_W2 + TCC_WBYTES;
 constexpr int TCC_OFF_A1 = TCC_OFF_W3 + TCC_WBYTES;
-constexpr int TCC_OFF_A2 = TCC_OFF_A1 + 2 * TCC_A1;
-constexpr int TCC_OFF_IN = TCC_OFF_A2 + 2 * TCC_A2;        // 2 x 200 floats
+constexpr int TCC_OFF_IN = TCC_OFF_A1 + TCC_SLOTS * TCC_ASLOT;   // 2 x 200 floats
 constexpr int TCC_OFF_W1 = TCC_OFF_IN + 2 * 200 * 4;       // 288 floats + 96 floats of biases
 constexpr int TCC_OFF_KEY = TCC_OFF_W1 + (288 + 96) * 4;   // 2 x 12 key words of the current pair
-constexpr int TCC_OFF_BAR = TCC_OFF_KEY + 2 * 12 * 4;      // 8 mbarriers + tmem pointer
-constexpr int TCC_SMEM = TCC_OFF_BAR + 80;
-constexpr int TCC_TMEM_COLS = 256;          // 2 slots x 2 layers x 64 columns (two partial sums of 32 couts)
+constexpr int TCC_OFF_BAR = TCC_OFF_KEY + 2 * 12 * 4;      // 4 x TCC_SLOTS mbarriers + tmem pointer
+constexpr int TCC_SMEM = TCC_OFF_BAR + 4 * TCC_SLOTS * 8 + 16;
+constexpr int TCC_TMEM_COLS = 512;          // 3 slots x 2 layers x 64 columns (two partial sums of 32 couts) = 384 -> 512
 constexpr int ACT3_KCHUNKS = 224;           // 1792 / 8
 
 struct TcWeights {
@@ -152,7 +169,7 @@ __device__ __forceinline__ size_t act3_off(int split, int n_tiles, int ridx, int
     return ((((size_t)split * n_tiles + (ridx >> 7)) * ACT3_KCHUNKS + kchunk) * 128 + (ridx & 127)) * 16;
 }
 
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // One 3x3 convolution layer as 36 tcgen05.mma (9 taps x 2 halves of the 32 input channels x 2 activation splits).
 // The operand fetch of an SS-mode MMA is shared-memory bound (~64 B/clk measured), so the two weight splits are stacked
@@ -187,193 +204,181 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     float *sB = sW1 + 288;
     uint32_t *sKey = reinterpret_cast<uint32_t *>(smem + TCC_OFF_KEY);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TCC_OFF_BAR);
-    uint64_t *bar_c2 = bars, *bar_c3 = bars + 2;       // tensor core -> workers: conv2 / conv3 of slot done
-    uint64_t *bar_a1 = bars + 4, *bar_a2 = bars + 6;   // workers -> issuer: act1 / act2 of slot written
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + TCC_OFF_BAR + 64);
+    uint64_t *bar_c2 = bars, *bar_c3 = bars + TCC_SLOTS;                       // tensor core -> workers: conv2 / conv3 of slot done
+    uint64_t *bar_a1 = bars + 2 * TCC_SLOTS, *bar_a2 = bars + 3 * TCC_SLOTS;   // workers -> issuer: act1 / act2 of slot written
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + TCC_OFF_BAR + 4 * TCC_SLOTS * 8);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     // ---- one-time setup: weights into smem, zeroed activations, barriers, TMEM
     for (int i = t; i < TCC_WBYTES / 16; i += TCC_THREADS) {
         reinterpret_cast<uint4 *>(smem + TCC_OFF_W2)[i] = reinterpret_cast<const uint4 *>(TW.wc2)[i];
         reinterpret_cast<uint4 *>(smem + TCC_OFF_W3)[i] = reinterpret_cast<const uint4 *>(TW.wc3)[i];
     }
-    for (int i = t; i < (2 * TCC_A1 + 2 * TCC_A2) / 16; i += TCC_THREADS) reinterpret_cast<uint4 *>(smem + TCC_OFF_A1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = t; i < TCC_SLOTS * TCC_ASLOT / 16; i += TCC_THREADS) reinterpret_cast<uint4 *>(smem + TCC_OFF_A1)[i] = make_uint4(0, 0, 0, 0);
     for (int i = t; i < 288; i += TCC_THREADS) sW1[i] = W.w1[i];
     if (t < 32) { sB[t] = W.b1[t]; sB[32 + t] = W.b2[t]; sB[64 + t] = W.b3[t]; }
     if (t == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
-        for (int i = 4; i < 8; ++i) mbar_init(&bars[i], TCC_WORKERS);
+        for (int i = 0; i < 2 * TCC_SLOTS; ++i) mbar_init(&bars[i], 1);
+        for (int i = 2 * TCC_SLOTS; i < 4 * TCC_SLOTS; ++i) mbar_init(&bars[i], TCC_WORKERS);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc<TCC_TMEM_COLS>(tmem_ptr);
+    if (warp == TCC_ISSUER) tmem_alloc<TCC_TMEM_COLS>(tmem_ptr);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int n_req = *n_req_ptr;
-    const int n_pairs = (n_req + 1) >> 1;
-    // pairs are handed out in runs of 4 (8 consecutive requests) so that neighbouring act3 rows are written close in time
-    const int n_runs = (n_pairs + 3) >> 2;
-    if (warp == 8) {
+    // Boards are handed out in runs of 8 consecutive requests (neighbouring act3 rows get written close in time); board i of
+    // this CTA's sequence lives in slot i % 3.  Three boards are in flight at different stages (software pipeline):
+    //   workers, iteration i :  S1(i) decode + conv1 | S2(i-1) conv2 epilogue | S3(i-2) conv3 epilogue
+    //   issuer               :  conv2(i) then conv3(i-1)
+    // Every MMA batch is issued about one full iteration before its result is consumed, so the tensor pipe works on one
+    // board while the CUDA cores prepare / drain two others.
+    const int n_runs = (n_req + 7) >> 3;
+    int n_local = 0;
+    for (int run = blockIdx.x; run < n_runs; run += gridDim.x) n_local += min(8, n_req - run * 8);
+    auto board_of = [&](int i) -> int { return ((i >> 3) * (int)gridDim.x + (int)blockIdx.x) * 8 + (i & 7); };
+    constexpr int NS = TCC_SLOTS;
+    if (warp == TCC_ISSUER) {
         // ===================================================== MMA issuer
         if (lane == 0) {
             const uint32_t s_w2 = smem_u32(smem + TCC_OFF_W2), s_w3 = smem_u32(smem + TCC_OFF_W3);
-            const uint32_t s_a1 = smem_u32(smem + TCC_OFF_A1), s_a2 = smem_u32(smem + TCC_OFF_A2);
-            uint32_t phase = 0;
+            const uint32_t s_act = smem_u32(smem + TCC_OFF_A1);
             const bool do_prof = blockIdx.x == 0;
             long long pacc[12] = {0}, ptick = clock64();
-            for (int run = blockIdx.x; run < n_runs; run += gridDim.x)
-                for (int pi = 0; pi < 4 && run * 4 + pi < n_pairs; ++pi) {
-                    for (int slot = 0; slot < 2; ++slot) {     // conv2 (model_vv.py:34): act1 on the 18x8 grid
-                        mbar_wait(&bar_a1[slot], phase);
-                        PROF_T(6);
-                        tc_fence_after();
-                        issue_conv_layer<TCC_R1, 8>(tmem_base + slot * 128, s_a1 + slot * TCC_A1, s_w2);
-                        umma_commit(&bar_c2[slot]);
-                        PROF_T(7);
-                    }
-                    for (int slot = 0; slot < 2; ++slot) {     // conv3 (model_vv.py:36): act2 on the compact 16x6 grid
-                        mbar_wait(&bar_a2[slot], phase);
-                        PROF_T(8);
-                        tc_fence_after();
-                        issue_conv_layer<TCC_R2, 6>(tmem_base + slot * 128 + 64, s_a2 + slot * TCC_A2, s_w3);
-                        umma_commit(&bar_c3[slot]);
-                        PROF_T(9);
-                    }
-                    phase ^= 1;
+            for (int i = 0; i <= n_local; ++i) {
+                if (i < n_local) {                               // conv2 (model_vv.py:34): act1 on the 18x8 grid
+                    const int slot = i % NS;
+                    mbar_wait(&bar_a1[slot], (uint32_t)(i / NS) & 1u);
+                    PROF_T(6);
+                    tc_fence_after();
+                    issue_conv_layer<TCC_R1, 8>(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
+                    umma_commit(&bar_c2[slot]);
+                    PROF_T(7);
                 }
+                if (i >= 1) {                                    // conv3 (model_vv.py:36): act2 on the compact 16x6 grid
+                    const int j = i - 1, slot = j % NS;
+                    mbar_wait(&bar_a2[slot], (uint32_t)(j / NS) & 1u);
+                    PROF_T(8);
+                    tc_fence_after();
+                    issue_conv_layer<TCC_R2, 6>(tmem_base + slot * 128 + 64, s_act + slot * TCC_ASLOT, s_w3);
+                    umma_commit(&bar_c3[slot]);
+                    PROF_T(9);
+                }
+            }
             if (prof && do_prof) for (int i = 6; i < 10; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
         }
     } else {
-        // ===================================================== workers (256 threads)
-        uint32_t phase = 0;
+        // ===================================================== workers (512 threads)
         const bool do_prof = blockIdx.x == 0 && t == 0;
         long long pacc[12] = {0}, ptick = clock64();
-        uint32_t kpre = 0;                                     // prefetched key word of the NEXT pair (threads 0..23)
-        auto fetch_key = [&](int pair) -> uint32_t {
-            const int ridx = pair * 2 + t / 12;
-            if (t < 24 && pair < n_pairs && ridx < n_req) {
-                uint2 rq = req[ridx];
-                return keys[((size_t)rq.x * M + (rq.y & 0x0fffffffu)) * KEY_WORDS + (t % 12)];
+        auto fetch_key = [&](int i) -> uint32_t {               // key word t of this CTA's i-th board (threads 0..11)
+            if (t < 12 && i < n_local) {
+                uint2 rq = req[board_of(i)];
+                return keys[((size_t)rq.x * M + (rq.y & 0x0fffffffu)) * KEY_WORDS + t];
             }
             return 0u;
         };
-        int first_pair = blockIdx.x * 4;
-        kpre = fetch_key(first_pair);
-        for (int run = blockIdx.x; run < n_runs; run += gridDim.x)
-            for (int pi = 0; pi < 4 && run * 4 + pi < n_pairs; ++pi) {
-                const int pair = run * 4 + pi;
-                if (t < 24) sKey[t] = kpre;
+        uint32_t kpre = fetch_key(0);
+        const int q = warp & 3, cq = warp >> 2, m = q * 32 + lane;
+        for (int i = 0; i < n_local + 2; ++i) {
+            // ---- S1(i): decode + conv1 -> act1 of the slot
+            if (i < n_local) {
+                const int slot = i % NS;
+                if (t < 12) sKey[t] = kpre;
                 worker_barrier();
-                {   // prefetch the next pair's keys (latency hidden behind this pair's work)
-                    int np = (pi < 3 && pair + 1 < n_pairs) ? pair + 1 : (run + (int)gridDim.x) * 4;
-                    kpre = fetch_key(np);
-                }
-                // ---- decode both boards: {-1,0,1} (model_vv.py:212)
-                for (int i = t; i < 400; i += TCC_WORKERS) {
-                    const int slot = i / 200, cell = i - slot * 200, r = cell / 10, c = cell - r * 10;
-                    const uint32_t *k = sKey + slot * 12;
-                    float v = 0.f;
-                    if (pair * 2 + slot < n_req) {
-                        v = (float)((k[r >> 1] >> ((r & 1) * 16 + c)) & 1u);
-                        uint32_t pc = k[10], ci = (uint32_t)cell;
-                        if ((pc & 0xffu) == ci || ((pc >> 8) & 0xffu) == ci || ((pc >> 16) & 0xffu) == ci || (pc >> 24) == ci) v = -1.f;
-                    }
-                    sIn[i] = v;
+                kpre = fetch_key(i + 1);                         // latency hidden behind this iteration's work
+                if (t < 200) {                                   // {-1,0,1} (model_vv.py:212)
+                    const int r = t / 10, c = t - r * 10;
+                    float v = (float)((sKey[r >> 1] >> ((r & 1) * 16 + c)) & 1u);
+                    uint32_t pc = sKey[10], ci = (uint32_t)t;
+                    if ((pc & 0xffu) == ci || ((pc >> 8) & 0xffu) == ci || ((pc >> 16) & 0xffu) == ci || (pc >> 24) == ci) v = -1.f;
+                    sIn[t] = v;
                 }
                 worker_barrier();
                 PROF_T(0);
-                // ---- conv1 (model_vv.py:32) on CUDA cores: task = (pixel of the 18x8 grid, 8-cout chunk)
-                for (int slot = 0; slot < 2; ++slot) {
-                    for (int task = t; task < 144 * 4; task += TCC_WORKERS) {
-                        const int cq = task & 3, pix = task >> 2, y = pix >> 3, x = pix & 7;
-                        float acc[8];
+                // conv1 (model_vv.py:32) on CUDA cores: task = (8-cout chunk, pixel of the 18x8 grid); consecutive lanes take
+                // consecutive pixels, so the 16-byte operand stores of a warp are contiguous (no bank conflicts)
+                for (int task = t; task < 576; task += TCC_WORKERS) {
+                    const int c4 = task / 144, pix = task - c4 * 144, y = pix >> 3, x = pix & 7;
+                    float acc[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = sB[cq * 8 + j];
+                    for (int e = 0; e < 8; ++e) acc[e] = sB[c4 * 8 + e];
 #pragma unroll
-                        for (int dy = 0; dy < 3; ++dy)
+                    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) {
-                                float in = sIn[slot * 200 + (y + dy) * 10 + x + dx];
-                                const float4 *w = reinterpret_cast<const float4 *>(sW1 + (dy * 3 + dx) * 32 + cq * 8);
-                                float4 wa = w[0], wb = w[1];
-                                acc[0] = fmaf(in, wa.x, acc[0]); acc[1] = fmaf(in, wa.y, acc[1]); acc[2] = fmaf(in, wa.z, acc[2]); acc[3] = fmaf(in, wa.w, acc[3]);
-                                acc[4] = fmaf(in, wb.x, acc[4]); acc[5] = fmaf(in, wb.y, acc[5]); acc[6] = fmaf(in, wb.z, acc[6]); acc[7] = fmaf(in, wb.w, acc[7]);
-                            }
+                        for (int dx = 0; dx < 3; ++dx) {
+                            float in = sIn[(y + dy) * 10 + x + dx];
+                            const float4 *w = reinterpret_cast<const float4 *>(sW1 + (dy * 3 + dx) * 32 + c4 * 8);
+                            float4 wa = w[0], wb = w[1];
+                            acc[0] = fmaf(in, wa.x, acc[0]); acc[1] = fmaf(in, wa.y, acc[1]); acc[2] = fmaf(in, wa.z, acc[2]); acc[3] = fmaf(in, wa.w, acc[3]);
+                            acc[4] = fmaf(in, wb.x, acc[4]); acc[5] = fmaf(in, wb.y, acc[5]); acc[6] = fmaf(in, wb.z, acc[6]); acc[7] = fmaf(in, wb.w, acc[7]);
+                        }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f) * TC_SCALE_A;
-                        uint4 c1, c2;
-                        split8(acc, c1, c2);
-                        uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_A1 + (cq * TCC_R1 + pix) * 16;
-                        *reinterpret_cast<uint4 *>(base) = c1;
-                        *reinterpret_cast<uint4 *>(base + 4 * TCC_R1 * 16) = c2;
-                    }
-                    tc_fence_before();          // orders this thread's earlier tcgen05.ld of the slot's accumulators
-                    fence_async_smem();
-                    mbar_arrive(&bar_a1[slot]);
+                    for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f) * TC_SCALE_A;
+                    uint4 c1, c2;
+                    split8(acc, c1, c2);
+                    uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (c4 * TCC_R1 + pix) * 16;
+                    *reinterpret_cast<uint4 *>(base) = c1;
+                    *reinterpret_cast<uint4 *>(base + 4 * TCC_R1 * 16) = c2;
                 }
+                fence_async_smem();
+                mbar_arrive(&bar_a1[slot]);
                 PROF_T(1);
-                // ---- conv2 epilogue: bias + ReLU + split -> act2[slot] (16x6 compact grid)
-                const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
-                for (int slot = 0; slot < 2; ++slot) {
-                    mbar_wait(&bar_c2[slot], phase);
-                    PROF_T(2);
-                    tc_fence_after();
-                    float v[16];
-                    tmem_ld16_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + half * 16, v);
-                    const int y = m >> 3, x = m & 7;
-                    if (x < 6) {
-                        const int r = y * 6 + x;
-#pragma unroll
-                        for (int c2 = 0; c2 < 2; ++c2) {
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[32 + half * 16 + c2 * 8 + j], 0.f) * TC_SCALE_A;
-                            uint4 c1, cc2;
-                            split8(o, c1, cc2);
-                            uint8_t *base = smem + TCC_OFF_A2 + slot * TCC_A2 + ((half * 2 + c2) * TCC_R2 + r) * 16;
-                            *reinterpret_cast<uint4 *>(base) = c1;
-                            *reinterpret_cast<uint4 *>(base + 4 * TCC_R2 * 16) = cc2;
-                        }
-                    }
-                    tc_fence_before();
-                    fence_async_smem();
-                    mbar_arrive(&bar_a2[slot]);
-                    PROF_T(3);
-                }
-                // ---- conv3 epilogue: bias + ReLU + split -> act3 in HBM (FC tile layout)
-                for (int slot = 0; slot < 2; ++slot) {
-                    mbar_wait(&bar_c3[slot], phase);
-                    PROF_T(4);
-                    tc_fence_after();
-                    const int ridx = pair * 2 + slot;
-                    const int y = m / 6, x = m - y * 6;
-                    float v[16];
-                    tmem_ld16_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + 64 + half * 16, v);
-                    if (m < 84 && x < 4 && ridx < n_req) {
-                        const int p = y * 4 + x;
-#pragma unroll
-                        for (int c2 = 0; c2 < 2; ++c2) {
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[c2 * 8 + j] + sB[64 + half * 16 + c2 * 8 + j], 0.f) * TC_SCALE_A;
-                            uint4 c1, cc2;
-                            split8(o, c1, cc2);
-                            const int kc = p * 4 + half * 2 + c2;
-                            *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
-                            *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = cc2;
-                        }
-                    }
-                    PROF_T(5);
-                }
-                phase ^= 1;
             }
+            // ---- S2(i-1): conv2 epilogue: bias + ReLU + split -> act2 (16x6 compact grid), in place of the slot's act1
+            if (i >= 1 && i - 1 < n_local) {
+                const int j = i - 1, slot = j % NS;
+                mbar_wait(&bar_c2[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(2);
+                tc_fence_after();
+                float v[8];
+                tmem_ld8_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + cq * 8, v);
+                const int y = m >> 3, x = m & 7;
+                if (x < 6) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[32 + cq * 8 + e], 0.f) * TC_SCALE_A;
+                    uint4 c1, c2;
+                    split8(o, c1, c2);
+                    uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (cq * TCC_R2 + y * 6 + x) * 16;
+                    *reinterpret_cast<uint4 *>(base) = c1;
+                    *reinterpret_cast<uint4 *>(base + 4 * TCC_R2 * 16) = c2;
+                }
+                tc_fence_before();
+                fence_async_smem();
+                mbar_arrive(&bar_a2[slot]);
+                PROF_T(3);
+            }
+            // ---- S3(i-2): conv3 epilogue: bias + ReLU + split -> act3 in HBM (FC tile layout)
+            if (i >= 2 && i - 2 < n_local) {
+                const int j = i - 2, slot = j % NS, ridx = board_of(j);
+                mbar_wait(&bar_c3[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(4);
+                tc_fence_after();
+                const int y = m / 6, x = m - y * 6;
+                float v[8];
+                tmem_ld8_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + 64 + cq * 8, v);
+                if (m < 84 && x < 4) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[64 + cq * 8 + e], 0.f) * TC_SCALE_A;
+                    uint4 c1, c2;
+                    split8(o, c1, c2);
+                    const int kc = (y * 4 + x) * 4 + cq;
+                    *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
+                    *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = c2;
+                }
+                tc_fence_before();
+                PROF_T(5);
+            }
+        }
         if (prof && do_prof) for (int i = 0; i < 6; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
     }
 #undef PROF_T
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<TCC_TMEM_COLS>(tmem_base);
+    if (warp == TCC_ISSUER) tmem_dealloc<TCC_TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------- fc kernel
