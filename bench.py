@@ -341,6 +341,28 @@ def run_b200(args, cfg):
                "phases_ms_per_step": {k: v[0] / steps for k, v in phases.items()},
                "counters_per_step": {k: v / steps for k, v in delta.items()}}
     eng.close()
+    # ---- BASELINE configs[1] alongside (Vanilla MCTS, random rollouts, no value net): short, so it rides in the same line
+    if cfg["mode"] != "vanilla" and not args.no_secondary:
+        G2, sims2 = 4096, 300
+        e2 = BatchedEngine(G2, max_nodes=8192, mode="vanilla", eval_kind="synthetic", env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank,
+                           device=local_rank, rollout_variance=1e3, overflow_reset=True)
+        e2.set_games(PT.new_games(G2, ENV_ARGS, D.shard_seeds(BASE_SEED, G2 * world, rank, world)))
+        for _ in range(max(args.warmup, 3)):
+            e2.play_move(sims2, auto_reset=True, want_stats=False)
+        k0 = e2.counters()
+        D.barrier()
+        torch.cuda.synchronize()
+        e2.timer_start()
+        for _ in range(max(args.steps, 1)):
+            e2.play_move(sims2, auto_reset=True, want_stats=False)
+        ms2 = D.max_over_ranks(e2.timer_stop(), dev)
+        k1 = e2.counters()
+        d2 = D.sum_over_ranks({k: k1[k] - k0[k] for k in k1}, dev)
+        e2.close()
+        if out is not None:
+            out["also_configs1_vanilla"] = {"workload": "BASELINE configs[1]: Vanilla MCTS, %d games/GPU, %d sims/move" % (G2, sims2), "value": d2["sims"] / (ms2 / 1e3),
+                                            "unit": "sims/s", "ms_per_step": ms2 / max(args.steps, 1), "rollout_steps_per_sim": d2["rollout_steps"] / max(d2["sims"], 1),
+                                            "mean_trace_len": d2["trace_levels"] / max(d2["sims"], 1)}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -362,6 +384,7 @@ def main():
     ap.add_argument("--eval", default=os.environ.get("B200_EVAL", "net_tc"), choices=["net", "net_tc", "synthetic"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--ref-moves-per-step", type=int, default=4)
     args = ap.parse_args()
     if args.workload == "vanilla":
@@ -372,7 +395,9 @@ def main():
         name = "BASELINE configs[2]: ValueSimLP + value net, %d games/GPU, %d sims/move" % (G, sims)
     cfg = dict(games_per_gpu=G, sims=sims, max_nodes=M, mode=mode, eval=args.eval, workload_key=args.workload,
                config={"workload": name, "games_per_gpu": G, "sims_per_move": sims, "max_nodes": M, "evaluator": args.eval if mode != "vanilla" else "rollout",
-                       "env_args": "((20,10),1,0,0)", "weights": "default-init distribution, numpy PCG64 seed 0"})
+                       "env_args": "((20,10),1,0,0)", "weights": "default-init distribution, numpy PCG64 seed 0",
+                       "arena_overflow": "reference semantics up to max_nodes per game; a game whose reachable set fills its arena (reference: IndexError) "
+                                         "drops its tree and re-roots (counters_per_step.tree_resets)"})
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

@@ -122,6 +122,15 @@ int b200_get_unique_child_obs(int index, const int32_t *child, const float *scor
                               int32_t *c_nodes, int32_t *c_obs, int32_t *k_out);
 int b200_get_all_childs(int index, const int32_t *child, int M, uint8_t *mark);
 
+/* --- distributional cores (agents/core_distributional.py, BASELINE config 5), operator level, reference array layout:
+ *     node_stats f32[M][5] = {visit, mean, reward, variance, M2}, node_dist f32[M][bins], child int32[M][7] */
+int b200_dist_shift_distribution(const float *dist, int bins, double x, double vmin, double vmax, float *out);     /* :12-36 */
+int b200_dist_mean_variance(const float *dist, int bins, double vmin, double vmax, double *mean, double *var);     /* :48-63 */
+int b200_dist_select_trace(int index, const int32_t *child, const float *node_stats, int M, int low, uint32_t *rng_state,
+                           int32_t *trace_out, int max_trace, int32_t *trace_len);                                 /* :82-106 */
+int b200_dist_backup_trace(const int32_t *trace, int D, float *node_stats, float *node_dist, int M, int bins, double r,
+                           const float *dist, double vmin, double vmax);                                           /* :109-124 */
+
 /* --- replay samples of the live search (ValueSim.store_nodes, agents/ValueSim.py:122-159): observations with
  *     visit >= min_visits and not end, packed as {int8 state[200], f32 value, f32 variance, f32 visit} = 212 B.
  *     out_dev is a DEVICE buffer of capacity*212 bytes (e.g. a torch tensor handed to the NCCL all-gather). */

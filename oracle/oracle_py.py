@@ -371,3 +371,55 @@ def mount_reference(ref="/root/reference"):
     if ref not in sys.path:
         sys.path.insert(0, ref)
     return pt, core
+
+
+# ----------------------------------------------------------------------------- distributional cores (a16)
+def _dsig():
+    L = lib()
+    if getattr(L, "_dsig", False):
+        return L
+    L.do_shift_distribution.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    L.do_mean_dist.restype = C.c_double
+    L.do_mean_dist.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    L.do_mean_variance.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    L.do_policy_dist.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p]
+    L.do_select_trace_distributional.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.do_backup_trace_distributional.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_double, C.c_double]
+    L._dsig = True
+    return L
+
+
+def shift_distribution(dist, x, vmin, vmax):
+    dist = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros_like(dist)
+    _dsig().do_shift_distribution(_p(dist), len(dist), float(x), float(vmin), float(vmax), _p(out))
+    return out
+
+
+def mean_variance(dist, vmin, vmax):
+    dist = np.ascontiguousarray(dist, np.float32)
+    m, v = C.c_double(), C.c_double()
+    _dsig().do_mean_variance(_p(dist), len(dist), float(vmin), float(vmax), C.byref(m), C.byref(v))
+    return m.value, v.value
+
+
+def policy_dist(child_nodes, node_stats, curr_reward):
+    cn = np.ascontiguousarray(child_nodes, np.int32)
+    q = np.zeros(len(cn), np.float64)
+    c = _dsig().do_policy_dist(_p(cn), len(cn), _p(node_stats), float(curr_reward), _p(q))
+    return c, q
+
+
+def select_trace_distributional(index, child, node_stats, low, rng_state=None, max_trace=512):
+    tr = np.zeros(max_trace, np.int32)
+    fn = C.cast(lib().mo_xorshift32, C.c_void_p)
+    st = rng_state if rng_state is not None else np.array([1], np.uint32)
+    D = _dsig().do_select_trace_distributional(int(index), _p(child), _p(node_stats), int(low), _p(tr), max_trace, fn, _p(st))
+    assert D > 0
+    return tr[:D].copy()
+
+
+def backup_trace_distributional(trace, node_stats, node_dist, r, dist, vmin, vmax):
+    trace = np.ascontiguousarray(trace, np.int32)
+    dist = np.ascontiguousarray(dist, np.float32)
+    _dsig().do_backup_trace_distributional(_p(trace), len(trace), _p(node_stats), _p(node_dist), node_dist.shape[1], float(r), _p(dist), float(vmin), float(vmax))

@@ -1,6 +1,3 @@
 set -x
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_pipe.json 2> gpurun_out/bench_r1_pipe.err; python scripts/show_bench.py gpurun_out/bench_r1_pipe.json; tail -3 gpurun_out/bench_r1_pipe.err
-timeout 600 python bench.py --workload vanilla --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1_vanilla.json 2> gpurun_out/bench_r1_vanilla.err; python scripts/show_bench.py gpurun_out/bench_r1_vanilla.json; tail -3 gpurun_out/bench_r1_vanilla.err
+timeout 600 python -m pytest tests/test_gpu_dist.py tests/test_gpu_valuenet.py -x -q -m gpu 2>&1 | tail -12

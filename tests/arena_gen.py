@@ -110,3 +110,24 @@ def state_to_obskey(s):
     cells.sort()
     key[10] = np.uint32(sum(v << (8 * i) for i, v in enumerate(cells[:4])))
     return key
+
+
+def make_dist_arena(seed, M=512, bins=50, max_depth=6, unvisited=0.0):
+    """Seeded node-indexed arena for the distributional cores: node_stats f32[M,5] = {visit, mean, reward, variance, M2},
+    node_dist f32[M,bins] (rows sum to 1), child int32[M,7] (agents/core_distributional.py)."""
+    a = make_arena(seed, M=M, max_depth=max_depth, p_dup=0.0)
+    rng = np.random.default_rng(seed + 7)
+    n = a["n_nodes"]
+    ns = np.zeros((M, 5), np.float32)
+    ns[1:n, 0] = rng.integers(1, 400, n - 1)
+    ns[1:n, 1] = rng.uniform(0, 800, n - 1)
+    ns[:, 2] = a["score"]
+    ns[1:n, 3] = rng.uniform(1, 5000, n - 1)
+    ns[1:n, 4] = ns[1:n, 3] * np.maximum(ns[1:n, 0] - 1, 1)
+    if unvisited > 0:
+        m = rng.random(M) < unvisited
+        m[:2] = False
+        ns[m, 0] = 0
+    nd = rng.random((M, bins)).astype(np.float32) ** 4
+    nd /= nd.sum(axis=1, keepdims=True)
+    return dict(child=a["child"], node_stats=ns, node_dist=nd.astype(np.float32), n_nodes=n)

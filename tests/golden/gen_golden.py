@@ -1,6 +1,7 @@
 """Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF in the build container (it cannot travel to the GPU box):
   core_golden.npz     outputs of the reference's own agents/cppmodule/core.cpp (compiled unchanged -> oracle/_ref/core*.so)
   valuenet_golden.npz outputs of the reference's own model/model_vv.py Model_VV (torch CPU) with seeded weights
+  dist_golden.npz     outputs of the reference's own numba cores agents/core_distributional.py (fastmath: pinned to 1e-5)
   agent_golden.npz    per-move statistics of the reference's own agents/ValueSimLP.py + agents/agent.py driving
                       the oracle env (the only non-reference part: pyTetris is absent upstream) with the synthetic
                       evaluator patched onto the agent instance (no reference file is modified)
@@ -131,9 +132,53 @@ def gen_agent(pt):
     print("agent_golden: %d cases" % len(cases))
 
 
+def gen_dist():
+    """Outputs of the reference's own numba cores (agents/core_distributional.py) on seeded inputs."""
+    import agents.core_distributional as R
+    from arena_gen import make_dist_arena
+    out = {}
+    rng = np.random.default_rng(5)
+    n = 10
+    for i in range(n):
+        p = "d%d_" % i
+        a = make_dist_arena(i, M=256, bins=50, max_depth=5)
+        dist = rng.random(50).astype(np.float32) ** 3
+        dist /= dist.sum()
+        x = float(rng.uniform(0, 4000))
+        out[p + "dist"], out[p + "x"] = dist, x
+        out[p + "shift"] = R.shift_distribution(dist, x, 0.0, 5000.0)
+        m, v = R.mean_variance(dist, 0.0, 5000.0)
+        out[p + "mv"] = np.array([m, v])
+        for k in ("child", "node_stats", "node_dist"):
+            out[p + k] = a[k]
+        # select_trace_distributional itself cannot run upstream: numba 0.65 fails to compile it, and un-jitted it raises in
+        # check_low(_child_nodes, node_stats, n) because `count[i] < n` is evaluated on a whole node_stats ROW
+        # (core_distributional.py:101 -> agents/core.py:464).  The per-level decision is therefore pinned through the
+        # reference's own jitted policy_dist (core_distributional.py:66-79), driven level by level here.
+        tr, idx = [], 1
+        while True:
+            tr.append(idx)
+            cn = sorted(set(int(c) for c in a["child"][idx] if c != 0))
+            if not cn:
+                break
+            idx = int(R.policy_dist(np.array(cn, np.int32), a["node_stats"], a["node_dist"], float(a["node_stats"][idx][2]), 0.0, 5000.0))
+        out[p + "trace"] = np.asarray(tr, np.int32)
+        ns, nd = a["node_stats"].copy(), a["node_dist"].copy()
+        r = float(a["node_stats"][tr[-1], 2] + rng.uniform(0, 300))
+        R.backup_trace_distributional(np.asarray(tr, np.int32), ns, nd, r, dist, 0.0, 5000.0)
+        out[p + "r"], out[p + "bk_stats"], out[p + "bk_dist"] = r, ns, nd
+    out["n_cases"] = n
+    np.savez_compressed(os.path.join(HERE, "dist_golden.npz"), **out)
+    print("dist_golden: %d cases" % n)
+
+
 if __name__ == "__main__":
     O.build(ref=True)
     pt, core = O.mount_reference()
-    gen_core(core)
-    gen_valuenet()
-    gen_agent(pt)
+    if "--dist" in sys.argv:
+        gen_dist()
+    else:
+        gen_core(core)
+        gen_valuenet()
+        gen_agent(pt)
+        gen_dist()

@@ -75,6 +75,10 @@ def lib():
         L.b200_get_unique_child_obs.argtypes = [C.c_int, P, P, P, C.c_int, P, P, P]
         L.b200_get_all_childs.argtypes = [C.c_int, P, C.c_int, P]
         L.b200_collect_samples_dev.argtypes = [P, C.c_int, P, C.c_int, P]
+        L.b200_dist_shift_distribution.argtypes = [P, C.c_int, C.c_double, C.c_double, C.c_double, P]
+        L.b200_dist_mean_variance.argtypes = [P, C.c_int, C.c_double, C.c_double, P, P]
+        L.b200_dist_select_trace.argtypes = [C.c_int, P, P, C.c_int, C.c_int, P, P, C.c_int, P]
+        L.b200_dist_backup_trace.argtypes = [P, C.c_int, P, P, C.c_int, C.c_int, C.c_double, P, C.c_double, C.c_double]
         _lib = L
     return _lib
 

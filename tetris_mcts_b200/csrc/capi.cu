@@ -12,6 +12,7 @@
 #include "../../include/b200_tetris_mcts.h"
 #include "kernels.cuh"
 #include "valuenet_simt.cuh"
+#include "dist_dev.cuh"
 #ifdef B200_WITH_TC
 #include "valuenet_tc.cuh"
 #endif
@@ -777,6 +778,64 @@ extern "C" int b200_get_all_childs(int index, const int32_t *child, int M, uint8
     k_twin_all_childs<<<1, 32>>>(b.child, M, index, d_mark, d_q);
     CK(cudaGetLastError());
     CK(cudaMemcpy(mark, d_mark, (size_t)M, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- distributional cores (a16)
+extern "C" int b200_dist_shift_distribution(const float *dist, int bins, double x, double vmin, double vmax, float *out) {
+    if (!dist || !out || bins < 1 || bins > 4096) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; float *d_in = nullptr, *d_out = nullptr;
+    TW(b.up(&d_in, dist, (size_t)bins)); TW(b.up(&d_out, (const float *)nullptr, (size_t)bins));
+    k_dist_shift<<<1, 1>>>(d_in, bins, x, vmin, vmax, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, d_out, (size_t)bins * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_dist_mean_variance(const float *dist, int bins, double vmin, double vmax, double *mean, double *var) {
+    if (!dist || !mean || !var || bins < 1) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; float *d_in = nullptr; double *d_out = nullptr;
+    TW(b.up(&d_in, dist, (size_t)bins)); TW(b.up(&d_out, (const double *)nullptr, 2));
+    k_dist_mean_variance<<<1, 1>>>(d_in, bins, vmin, vmax, d_out);
+    CK(cudaGetLastError());
+    double h[2];
+    CK(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
+    *mean = h[0]; *var = h[1];
+    return B200_OK;
+}
+
+extern "C" int b200_dist_select_trace(int index, const int32_t *child, const float *node_stats, int M, int low, uint32_t *rng_state,
+                                      int32_t *trace_out, int max_trace, int32_t *trace_len) {
+    if (!child || !node_stats || !trace_out || !trace_len || index < 0 || index >= M) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; float *d_ns = nullptr; int32_t *d_len = nullptr;
+    uint32_t seed = rng_state ? *rng_state : 0x2545F491u;
+    TW(b.up(&b.child, child, (size_t)M * 7)); TW(b.up(&d_ns, node_stats, (size_t)M * 5)); TW(b.up(&b.trace, (const int32_t *)nullptr, (size_t)max_trace));
+    TW(b.up(&b.rng, &seed, 1)); TW(b.up(&d_len, (const int32_t *)nullptr, 1));
+    k_dist_select<<<1, 1>>>(index, b.child, d_ns, low, b.trace, max_trace, b.rng, d_len);
+    CK(cudaGetLastError());
+    int32_t n = 0;
+    CK(cudaMemcpy(&n, d_len, 4, cudaMemcpyDeviceToHost));
+    if (n < 0) return fail(B200_ERR_TRACE_FULL, "trace longer than max_trace");
+    CK(cudaMemcpy(trace_out, b.trace, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (rng_state) CK(cudaMemcpy(rng_state, b.rng, 4, cudaMemcpyDeviceToHost));
+    *trace_len = n;
+    return B200_OK;
+}
+
+extern "C" int b200_dist_backup_trace(const int32_t *trace, int D, float *node_stats, float *node_dist, int M, int bins, double r,
+                                      const float *dist, double vmin, double vmax) {
+    if (!trace || D < 1 || !node_stats || !node_dist || !dist || bins < 1) return fail(B200_ERR_BAD_ARG, "bad argument");
+    if (b200_device_count() == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    TwinBufs b; float *d_ns = nullptr, *d_nd = nullptr, *d_dist = nullptr, *d_scr = nullptr;
+    TW(b.up(&b.trace, trace, (size_t)D)); TW(b.up(&d_ns, (const float *)node_stats, (size_t)M * 5)); TW(b.up(&d_nd, (const float *)node_dist, (size_t)M * bins));
+    TW(b.up(&d_dist, dist, (size_t)bins)); TW(b.up(&d_scr, (const float *)nullptr, (size_t)bins));
+    k_dist_backup<<<1, 1>>>(b.trace, D, d_ns, d_nd, bins, r, d_dist, vmin, vmax, d_scr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(node_stats, d_ns, (size_t)M * 5 * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(node_dist, d_nd, (size_t)M * bins * 4, cudaMemcpyDeviceToHost));
     return B200_OK;
 }
 
