@@ -230,8 +230,12 @@ def run_b200(args, cfg):
     G, sims, M = cfg["games_per_gpu"], cfg["sims"], cfg["max_nodes"]
     seeds = D.shard_seeds(BASE_SEED, G * world, rank, world)
     recs = PT.new_games(G, ENV_ARGS, seeds)
-    eng = BatchedEngine(G, max_nodes=M, mode=cfg["mode"], eval_kind=cfg["eval"], weights=None if cfg["mode"] == "vanilla" else init_weights(0),
-                        env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank, device=local_rank, rollout_variance=1e3, overflow_reset=True)
+    dist_w = None
+    if cfg["mode"] == "dist":
+        from tetris_mcts_b200.agents.DistValueSimOnline import init_dist_weights
+        dist_w = init_dist_weights(0, 50)
+    eng = BatchedEngine(G, max_nodes=M, mode=cfg["mode"], eval_kind=cfg["eval"], weights=init_weights(0) if cfg["mode"] in ("lp", "single") else None,
+                        dist_weights=dist_w, env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank, device=local_rank, rollout_variance=1e3, overflow_reset=True)
     eng.set_games(recs)
     for _ in range(args.warmup):
         eng.play_move(sims, auto_reset=True, want_stats=False)
@@ -302,7 +306,14 @@ def run_b200(args, cfg):
                          "traffic": (tr_s + tr_b) if tr_s and tr_b else None, "algorithmic_bytes_per_launch_pair": tree_bytes / max(sel_n, 1),
                          "kernels": "k_select_expand + k_backup", "mean_trace_len": D_mean, "ms_per_launch_pair": (sel_ms + bk_ms) / max(sel_n, 1),
                          "peak_src": peaks["src"]}
-        if cfg["mode"] != "vanilla":
+        if cfg["mode"] == "dist":
+            conv_ms, conv_n = phases["conv"]
+            flop = 121856 + 16 * 4 * 32 * 512 * 2          # conv1 + conv2 on the 22x10 input of model_distributional.py:27
+            ach = delta["eval_requests"] * flop / max(conv_ms / 1e3, 1e-9) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
+                    "kernel": "k_dn_conv", "ms_per_launch": conv_ms / max(conv_n, 1), "share_of_step": conv_ms / ms,
+                    "note": "fp32 CUDA-core kernel (the distributional head is not on tensor cores yet); bf16 peak shown as the driver-measured denominator"}
+        elif cfg["mode"] != "vanilla":
             conv_ms, conv_n = phases["conv"]
             fc_ms, fc_n = phases["fc"]
             boards = delta["eval_requests"]
@@ -342,7 +353,7 @@ def run_b200(args, cfg):
                "counters_per_step": {k: v / steps for k, v in delta.items()}}
     eng.close()
     # ---- BASELINE configs[1] alongside (Vanilla MCTS, random rollouts, no value net): short, so it rides in the same line
-    if cfg["mode"] != "vanilla" and not args.no_secondary:
+    if cfg["mode"] == "lp" and not args.no_secondary:
         G2, sims2 = 4096, 300
         e2 = BatchedEngine(G2, max_nodes=8192, mode="vanilla", eval_kind="synthetic", env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank,
                            device=local_rank, rollout_variance=1e3, overflow_reset=True)
@@ -377,7 +388,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="valuesimlp", choices=["valuesimlp", "vanilla"])
+    ap.add_argument("--workload", default="valuesimlp", choices=["valuesimlp", "vanilla", "dist"])
     ap.add_argument("--games-per-gpu", type=int, default=None)
     ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--max-nodes", type=int, default=None)
@@ -390,6 +401,11 @@ def main():
     if args.workload == "vanilla":
         G, sims, M, mode = args.games_per_gpu or 4096, args.sims or 300, args.max_nodes or 8192, "vanilla"
         name = "BASELINE configs[1]: Vanilla MCTS (random rollouts, no value net), %d games/GPU, %d sims/move" % (G, sims)
+    elif args.workload == "dist":
+        G, sims, M, mode = args.games_per_gpu or 2048, args.sims or 1500, args.max_nodes or 32768, "dist"
+        name = "BASELINE configs[4]: distributional head (agents/core_distributional.py), %d games/GPU (16384 over 8 GPUs), %d sims/move" % (G, sims)
+        if args.eval == "net_tc":
+            args.eval = "net"
     else:
         G, sims, M, mode = args.games_per_gpu or 16384, args.sims or 500, args.max_nodes or 16384, "lp"
         name = "BASELINE configs[2]: ValueSimLP + value net, %d games/GPU, %d sims/move" % (G, sims)

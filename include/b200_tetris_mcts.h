@@ -31,7 +31,8 @@ extern "C" {
 
 enum { B200_MODE_LP = 0,        /* agents/ValueSimLP.py:13-70 */
        B200_MODE_SINGLE = 1,    /* agents/ValueSim.py:52-94 */
-       B200_MODE_VANILLA = 2 }; /* agents/Vanilla.py:17-64 */
+       B200_MODE_VANILLA = 2,   /* agents/Vanilla.py:17-64 */
+       B200_MODE_DIST = 3 };    /* agents/core_distributional.py:82-124 driven as agents/DistValueSimOnline.py:36-75 sketches */
 enum { B200_EVAL_SYNTHETIC = 0, /* test evaluator (hash of the observation), shared with the CPU oracle */
        B200_EVAL_NET = 1,       /* model/model_vv.py Model_VV.inference, fp32 CUDA cores */
        B200_EVAL_NET_TC = 2 };  /* same network on tcgen05 tensor cores (3xTF32 split) */
@@ -55,6 +56,8 @@ typedef struct {
     uint32_t seed;              /* search RNG stream base (replaces libc rand(), core.h:62,76, and random.randint, Vanilla.py:52) */
     double gamma;               /* ValueSim.py:14 0.999 / Vanilla.py:9 0.99 */
     double rollout_variance;    /* Vanilla.py:54 1e3 / VanillaC.py:8 1e5 */
+    int32_t dist_bins;          /* B200_MODE_DIST: atoms, DistValueSimOnline.py:13 (50) */
+    double dist_vmin, dist_vmax;   /* value range, DistValueSimOnline.py:13 (0, 5000) */
 } b200_config;
 
 const char *b200_last_error(void);
@@ -130,6 +133,14 @@ int b200_dist_select_trace(int index, const int32_t *child, const float *node_st
                            int32_t *trace_out, int max_trace, int32_t *trace_len);                                 /* :82-106 */
 int b200_dist_backup_trace(const int32_t *trace, int D, float *node_stats, float *node_dist, int M, int bins, double r,
                            const float *dist, double vmin, double vmax);                                           /* :109-124 */
+
+/* --- distributional engine (B200_MODE_DIST): Model.load / Model.inference of model/model_distributional.py:18-57 and the
+ *     node-indexed arrays of one game.  weights: seq.conv1.w[32,1,4,4] b[32] seq.conv2.w[32,32,4,4] b[32] seq.fc1.w[128,2048]
+ *     b[128] seq.fc_v.w[atoms,128] b[atoms] concatenated (the reference hard-codes a 22x10 input, model_distributional.py:27:
+ *     the 20x10 observation gets two empty rows on top). */
+int b200_load_dist_weights(b200_engine *e, const float *weights, int atoms);
+int b200_distnet_forward(b200_engine *e, const int8_t *states, int k, int atoms, float *dist);
+int b200_export_dist(b200_engine *e, int game, float *node_stats /* [M][5] */, float *node_dist /* [M][bins] */);
 
 /* --- replay samples of the live search (ValueSim.store_nodes, agents/ValueSim.py:122-159): observations with
  *     visit >= min_visits and not end, packed as {int8 state[200], f32 value, f32 variance, f32 visit} = 212 B.

@@ -195,6 +195,27 @@ void mo_synthetic_eval(const uint32_t *k, float *v, float *var) {
     *var = 0.5f + (float)((h >> 21) & 0x3ffu) * 0.0625f;
 }
 
+/* test evaluator for the distributional mode: integer hash per bin -> weights 1..256, normalised with one float division */
+void mo_synthetic_dist(const uint32_t *k, int bins, float *dist) {
+    uint32_t raw[256], sum = 0;
+    for (int b = 0; b < bins; ++b) {
+        uint32_t h = 2166136261u;
+        for (int i = 0; i < 11; ++i) { h ^= k[i]; h *= 16777619u; }
+        h ^= (uint32_t)b * 0x9E3779B9u; h *= 16777619u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        raw[b] = ((h >> 9) & 0xffu) + 1u;
+        sum += raw[b];
+    }
+    for (int b = 0; b < bins; ++b) dist[b] = (float)raw[b] / (float)sum;
+}
+
+/* dist_oracle.c */
+int do_select_trace_distributional(int index, const int32_t *child, const float *node_stats, int low, int32_t *trace,
+                                   int max_trace, mo_rand_fn rnd, void *ctx);
+void do_backup_trace_distributional(const int32_t *trace, int D, float *node_stats, float *node_dist, int bins, double r,
+                                    const float *dist, double vmin, double vmax);
+void dn_forward(const float *weights, const int8_t *states, int k, int bins, float *dist);   /* distnet_oracle.c */
+
 /* ================================================================== tree agent (agents/agent.py) */
 void vo_forward(const float *weights, const int8_t *states, int k, float *v, float *var); /* valuenet_oracle.c */
 
@@ -215,6 +236,7 @@ struct mo_agent {
     int32_t last_trace[512]; int last_D;
     int overflow;
     uint8_t *end_scratch;
+    float *nstat, *ndist;          /* MO_MODE_DIST: node_stats f32[M][5], node_dist f32[M][bins] */
 };
 
 static uint64_t hash_words(const uint32_t *w, int n) {
@@ -279,6 +301,10 @@ mo_agent *mo_agent_create(const mo_config *cfg, int app, int scoring, int random
     a->ostate = (uint32_t *)calloc((size_t)M * TO_OBSKEY_WORDS, 4);
     a->ovisit = (int32_t *)calloc((size_t)M, 4); a->ovalue = (float *)calloc((size_t)M, 4);
     a->ovariance = (float *)calloc((size_t)M, 4); a->oend = (uint8_t *)calloc((size_t)M, 1);
+    if (cfg->mode == MO_MODE_DIST) {
+        a->nstat = (float *)calloc((size_t)M * 5, 4);
+        a->ndist = (float *)calloc((size_t)M * (size_t)cfg->dist_bins, 4);
+    }
     a->oavailable = (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
     for (int i = 1; i < M; ++i) a->oavailable[i - 1] = i;
     a->n_oavail = M - 1;
@@ -291,7 +317,7 @@ void mo_agent_destroy(mo_agent *a) {
     if (!a) return;
     free(a->child); free(a->visit_n); free(a->value_n); free(a->variance_n); free(a->episode_n); free(a->score);
     free(a->end_n); free(a->game); free(a->available); free(a->n2o); free(a->ostate); free(a->ovisit);
-    free(a->ovalue); free(a->ovariance); free(a->oend); free(a->oavailable); free(a->ntab.slot); free(a->otab.slot); free(a->end_scratch);
+    free(a->ovalue); free(a->ovariance); free(a->oend); free(a->oavailable); free(a->ntab.slot); free(a->otab.slot); free(a->end_scratch); free(a->nstat); free(a->ndist);
     free(a);
 }
 
@@ -318,6 +344,7 @@ static void remove_nodes(mo_agent *a) {
         int i = a->available[j];
         memset(a->child + (size_t)i * MO_NA, 0, sizeof(int32_t) * MO_NA);
         a->visit_n[i] = 0; a->value_n[i] = 0; a->variance_n[i] = 0; a->episode_n[i] = 0; a->score[i] = 0; a->end_n[i] = 0;
+        if (a->nstat) { memset(a->nstat + (size_t)i * 5, 0, 20); memset(a->ndist + (size_t)i * a->cfg.dist_bins, 0, 4 * (size_t)a->cfg.dist_bins); }
     }
     for (int j = 0; j < a->n_oavail; ++j)
         tab_erase(&a->otab, a->ostate, a->ostate + (size_t)a->oavailable[j] * TO_OBSKEY_WORDS);
@@ -353,6 +380,7 @@ static int new_node(mo_agent *a, const to_game *g) {
     memcpy(a->game + (size_t)idx * TO_RECORD_WORDS, rec, sizeof(rec));
     a->episode_n[idx] = a->episode;
     a->score[idx] = (float)g->score;
+    if (a->nstat) a->nstat[(size_t)idx * 5 + 2] = (float)g->score;   /* node_stats[idx][2] = reward (core_distributional.py:86,112) */
     tab_insert(&a->ntab, rec, idx);
     uint32_t key[TO_OBSKEY_WORDS];
     to_obskey(g, key);
@@ -407,6 +435,37 @@ static void evaluate(mo_agent *a, const int32_t *obs, int k, float *v, float *va
 int mo_agent_mcts(mo_agent *a, int sims) {
     const mo_config *cf = &a->cfg;
     for (int s = 0; s < sims; ++s) {
+        if (cf->mode == MO_MODE_DIST) {
+            /* The loop agents/DistValueSimOnline.py:36-75 sketches (not runnable upstream), on the numba cores:
+             * select_trace_distributional -> r = leaf score; leaf not ended: dist = net(leaf state), expand;
+             * ended: all mass in bin 0 (v_dummy, DistValueSimOnline.py:26-27) -> backup_trace_distributional */
+            float dist[256];
+            int D = do_select_trace_distributional(a->root, a->child, a->nstat, cf->low, a->last_trace, 512, agent_rand, a);
+            if (D < 0) return -2;
+            a->last_D = D; a->counters[0] += 1; a->counters[4] += D;
+            int leaf = a->last_trace[D - 1];
+            to_game lg;
+            to_unpack(&lg, a->game + (size_t)leaf * TO_RECORD_WORDS);
+            if (!lg.end) {
+                const uint32_t *key = a->ostate + (size_t)a->n2o[leaf] * TO_OBSKEY_WORDS;
+                a->counters[2] += 1;
+                if (cf->eval_mode == MO_EVAL_SYNTHETIC) mo_synthetic_dist(key, cf->dist_bins, dist);
+                else {
+                    int8_t st[200];
+                    for (int r = 0; r < 20; ++r)
+                        for (int c = 0; c < 10; ++c) st[r * 10 + c] = (int8_t)((key[r >> 1] >> ((r & 1) * 16 + c)) & 1);
+                    for (int j = 0; j < 4; ++j) st[(key[10] >> (8 * j)) & 0xff] = -1;
+                    dn_forward(cf->weights, st, 1, cf->dist_bins, dist);
+                }
+                expand(a, leaf);
+                if (a->overflow) return -1;
+            } else {
+                memset(dist, 0, sizeof(float) * (size_t)cf->dist_bins);
+                dist[0] = 1.f;
+            }
+            do_backup_trace_distributional(a->last_trace, D, a->nstat, a->ndist, cf->dist_bins, (double)lg.score, dist, cf->dist_vmin, cf->dist_vmax);
+            continue;
+        }
         int D = mo_select_trace_obs(a->root, a->child, a->ovisit, a->ovalue, a->ovariance, a->score, a->n2o, cf->low,
                                     a->last_trace, 512, agent_rand, a);
         if (D < 0) return -2;
@@ -485,6 +544,18 @@ int mo_agent_mcts(mo_agent *a, int sims) {
 /* agent.py:153-185 compute_stats + get_action */
 int mo_agent_get_action(mo_agent *a, float *stats) {
     int idx = a->root;
+    if (a->cfg.mode == MO_MODE_DIST) {                      /* DistValueSimOnline.py:77-104: visit, mean + reward - root reward, variance */
+        for (int i = 0; i < MO_NA; ++i) {
+            int c = a->child[(size_t)idx * MO_NA + i];
+            const float *ns = a->nstat + (size_t)c * 5;
+            stats[i] = ns[0];
+            stats[MO_NA + i] = (ns[1] + ns[2]) - a->nstat[(size_t)idx * 5 + 2];
+            stats[2 * MO_NA + i] = ns[3];
+        }
+        int b = 0;
+        for (int i = 1; i < MO_NA; ++i) if (stats[MO_NA + i] > stats[MO_NA + b]) b = i;
+        return b;
+    }
     for (int i = 0; i < MO_NA; ++i) {
         int c = a->child[(size_t)idx * MO_NA + i];
         int o = a->n2o[c];
@@ -515,6 +586,12 @@ void mo_agent_export(const mo_agent *a, int32_t *child, float *score, int32_t *e
     if (obs_end) memcpy(obs_end, a->oend, M);
     if (game_recs) memcpy(game_recs, a->game, M * TO_RECORD_WORDS * 4);
     if (obs_keys) memcpy(obs_keys, a->ostate, M * TO_OBSKEY_WORDS * 4);
+}
+
+void mo_agent_export_dist(const mo_agent *a, float *node_stats, float *node_dist) {
+    if (!a->nstat) return;
+    if (node_stats) memcpy(node_stats, a->nstat, (size_t)a->M * 5 * 4);
+    if (node_dist) memcpy(node_dist, a->ndist, (size_t)a->M * (size_t)a->cfg.dist_bins * 4);
 }
 
 int mo_agent_last_trace(const mo_agent *a, int32_t *trace, int max) {

@@ -39,7 +39,7 @@ int mo_get_all_childs(int index, const int32_t *child, int M, uint8_t *mark);  /
 void mo_synthetic_eval(const uint32_t *obskey12, float *v, float *var);        /* test evaluator shared with the device */
 
 /* ---- tree agent (agents/agent.py TreeAgent + ValueSim/ValueSimLP/Vanilla mcts loops) ---- */
-enum { MO_MODE_LP = 0, MO_MODE_SINGLE = 1, MO_MODE_VANILLA = 2 };
+enum { MO_MODE_LP = 0, MO_MODE_SINGLE = 1, MO_MODE_VANILLA = 2, MO_MODE_DIST = 3 /* agents/core_distributional.py loop, see mcts_oracle.c */ };
 enum { MO_EVAL_SYNTHETIC = 0, MO_EVAL_NET = 1, MO_EVAL_CALLBACK = 2 };
 typedef void (*mo_eval_fn)(void *ctx, const int8_t *states, int k, float *v, float *var);
 
@@ -56,6 +56,8 @@ typedef struct {
     mo_eval_fn eval_cb; void *eval_ctx;
     uint32_t search_seed;  /* per-agent xorshift stream replacing rand()/random.randint */
     int stale_pop;         /* agent.py:229-232 erases by the freed slot's STALE game; 1 = reproduce */
+    int dist_bins;         /* MO_MODE_DIST: atoms (DistValueSimOnline.py:13: 50) */
+    double dist_vmin, dist_vmax;   /* value range (DistValueSimOnline.py:13: 0, 5000) */
 } mo_config;
 
 typedef struct mo_agent mo_agent;
@@ -72,6 +74,8 @@ void mo_agent_export(const mo_agent *a, int32_t *child, float *score, int32_t *e
                      int32_t *visit, float *value, float *variance, uint8_t *obs_end, uint32_t *game_recs,
                      uint32_t *obs_keys);
 int mo_agent_last_trace(const mo_agent *a, int32_t *trace, int max);
+void mo_agent_export_dist(const mo_agent *a, float *node_stats, float *node_dist);   /* MO_MODE_DIST: f32[M][5], f32[M][bins] */
+void mo_synthetic_dist(const uint32_t *obskey12, int bins, float *dist);             /* test evaluator shared with the device */
 #ifdef __cplusplus
 }
 #endif

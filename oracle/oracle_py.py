@@ -43,7 +43,7 @@ class MoConfig(C.Structure):
         ("max_nodes", C.c_int), ("mode", C.c_int), ("gamma", C.c_double), ("low", C.c_int),
         ("lp_end_from_obs", C.c_int), ("lp_var_gamma2", C.c_int), ("rollout_variance", C.c_double),
         ("eval_mode", C.c_int), ("weights", C.c_void_p), ("eval_cb", C.c_void_p), ("eval_ctx", C.c_void_p),
-        ("search_seed", C.c_uint32), ("stale_pop", C.c_int),
+        ("search_seed", C.c_uint32), ("stale_pop", C.c_int), ("dist_bins", C.c_int), ("dist_vmin", C.c_double), ("dist_vmax", C.c_double),
     ]
 
 
@@ -233,8 +233,10 @@ class Agent:
 
     def __init__(self, max_nodes=100000, mode=0, gamma=0.999, low=1, eval_mode=0, weights=None, eval_cb=None,
                  lp_end_from_obs=0, lp_var_gamma2=1, rollout_variance=1e3, search_seed=0, stale_pop=1,
-                 app=1, scoring=0, randomizer=0):
+                 app=1, scoring=0, randomizer=0, dist_bins=50, dist_vmin=0.0, dist_vmax=5000.0):
         cfg = MoConfig()
+        cfg.dist_bins, cfg.dist_vmin, cfg.dist_vmax = dist_bins, dist_vmin, dist_vmax
+        self.dist_bins = dist_bins
         cfg.max_nodes, cfg.mode, cfg.gamma, cfg.low = max_nodes, mode, gamma, low
         cfg.lp_end_from_obs, cfg.lp_var_gamma2, cfg.rollout_variance = lp_end_from_obs, lp_var_gamma2, rollout_variance
         cfg.eval_mode = eval_mode
@@ -293,6 +295,13 @@ class Agent:
         lib().mo_agent_export(self.h, _p(d["child"]), _p(d["score"]), _p(d["episode"]), _p(d["n2o"]), _p(d["visit"]),
                               _p(d["value"]), _p(d["variance"]), _p(d["obs_end"]), _p(d["game"]), _p(d["obs_key"]))
         return d
+
+    def export_dist(self):
+        ns = np.zeros((self.M, 5), np.float32)
+        nd = np.zeros((self.M, self.dist_bins), np.float32)
+        lib().mo_agent_export_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib().mo_agent_export_dist(self.h, _p(ns), _p(nd))
+        return ns, nd
 
     def last_trace(self):
         tr = np.zeros(512, np.int32)
@@ -423,3 +432,47 @@ def backup_trace_distributional(trace, node_stats, node_dist, r, dist, vmin, vma
     trace = np.ascontiguousarray(trace, np.int32)
     dist = np.ascontiguousarray(dist, np.float32)
     _dsig().do_backup_trace_distributional(_p(trace), len(trace), _p(node_stats), _p(node_dist), node_dist.shape[1], float(r), _p(dist), float(vmin), float(vmax))
+
+
+def synthetic_dist(key, bins=50):
+    key = np.ascontiguousarray(key, np.uint32)
+    out = np.zeros(bins, np.float32)
+    lib().mo_synthetic_dist.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib().mo_synthetic_dist(_p(key), bins, _p(out))
+    return out
+
+
+DIST_WEIGHT_KEYS = (("seq.conv1.weight", (32, 1, 4, 4)), ("seq.conv1.bias", (32,)), ("seq.conv2.weight", (32, 32, 4, 4)),
+                    ("seq.conv2.bias", (32,)), ("seq.fc1.weight", (128, 2048)), ("seq.fc1.bias", (128,)),
+                    ("seq.fc_v.weight", (50, 128)), ("seq.fc_v.bias", (50,)))
+
+
+def seeded_dist_weights(seed=0, atoms=50):
+    """Default-init-distributed weights of model/model_distributional.py:18-45 Net (22x10 input, flatten 2048), numpy PCG64."""
+    rng = np.random.default_rng(seed + 1000)
+    parts = []
+    for shape, fan_in in (((32, 1, 4, 4), 16), ((32,), 16), ((32, 32, 4, 4), 512), ((32,), 512), ((128, 2048), 2048), ((128,), 2048),
+                          ((atoms, 128), 128), ((atoms,), 128)):
+        b = 1.0 / np.sqrt(fan_in)
+        parts.append(rng.uniform(-b, b, size=shape).astype(np.float32).ravel())
+    return np.concatenate(parts)
+
+
+def dist_weights_to_state_dict(w, atoms=50):
+    out, off = {}, 0
+    for name, shape in DIST_WEIGHT_KEYS:
+        if name.startswith("seq.fc_v"):
+            shape = (atoms,) + tuple(shape[1:])
+        n = int(np.prod(shape))
+        out[name] = np.asarray(w[off:off + n], np.float32).reshape(shape)
+        off += n
+    return out
+
+
+def distnet_forward(weights, states, bins=50):
+    states = np.ascontiguousarray(states, np.int8).reshape(-1, 200)
+    w = np.ascontiguousarray(weights, np.float32)
+    out = np.zeros((len(states), bins), np.float32)
+    lib().dn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib().dn_forward(_p(w), _p(states), len(states), bins, _p(out))
+    return out

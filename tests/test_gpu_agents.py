@@ -79,3 +79,21 @@ def test_core_module_signatures(gpu_lib, oracle):
     assert core.get_all_childs(1, a["child"]) == oracle.get_all_childs(1, a["child"])
     with pytest.raises(TypeError):
         core.backup_trace_obs(tr, dev["visit"].astype(np.int64), dev["value"], dev["variance"], a["n2o"], a["score"], 1.0, 1.0, 0.9)
+
+
+def test_dist_agent_class_like_play_py(gpu_lib, oracle):
+    """play.py would do getattr(import_module('agents.DistValueSimOnline'), 'DistValueSimOnline') (play.py:81-82)."""
+    from tetris_mcts_b200.agents import DistValueSimOnline as mod
+    from tetris_mcts_b200.pyTetris import Tetris
+    env_args = ((20, 10), 1, 0, 0)
+    game = Tetris(*env_args)
+    agent = getattr(mod, "DistValueSimOnline")(sims=80, env=Tetris, env_args=env_args, benchmark=True, online=False, min_visit=40)
+    agent.update_root(game)
+    for _ in range(3):
+        a = agent.play()
+        assert 0 <= a < 7
+        game.play(a)
+        agent.update_root(game)
+    m, v = agent.get_value()
+    assert 0 <= m <= 5000 and v >= 0
+    agent.close()

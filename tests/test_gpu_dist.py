@@ -44,3 +44,71 @@ def test_dist_twins_match_oracle_with_rng(gpu_lib, oracle):
         CD.backup_trace_distributional(want, ns1, nd1, r, dist, 0, 5000)
         oracle.backup_trace_distributional(want, ns2, nd2, r, dist, 0, 5000)
         assert np.array_equal(ns1, ns2) and np.array_equal(nd1, nd2)
+
+
+def _search_seed(seed, g):
+    s = (seed + 0x9E3779B9 * (g + 1)) & 0xffffffff
+    return s or 0x2545F491
+
+
+def test_dist_engine_matches_oracle_agent(gpu_lib, oracle):
+    """BASELINE config 5 path end to end (select_trace_distributional -> evaluate leaf -> expand -> backup_trace_distributional),
+    synthetic histogram evaluator on both sides: actions, stats and the node_stats / node_dist arrays must be identical."""
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    n, M, sims, moves, seed = 12, 4096, 60, 10, 77
+    recs = PT.new_games(n, (1, 0, 0), np.arange(seed, seed + n, dtype=np.uint32))
+    eng = BatchedEngine(n, max_nodes=M, mode="dist", eval_kind="synthetic", seed=seed)
+    eng.set_games(recs)
+    agents = [oracle.Agent(max_nodes=M, mode=3, low=5, eval_mode=0, search_seed=_search_seed(seed, g)) for g in range(n)]
+    games = [oracle.Game(record=recs[g]) for g in range(n)]
+    for g in range(n):
+        agents[g].update_root(games[g].record())
+    for mv in range(moves):
+        eng.run_sims(sims)
+        stats, action = eng.get_stats()
+        for g in range(n):
+            agents[g].mcts(sims)
+            a, st = agents[g].get_action()
+            assert np.array_equal(st, stats[g]), (mv, g, st, stats[g])
+            assert a == action[g]
+            games[g].play(a)
+            agents[g].update_root(games[g].record())
+            if games[g].end:
+                games[g].reset()
+                agents[g].update_root(games[g].record())
+        eng.env_step(None)
+        eng.update_root(auto_reset=True)
+    for g in range(4):
+        ns, nd = eng.export_dist(g)
+        wns, wnd = agents[g].export_dist()
+        assert np.array_equal(ns, wns) and np.array_equal(nd, wnd), g
+    eng.close()
+
+
+def test_dist_network_matches_reference_golden(gpu_lib, oracle):
+    """model/model_distributional.py Net (torch CPU) outputs recorded in tests/golden/distnet_golden.npz."""
+    from tetris_mcts_b200.engine import BatchedEngine
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "distnet_golden.npz"))
+    w = oracle.seeded_dist_weights(int(z["seed"]))
+    eng = BatchedEngine(1, max_nodes=64, mode="dist", eval_kind="net", dist_weights=w)
+    got = eng.distnet(z["states"])
+    assert np.allclose(got, z["dist"], rtol=1e-5, atol=1e-7), np.abs(got - z["dist"]).max()
+    assert np.allclose(got, oracle.distnet_forward(w, z["states"]), rtol=1e-5, atol=1e-7)
+    assert np.allclose(got.sum(axis=1), 1.0, atol=1e-5)
+    eng.close()
+
+
+def test_dist_engine_runs_with_network(gpu_lib, oracle):
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    n = 256
+    eng = BatchedEngine(n, max_nodes=2048, mode="dist", eval_kind="net", dist_weights=oracle.seeded_dist_weights(0), overflow_reset=True)
+    eng.set_games(PT.new_games(n, (1, 0, 0), np.arange(1, n + 1, dtype=np.uint32)))
+    for _ in range(3):
+        actions, stats = eng.play_move(100, auto_reset=True)
+    ns, nd = eng.export_dist(0)
+    live = ns[:, 0] > 0
+    assert live.any() and np.allclose(nd[live].sum(axis=1), 1.0, atol=1e-3)
+    assert eng.counters()["sims"] == n * 300
+    eng.close()

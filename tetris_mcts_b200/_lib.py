@@ -13,7 +13,7 @@ KEY_WORDS = 12
 N_ACTIONS = 7
 N_WEIGHTS = 478342
 
-MODE_LP, MODE_SINGLE, MODE_VANILLA = 0, 1, 2
+MODE_LP, MODE_SINGLE, MODE_VANILLA, MODE_DIST = 0, 1, 2, 3
 EVAL_SYNTHETIC, EVAL_NET, EVAL_NET_TC = 0, 1, 2
 ERR_NAMES = {1: "BAD_ARG", 2: "CUDA", 3: "ARENA_FULL", 4: "TRACE_FULL", 5: "NO_WEIGHTS"}
 
@@ -29,7 +29,7 @@ class Config(C.Structure):
                 ("lp_end_from_obs", C.c_int32), ("lp_var_gamma2", C.c_int32), ("stale_pop", C.c_int32), ("overflow_reset", C.c_int32),
                 ("eval_kind", C.c_int32), ("trace_max", C.c_int32), ("actions_per_drop", C.c_int32),
                 ("scoring", C.c_int32), ("randomizer", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint32),
-                ("gamma", C.c_double), ("rollout_variance", C.c_double)]
+                ("gamma", C.c_double), ("rollout_variance", C.c_double), ("dist_bins", C.c_int32), ("dist_vmin", C.c_double), ("dist_vmax", C.c_double)]
 
 
 _lib = None
@@ -75,6 +75,9 @@ def lib():
         L.b200_get_unique_child_obs.argtypes = [C.c_int, P, P, P, C.c_int, P, P, P]
         L.b200_get_all_childs.argtypes = [C.c_int, P, C.c_int, P]
         L.b200_collect_samples_dev.argtypes = [P, C.c_int, P, C.c_int, P]
+        L.b200_load_dist_weights.argtypes = [P, P, C.c_int]
+        L.b200_distnet_forward.argtypes = [P, P, C.c_int, C.c_int, P]
+        L.b200_export_dist.argtypes = [P, C.c_int, P, P]
         L.b200_dist_shift_distribution.argtypes = [P, C.c_int, C.c_double, C.c_double, C.c_double, P]
         L.b200_dist_mean_variance.argtypes = [P, C.c_int, C.c_double, C.c_double, P, P]
         L.b200_dist_select_trace.argtypes = [C.c_int, P, P, C.c_int, C.c_int, P, P, C.c_int, P]

@@ -65,9 +65,12 @@ class TreeAgent(Agent):                                          # agents/agent.
         self.gamma = gamma
         self.stats = np.zeros((3, self.n_actions), np.float32)
         self._eng = BatchedEngine(1, max_nodes=self.max_nodes, mode=self._mode, gamma=gamma, low=low, eval_kind=eval_kind, weights=weights,
-                                  env_args=self.env_args, device=device, overflow_reset=overflow_reset)
+                                  env_args=self.env_args, device=device, overflow_reset=overflow_reset, **self._engine_kwargs())
         self._snap = None
         self.game_arr = _GameArr(self)
+
+    def _engine_kwargs(self):
+        return {}
 
     # ---- snapshots in the reference layout
     def _snapshot(self):

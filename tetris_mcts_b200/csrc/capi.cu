@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "valuenet_simt.cuh"
 #include "dist_dev.cuh"
+#include "distnet_simt.cuh"
 #ifdef B200_WITH_TC
 #include "valuenet_tc.cuh"
 #endif
@@ -51,6 +52,7 @@ struct b200_engine {
     NetWeights W{};
     float *d_act3 = nullptr; size_t act3_rows = 0;
     void *tc_state = nullptr;
+    bool have_dist_weights = false; float *d_dnw = nullptr; DistNetWeights DW{}; float *d_dn_act = nullptr; size_t dn_rows = 0;
     int n_sm = 148;
     // timing
     bool timing = false;
@@ -132,7 +134,9 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     if (!cfg || !out) return fail(B200_ERR_BAD_ARG, "null argument");
     if (cfg->n_games < 1 || cfg->max_nodes < 16 || cfg->max_nodes >= (1 << 28) || (cfg->max_nodes & 3))
         return fail(B200_ERR_BAD_ARG, "n_games >= 1, 16 <= max_nodes < 2^28, max_nodes % 4 == 0");
-    if (cfg->mode < 0 || cfg->mode > 2) return fail(B200_ERR_BAD_ARG, "mode");
+    if (cfg->mode < 0 || cfg->mode > 3) return fail(B200_ERR_BAD_ARG, "mode");
+    if (cfg->mode == MODE_DIST && (cfg->dist_bins < 2 || cfg->dist_bins > 64 || !(cfg->dist_vmax > cfg->dist_vmin)))
+        return fail(B200_ERR_BAD_ARG, "distributional mode needs 2 <= dist_bins <= 64 and dist_vmax > dist_vmin");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
     CK(cudaSetDevice(cfg->device));
@@ -167,6 +171,10 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     rc |= dalloc(e, &A.gc_list, G); rc |= dalloc(e, &A.pending, G); rc |= dalloc(e, &A.resume_a, G);
     rc |= dalloc(e, &A.eval_out, G * 8); rc |= dalloc(e, &A.rollout_val, G);
     rc |= dalloc(e, &A.counters, 32);
+    if (cfg->mode == MODE_DIST) {
+        A.dist_bins = cfg->dist_bins; A.dist_vmin = cfg->dist_vmin; A.dist_vmax = cfg->dist_vmax;
+        rc |= dalloc(e, &A.nstat, GM * NSTAT_WORDS); rc |= dalloc(e, &A.ndist, GM * (size_t)A.dist_bins); rc |= dalloc(e, &A.dist_eval, G * (size_t)A.dist_bins);
+    }
     rc |= dalloc(e, &e->d_default_rec, REC_WORDS);
     rc |= dalloc(e, &e->d_stats, G * 21); rc |= dalloc(e, &e->d_action, G);
     e->d_game_stats = A.counters + 8;
@@ -298,6 +306,68 @@ static int launch_net(b200_engine *e, const uint2 *req, const int32_t *n_req, co
     return B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------- distributional network
+__global__ void k_states_to_keys(const int8_t *states, int k, uint32_t *keys, uint2 *req);   // defined with the standalone value net below
+
+extern "C" int b200_load_dist_weights(b200_engine *e, const float *w, int atoms) {
+    if (!e || !w || atoms < 2 || atoms > 64) return fail(B200_ERR_BAD_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->A.mode == MODE_DIST && atoms != e->A.dist_bins) return fail(B200_ERR_BAD_ARG, "atoms must equal dist_bins");
+    std::vector<float> h;
+    dn_relayout(w, atoms, h);
+    if (!e->d_dnw) { if (dalloc(e, &e->d_dnw, h.size(), false)) return B200_ERR_CUDA; }
+    CK(cudaMemcpyAsync(e->d_dnw, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->DW = dn_pointers(e->d_dnw, atoms);
+    CK(cudaFuncSetAttribute(k_dn_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_CONV_SMEM));
+    CK(cudaFuncSetAttribute(k_dn_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_FC_SMEM));
+    e->have_dist_weights = true;
+    return B200_OK;
+}
+
+static int launch_distnet_on(b200_engine *e, const uint2 *req, const int32_t *n_req, const uint32_t *keys, int M, float *out, size_t max_rows) {
+    if (!e->have_dist_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_dist_weights was not called");
+    if (e->dn_rows < max_rows) {
+        if (dalloc(e, &e->d_dn_act, max_rows * 2048, false)) return B200_ERR_CUDA;
+        e->dn_rows = max_rows;
+    }
+    {
+        PhaseTimer t(e, PH_CONV);
+        k_dn_conv<<<e->n_sm * 2, DN_THREADS, DN_CONV_SMEM, e->stream>>>(e->DW, req, n_req, keys, M, e->d_dn_act);
+    }
+    {
+        PhaseTimer t(e, PH_FC);
+        k_dn_fc<<<e->n_sm, DN_THREADS, DN_FC_SMEM, e->stream>>>(e->DW, e->d_dn_act, req, n_req, out);
+    }
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+static int launch_distnet(b200_engine *e) {
+    return launch_distnet_on(e, e->A.req, e->A.n_req, e->A.key, e->A.M, e->A.dist_eval, (size_t)e->A.G);
+}
+
+// Model.inference of model/model_distributional.py (softmax over atoms): states[k][200] int8 -> dist[k][atoms]
+extern "C" int b200_distnet_forward(b200_engine *e, const int8_t *states, int k, int atoms, float *dist) {
+    if (!e || !states || !dist || k < 1 || atoms != e->DW.atoms) return fail(B200_ERR_BAD_ARG, "bad argument (atoms must match the loaded weights)");
+    CK(cudaSetDevice(e->cfg.device));
+    int8_t *d_states = nullptr; uint32_t *d_keys = nullptr; uint2 *d_req = nullptr; int32_t *d_n = nullptr; float *d_out = nullptr;
+    CK(cudaMalloc(&d_states, (size_t)k * 200)); CK(cudaMalloc(&d_keys, (size_t)k * KEY_WORDS * 4)); CK(cudaMalloc(&d_req, (size_t)k * 8));
+    CK(cudaMalloc(&d_n, 4)); CK(cudaMalloc(&d_out, (size_t)k * atoms * 4));
+    CK(cudaMemcpyAsync(d_states, states, (size_t)k * 200, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d_n, &k, 4, cudaMemcpyHostToDevice, e->stream));
+    k_states_to_keys<<<(k + 127) / 128, 128, 0, e->stream>>>(d_states, k, d_keys, d_req);
+    k_dn_req_rows<<<(k + 127) / 128, 128, 0, e->stream>>>(d_req, k);      // request i -> output row i
+    int rc = launch_distnet_on(e, d_req, d_n, d_keys, 0, d_out, (size_t)k);
+    if (rc == B200_OK) {
+        cudaError_t ce = cudaMemcpyAsync(dist, d_out, (size_t)k * atoms * 4, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) rc = fail(B200_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d_states); cudaFree(d_keys); cudaFree(d_req); cudaFree(d_n); cudaFree(d_out);
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------------- games / roots
 static inline int blocks_groups(int G) { return (G + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK; }
 static inline int gc_blocks(b200_engine *e) { int b = e->n_sm * 4; return e->A.G < b ? e->A.G : b; }
@@ -352,7 +422,7 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
     const Arena &A = e->A;
     const int G = A.G;
     const bool need_net = A.mode != MODE_VANILLA && e->cfg.eval_kind != B200_EVAL_SYNTHETIC;
-    if (need_net && !e->have_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
+    if (need_net && !(A.mode == MODE_DIST ? e->have_dist_weights : e->have_weights)) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
     for (int s = 0; s < sims; ++s) {
         CK(cudaMemsetAsync(A.n_req, 0, 2 * sizeof(int32_t), e->stream));
         {
@@ -367,6 +437,14 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
         if (A.mode == MODE_VANILLA) {
             PhaseTimer t(e, PH_ROLLOUT);
             k_rollout<<<(G + 63) / 64, 64, 0, e->stream>>>(A);
+        } else if (A.mode == MODE_DIST) {
+            if (e->cfg.eval_kind == B200_EVAL_SYNTHETIC) {
+                PhaseTimer t(e, PH_SYNTH);
+                k_eval_synthetic_dist<<<(G + 127) / 128, 128, 0, e->stream>>>(A);
+            } else {
+                int rc = launch_distnet(e);
+                if (rc) return rc;
+            }
         } else if (e->cfg.eval_kind == B200_EVAL_SYNTHETIC) {
             PhaseTimer t(e, PH_SYNTH);
             k_eval_synthetic<<<(G * 7 + 255) / 256 < 1184 ? (G * 7 + 255) / 256 : 1184, 256, 0, e->stream>>>(A);
@@ -376,7 +454,8 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
         }
         {
             PhaseTimer t(e, PH_BACKUP);
-            k_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
+            if (A.mode == MODE_DIST) k_dist_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
+            else k_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
         }
     }
     CK(cudaGetLastError());
@@ -520,6 +599,18 @@ extern "C" int b200_export_game(b200_engine *e, int game, int32_t *child, float 
         if (variance) memcpy(&variance[i], &stat[i].z, 4);
         if (obs_end) obs_end[i] = (uint8_t)(stat[i].w != 0);
     }
+    return B200_OK;
+}
+
+extern "C" int b200_export_dist(b200_engine *e, int game, float *node_stats, float *node_dist) {
+    if (!e || game < 0 || game >= e->A.G || !e->A.nstat) return fail(B200_ERR_BAD_ARG, "not a distributional engine / bad game index");
+    CK(cudaSetDevice(e->cfg.device));
+    size_t M = e->A.M;
+    std::vector<float> ns(M * NSTAT_WORDS);
+    CK(cudaMemcpyAsync(ns.data(), e->A.nstat + (size_t)game * M * NSTAT_WORDS, ns.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (node_dist) CK(cudaMemcpyAsync(node_dist, e->A.ndist + (size_t)game * M * e->A.dist_bins, M * e->A.dist_bins * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (node_stats) for (size_t i = 0; i < M; ++i) for (int j = 0; j < 5; ++j) node_stats[i * 5 + j] = ns[i * NSTAT_WORDS + j];
     return B200_OK;
 }
 

@@ -163,14 +163,15 @@ __global__ void __launch_bounds__(TPB) k_select_expand(Arena A) {
     if (status != ST_OK) return;
     ArenaAcc acc{A, g};
     int D = 0;
-    int leaf = select_trace(acc, gp, A.root[g], A.low, A.trace_max, D, status);
+    int leaf = A.mode == MODE_DIST ? dist_select_group(A, gp, g, A.root[g], D, status)
+                                   : select_trace(acc, gp, A.root[g], A.low, A.trace_max, D, status);
     if (status != ST_OK) { if (gp.lane == 0) A.status[g] = status; return; }
     uint32_t w[REC_WORDS];
     load_rec(A.rec + node_at(A, g, leaf) * REC_WORDS, w);
     bool ended = (w[10] >> 21) & 1u;
     int kind = ended ? LEAF_TERMINAL : LEAF_EXPANDED;
     if (!ended) {
-        if (A.mode == MODE_SINGLE)            // ValueSim.py:83-88 evaluates the leaf itself, before expanding
+        if (A.mode == MODE_SINGLE || A.mode == MODE_DIST)   // ValueSim.py:83-88 / DistValueSimOnline.py:66-70: the leaf itself is evaluated
             emit_requests(A, gp, g, 1u << 7, A.row[node_at(A, g, leaf) * ROW_WORDS + 15]);
         int c, o, a_stop; float s;
         expand_leaf(A, gp, g, leaf, w, c, o, s, status, 0, true, a_stop);
@@ -352,6 +353,11 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
             int4 *r = reinterpret_cast<int4 *>(rowb + (size_t)nfree[i / 6] * ROW_WORDS) + (i % 6);
             *r = make_int4(0, 0, 0, (i % 6) == 3 ? r->w : 0);
         }
+        if (A.nstat) {
+            float *nsb = A.nstat + (size_t)g * M * NSTAT_WORDS, *ndb = A.ndist + (size_t)g * M * A.dist_bins;
+            for (int i = t; i < nn * NSTAT_WORDS; i += GC_THREADS) nsb[(size_t)nfree[i / NSTAT_WORDS] * NSTAT_WORDS + (i % NSTAT_WORDS)] = 0.f;
+            for (int i = t; i < nn * A.dist_bins; i += GC_THREADS) ndb[(size_t)nfree[i / A.dist_bins] * A.dist_bins + (i % A.dist_bins)] = 0.f;
+        }
         int4 *statb = A.stat + (size_t)g * M;
         uint4 *keyb = reinterpret_cast<uint4 *>(A.key + (size_t)g * M * KEY_WORDS);
         for (int i = t; i < no; i += GC_THREADS) statb[ofree[i]] = make_int4(0, 0, 0, 0);
@@ -499,6 +505,89 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
     }
 }
 
+// ---------------------------------------------------------------- distributional mode (config 5): evaluator + backup
+// test evaluator, shared definition with oracle/mcts_oracle.c: mo_synthetic_dist
+__global__ void k_eval_synthetic_dist(Arena A) {
+    int n = *A.n_req;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint2 r = A.req[i];
+        int g = (int)r.x, o = (int)(r.y & 0x0fffffffu);
+        const uint32_t *k = A.key + node_at(A, g, o) * KEY_WORDS;
+        uint32_t sum = 0;
+        float *out = A.dist_eval + (size_t)g * A.dist_bins;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int b = 0; b < A.dist_bins; ++b) {
+                uint32_t h = 2166136261u;
+                for (int j = 0; j < 11; ++j) { h ^= k[j]; h *= 16777619u; }
+                h ^= (uint32_t)b * 0x9E3779B9u; h *= 16777619u;
+                h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+                uint32_t raw = ((h >> 9) & 0xffu) + 1u;
+                if (pass == 0) sum += raw; else out[b] = __fdiv_rn((float)raw, (float)sum);
+            }
+    }
+}
+
+// backup_trace_distributional (core_distributional.py:109-124), one warp per game, lanes over the histogram bins.
+// The trace levels are independent of each other (dist and r are fixed), so each level is: shift the evaluator's
+// histogram by (r - reward[idx]) (closed-form gather of shift_distribution, same add order per bin; the clamped top bin is
+// summed sequentially), fold it into the node's running average, update the node's Welford statistics.
+__global__ void __launch_bounds__(128) k_dist_backup(Arena A) {
+    __shared__ float s_dist[4][64];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 4 + wid;
+    if (g >= A.G || A.status[g] != ST_OK) return;
+    const int D = A.trace_len[g], kind = A.leaf_kind[g];
+    if (kind == LEAF_SUSPENDED || D <= 0) return;
+    const int bins = A.dist_bins, T = bins - 1;
+    const int32_t *trace = A.trace + (size_t)g * A.trace_max;
+    const int leaf = trace[D - 1];
+    float *nsb = A.nstat + (size_t)g * A.M * NSTAT_WORDS, *ndb = A.ndist + (size_t)g * A.M * bins;
+    const double r = (double)__int_as_float(A.row[node_at(A, g, leaf) * ROW_WORDS + 23]);   // leaf_game.getScore(), DistValueSimOnline.py:64
+    float *d = s_dist[wid];
+    for (int b = lane; b < bins; b += 32)
+        d[b] = kind == LEAF_EXPANDED ? A.dist_eval[(size_t)g * bins + b] : (b == 0 ? 1.f : 0.f);   // v_dummy, DistValueSimOnline.py:26-27
+    __syncwarp();
+    const double delta = (A.dist_vmax - A.dist_vmin) / bins;
+    double mean = 0.0;                                               // mean_dist, core_distributional.py:39-45 (sequential order)
+    for (int b = 0; b < bins; ++b) mean = __dadd_rn(mean, __dmul_rn((double)d[b], (b + 0.5) * delta));
+    for (int t = 0; t < D; ++t) {
+        const int idx = trace[t];
+        float *ns = nsb + (size_t)idx * NSTAT_WORDS, *nd = ndb + (size_t)idx * bins;
+        const float ns0 = ns[0], ns1 = ns[1], ns2 = ns[2], ns4 = ns[4];
+        const double _r = r - (double)ns2;
+        const double bin_shift = _r / delta, frac = bin_shift - floor(bin_shift);
+        const int s = (int)bin_shift;                                // (int)(b + bin_shift) = b + s for bin_shift >= 0
+        for (int tb = lane; tb < bins; tb += 32) {
+            float acc = 0.f;
+            if (tb < T) {
+                int b1 = tb - s - 1, b2 = tb - s;
+                if (b1 >= 0 && b1 < bins) acc = (float)__dadd_rn((double)acc, __dmul_rn((double)d[b1], frac));          // its upper target
+                if (b2 >= 0 && b2 < bins) acc = (float)__dadd_rn((double)acc, __dmul_rn((double)d[b2], 1.0 - frac));    // its lower target
+            } else {
+                int b0 = T - s - 1;
+                if (b0 >= 0 && b0 < bins) acc = (float)__dadd_rn((double)acc, __dmul_rn((double)d[b0], frac));
+                for (int b = (T - s < 0 ? 0 : T - s); b < bins; ++b) {                                                   // clamped bins
+                    acc = (float)__dadd_rn((double)acc, __dmul_rn((double)d[b], 1.0 - frac));
+                    acc = (float)__dadd_rn((double)acc, __dmul_rn((double)d[b], frac));
+                }
+            }
+            float num = __fadd_rn(__fmul_rn(nd[tb], ns0), acc);
+            nd[tb] = (float)((double)num / ((double)ns0 + 1.0));
+        }
+        if (lane == 0) {
+            const double x = mean + _r;
+            const float n1 = __fadd_rn(ns0, 1.f);
+            const double dl = x - (double)ns1;
+            const float m1 = (float)((double)ns1 + dl / (double)n1);
+            const double dl2 = x - (double)m1;
+            const float m2 = (float)((double)ns4 + dl * dl2);
+            ns[0] = n1; ns[1] = m1; ns[4] = m2;
+            if (n1 > 1.f) ns[3] = (float)((double)m2 / ((double)n1 - 1.0));
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------- compute_stats / get_action (agent.py:153-185)
 __global__ void k_root_stats(Arena A, float *stats, int32_t *action) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,6 +597,19 @@ __global__ void k_root_stats(Arena A, float *stats, int32_t *action) {
     int ro; float rs;
     acc.meta(root, ro, rs);
     float best = 0.f; int arg = 0;
+    if (A.mode == MODE_DIST) {      // DistValueSimOnline.py:77-104: visit, mean + reward - root reward, variance; argmax of row 1
+        const float *nsb = A.nstat + (size_t)g * A.M * NSTAT_WORDS;
+        const float rr = nsb[(size_t)root * NSTAT_WORDS + 2];
+        for (int a = 0; a < 7; ++a) {
+            int c = A.row[node_at(A, g, root) * ROW_WORDS + a];
+            const float *ns = nsb + (size_t)c * NSTAT_WORDS;
+            float val = __fsub_rn(__fadd_rn(ns[1], ns[2]), rr);
+            stats[(size_t)g * 21 + a] = ns[0]; stats[(size_t)g * 21 + 7 + a] = val; stats[(size_t)g * 21 + 14 + a] = ns[3];
+            if (a == 0 || val > best) { best = val; arg = a; }
+        }
+        action[g] = arg;
+        return;
+    }
     for (int a = 0; a < 7; ++a) {
         int c, o; float s;
         acc.children(root, a, c, o, s);

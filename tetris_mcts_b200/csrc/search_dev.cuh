@@ -29,7 +29,8 @@ constexpr int ZTABLE_N = 65536;   // z(n) table computed on the host with the re
 enum : int { ST_OK = 0, ST_ARENA_FULL = 1, ST_TRACE_FULL = 2, ST_NEED_GC = 3 };
 enum : int { LEAF_TERMINAL = 0, LEAF_EXPANDED = 1, LEAF_SUSPENDED = 2 };
 enum : int { PEND_NONE = 0, PEND_EXPAND = 1, PEND_ROOT = 2 };
-enum : int { MODE_LP = 0, MODE_SINGLE = 1, MODE_VANILLA = 2 };
+enum : int { MODE_LP = 0, MODE_SINGLE = 1, MODE_VANILLA = 2, MODE_DIST = 3 };
+constexpr int NSTAT_WORDS = 8;    // node_stats row: {visit, mean, reward, variance, M2, -, -, -} (agents/core_distributional.py:109-124)
 
 // HBM layout (all arrays are [game][...]; SoA across games, records kept 16-byte aligned):
 //   row      [G][M][24] i32/f32  node record: child ids c[0..6], c[7]=episode | child obs o[0..6], o[7]=own obs |
@@ -56,6 +57,8 @@ struct Arena {
     int32_t *gc_list, *pending, *resume_a;   // [G] games waiting for a collection, what to resume, and at which child
     float2 *eval_out;              // [G][8] (value, variance) per child slot; slot 7 = the leaf itself
     float *rollout_val;            // [G]
+    // distributional mode (agents/core_distributional.py; BASELINE config 5): node-indexed statistics and value histograms
+    float *nstat; float *ndist; float *dist_eval; int dist_bins; double dist_vmin, dist_vmax;   // [G][M][8], [G][M][bins], [G][bins]
     unsigned long long *counters;  // [8] 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels 5 rollout steps 6 new nodes
 };
 
@@ -332,7 +335,10 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
         int32_t *r = rowb + (size_t)idx * ROW_WORDS;
         r[7] = A.episode[g]; r[15] = o; r[23] = __float_as_int(sc);
     }
-    if (gp.lane == 0) atomicAdd(&A.counters[6], 1ull);
+    if (gp.lane == 0) {
+        atomicAdd(&A.counters[6], 1ull);
+        if (A.nstat) A.nstat[node_at(A, g, idx) * NSTAT_WORDS + 2] = sc;   // node_stats[idx][2] = reward (core_distributional.py:86,112)
+    }
     gp.sync();
     o_out = o; score_out = sc;
     return idx;
@@ -352,6 +358,11 @@ __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, in
     for (int i = gp.lane; i < M * 3; i += 8) keyb[i] = make_uint4(0, 0, 0, 0);
     uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
     for (int i = gp.lane; i < H; i += 8) { ntab[i] = make_uint2(0, 0); otab[i] = make_uint2(0, 0); }
+    if (A.nstat) {
+        float *ns = A.nstat + (size_t)g * M * NSTAT_WORDS, *nd = A.ndist + (size_t)g * M * A.dist_bins;
+        for (int i = gp.lane; i < M * NSTAT_WORDS; i += 8) ns[i] = 0.f;
+        for (size_t i = gp.lane; i < (size_t)M * A.dist_bins; i += 8) nd[i] = 0.f;
+    }
     int32_t *nfree = A.nfree + (size_t)g * M, *ofree = A.ofree + (size_t)g * M;
     for (int i = gp.lane; i < M - 1; i += 8) { nfree[i] = i + 1; ofree[i] = i + 1; }
     if (gp.lane == 0) { A.n_nfree[g] = M - 1; A.n_ofree[g] = M - 1; atomicAdd(&A.counters[7], 1ull); }
@@ -485,6 +496,75 @@ __device__ __forceinline__ void lp_backup(const Acc &acc, int D, int k, const in
         if (mixture) backup_trace_mixture(acc, D, (double)leaf_score, 0.0, gamma);
         else backup_trace(acc, D, (double)leaf_score, 0.0, gamma);
     }
+}
+
+// ------------------------------------------------------------------ distributional select (core_distributional.py:82-106)
+// Group form of dist_dev.cuh: dist_select_trace on the packed arena.  Unique children are ordered by ascending node index
+// (the documented stand-in for numba's set order); lane a holds child slot a.
+__device__ __forceinline__ double dist_z(double n) {
+    double alpha = 1.0 - 1.0 / n;
+    return 10.0 * log(1.0 - log(-log(alpha) / log(2.0)) / log(22.0)) / log(41.0);
+}
+
+__device__ __forceinline__ int dist_select_group(const Arena &A, const Grp &gp, int g, int root, int &D_out, int &status) {
+    int idx = root, D = 0;
+    const float *nsb = A.nstat + (size_t)g * A.M * NSTAT_WORDS;
+    for (;;) {
+        if (D >= A.trace_max) { status = ST_TRACE_FULL; break; }
+        if (gp.lane == 0) A.trace[(size_t)g * A.trace_max + D] = idx;
+        ++D;
+        const int32_t *row = A.row + node_at(A, g, idx) * ROW_WORDS;
+        int c = gp.lane < 7 ? row[gp.lane] : 0;
+        bool uniq = c != 0;
+        int rank = 0;                                    // position of this child in ascending-index order among the unique ones
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            int cj = gp.bcast(c, j);
+            if (cj != 0 && cj == c && j < gp.lane) uniq = false;
+        }
+        unsigned umask = gp.ballot(uniq);
+        if (umask == 0) break;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            int cj = gp.bcast(c, j);
+            if (((umask >> j) & 1u) && cj < c) ++rank;
+        }
+        float4 ns = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (uniq) ns = *reinterpret_cast<const float4 *>(nsb + (size_t)c * NSTAT_WORDS);    // visit, mean, reward, variance
+        const double r = (double)nsb[(size_t)idx * NSTAT_WORDS + 2];
+        unsigned lowmask = gp.ballot(uniq && ns.x < (float)A.low);
+        int pick_lane = -1;
+        if (lowmask) {                                   // agents/core.py:462-468 check_low: uniform pick among the low children
+            uint32_t x = 0;
+            if (gp.lane == 0) { uint32_t sr = A.srng[g]; x = rng_next(sr); A.srng[g] = sr; }
+            x = gp.bcast(x, 0);
+            int want = (int)(x % (uint32_t)__popc(lowmask));
+            int lrank = 0;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                int cj = gp.bcast(c, j);
+                if (((lowmask >> j) & 1u) && cj < c) ++lrank;
+            }
+            pick_lane = __ffs(gp.ballot(((lowmask >> gp.lane) & 1u) && lrank == want)) - 1;
+        } else {                                         // policy_dist, core_distributional.py:66-79
+            double n = uniq ? (double)ns.x : 0.0;        // visits are integers: the double sum is exact in any order
+            n += __shfl_xor_sync(gp.mask, n, 1, 8); n += __shfl_xor_sync(gp.mask, n, 2, 8); n += __shfl_xor_sync(gp.mask, n, 4, 8);
+            const double z = dist_z(n);
+            float s0 = (float)((double)__fadd_rn(ns.y, ns.z) - r);
+            float s1 = (float)((double)ns.w / ((double)ns.x + 1e-3));
+            double q = (double)s0 + z * (double)__fsqrt_rn(s1);
+            double bq = 0.0;
+            const int k = __popc(umask);
+            for (int rr = 0; rr < k; ++rr) {             // np.argmax over the ascending list: first maximum
+                int L = __ffs(gp.ballot(uniq && rank == rr)) - 1;
+                double qL = gp.bcast(q, L);
+                if (rr == 0 || qL > bq) { bq = qL; pick_lane = L; }
+            }
+        }
+        idx = gp.bcast(c, pick_lane);
+    }
+    D_out = D;
+    return idx;
 }
 
 // Scalar form of core.h:111-144 for one thread (backup side): fills c_obs / c_score(rep) / first-slot list.

@@ -12,8 +12,9 @@ from . import _lib as L
 class BatchedEngine:
     def __init__(self, n_games, max_nodes=8192, mode="lp", gamma=None, low=None, eval_kind="net", weights=None,
                  env_args=((20, 10), 1, 0, 0), seed=123, device=0, lp_end_from_obs=False, lp_var_gamma2=True,
-                 stale_pop=True, rollout_variance=1e3, trace_max=512, overflow_reset=False):
-        mode_id = {"lp": L.MODE_LP, "single": L.MODE_SINGLE, "vanilla": L.MODE_VANILLA}[mode] if isinstance(mode, str) else int(mode)
+                 stale_pop=True, rollout_variance=1e3, trace_max=512, overflow_reset=False, dist_bins=50, dist_vmin=0.0, dist_vmax=5000.0,
+                 dist_weights=None):
+        mode_id = {"lp": L.MODE_LP, "single": L.MODE_SINGLE, "vanilla": L.MODE_VANILLA, "dist": L.MODE_DIST}[mode] if isinstance(mode, str) else int(mode)
         eval_id = {"synthetic": L.EVAL_SYNTHETIC, "net": L.EVAL_NET, "net_tc": L.EVAL_NET_TC}[eval_kind] if isinstance(eval_kind, str) else int(eval_kind)
         if tuple(env_args[0]) != (20, 10):
             raise ValueError("only 20x10 boards (SPEC_PYTETRIS.md §1)")
@@ -21,7 +22,9 @@ class BatchedEngine:
         cfg.n_games, cfg.max_nodes, cfg.mode = int(n_games), int(max_nodes), mode_id
         # reference defaults: ValueSim.py:14 gamma=0.999, ValueSimLP.py:27 low=1; Vanilla.py:9 gamma=0.99, :27 low=5
         cfg.gamma = float(gamma if gamma is not None else (0.99 if mode_id == L.MODE_VANILLA else 0.999))
-        cfg.low = int(low if low is not None else (5 if mode_id == L.MODE_VANILLA else 1))
+        # distributional cores: select_trace_distributional(..., low=5) (agents/core_distributional.py:83)
+        cfg.low = int(low if low is not None else (5 if mode_id in (L.MODE_VANILLA, L.MODE_DIST) else 1))
+        cfg.dist_bins, cfg.dist_vmin, cfg.dist_vmax = int(dist_bins), float(dist_vmin), float(dist_vmax)
         cfg.lp_end_from_obs, cfg.lp_var_gamma2, cfg.stale_pop = int(lp_end_from_obs), int(lp_var_gamma2), int(stale_pop)
         cfg.eval_kind, cfg.trace_max, cfg.overflow_reset = eval_id, int(trace_max), int(overflow_reset)
         cfg.actions_per_drop, cfg.scoring, cfg.randomizer = int(env_args[1]), int(env_args[2]), int(env_args[3])
@@ -32,6 +35,8 @@ class BatchedEngine:
         L.check(L.lib().b200_engine_create(C.byref(cfg), C.byref(self.h)))
         if weights is not None:
             self.load_weights(weights)
+        if dist_weights is not None:
+            self.load_dist_weights(dist_weights, dist_bins)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -51,6 +56,27 @@ class BatchedEngine:
         if w.size != L.N_WEIGHTS:
             raise ValueError("expected %d floats (state_dict order), got %d" % (L.N_WEIGHTS, w.size))
         L.check(L.lib().b200_load_weights(self.h, L.ptr(w)))
+
+    def load_dist_weights(self, weights, atoms=50):
+        """model/model_distributional.py Net state_dict tensors concatenated (seq.conv1 ... seq.fc_v)."""
+        w = np.ascontiguousarray(weights, np.float32).ravel()
+        need = 512 + 32 + 16384 + 32 + 128 * 2048 + 128 + atoms * 128 + atoms
+        if w.size != need:
+            raise ValueError("expected %d floats, got %d" % (need, w.size))
+        L.check(L.lib().b200_load_dist_weights(self.h, L.ptr(w), int(atoms)))
+        self._atoms = int(atoms)
+
+    def distnet(self, states):
+        s = np.ascontiguousarray(states, np.int8).reshape(-1, 200)
+        out = np.zeros((len(s), self._atoms), np.float32)
+        L.check(L.lib().b200_distnet_forward(self.h, L.ptr(s), len(s), self._atoms, L.ptr(out)))
+        return out
+
+    def export_dist(self, game):
+        ns = np.zeros((self.max_nodes, 5), np.float32)
+        nd = np.zeros((self.max_nodes, int(self.cfg.dist_bins)), np.float32)
+        L.check(L.lib().b200_export_dist(self.h, int(game), L.ptr(ns), L.ptr(nd)))
+        return ns, nd
 
     # ------------------------------------------------------------------ games
     def set_games(self, recs):
