@@ -147,6 +147,13 @@ int b200_export_dist(b200_engine *e, int game, float *node_stats /* [M][5] */, f
  *     out_dev is a DEVICE buffer of capacity*212 bytes (e.g. a torch tensor handed to the NCCL all-gather). */
 int b200_collect_samples_dev(b200_engine *e, int min_visits, void *out_dev, int capacity, int32_t *count_out);
 
+/* --- online replay memory (ValueSim.memory agents/ValueSim.py:14-37; OnlineMCTSAgent agent.cpp:588-617): when enabled, every
+ *     garbage collection appends the observations it frees that have visit >= min_visits and are not `end`
+ *     (store_nodes, ValueSim.py:122-159 / agent.cpp:777-819) until `capacity` rows are held.  b200_replay_drain_dev copies the
+ *     rows to a DEVICE buffer (trainer input / NCCL all-gather block) and empties the memory (ValueSim.py:183). */
+int b200_replay_enable(b200_engine *e, int min_visits, int capacity);
+int b200_replay_drain_dev(b200_engine *e, void *out_dev, int capacity, int32_t *count_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,6 +237,7 @@ struct mo_agent {
     int overflow;
     uint8_t *end_scratch;
     float *nstat, *ndist;          /* MO_MODE_DIST: node_stats f32[M][5], node_dist f32[M][bins] */
+    uint8_t *replay_rows; int replay_n;   /* ValueSim.memory rows (212 B), filled by remove_nodes */
 };
 
 static uint64_t hash_words(const uint32_t *w, int n) {
@@ -345,6 +346,23 @@ static void remove_nodes(mo_agent *a) {
         memset(a->child + (size_t)i * MO_NA, 0, sizeof(int32_t) * MO_NA);
         a->visit_n[i] = 0; a->value_n[i] = 0; a->variance_n[i] = 0; a->episode_n[i] = 0; a->score[i] = 0; a->end_n[i] = 0;
         if (a->nstat) { memset(a->nstat + (size_t)i * 5, 0, 20); memset(a->ndist + (size_t)i * a->cfg.dist_bins, 0, 4 * (size_t)a->cfg.dist_bins); }
+    }
+    /* ValueSim.remove_nodes -> store_nodes(self.obs_available) (ValueSim.py:101-159): freed observations with
+     * visit >= min_visits_to_store and not end, in ascending index order, until the memory is full */
+    if (a->cfg.replay_cap > 0) {
+        if (!a->replay_rows) { a->replay_rows = (uint8_t *)malloc((size_t)a->cfg.replay_cap * 212); a->replay_n = 0; }
+        for (int j = 0; j < a->n_oavail && a->replay_n < a->cfg.replay_cap; ++j) {
+            int i = a->oavailable[j];
+            if (a->ovisit[i] < a->cfg.replay_min_visits || a->ovisit[i] == 0 || a->oend[i]) continue;
+            uint8_t *dst = a->replay_rows + (size_t)a->replay_n * 212;
+            const uint32_t *key = a->ostate + (size_t)i * TO_OBSKEY_WORDS;
+            for (int r = 0; r < 20; ++r)
+                for (int c = 0; c < 10; ++c) dst[r * 10 + c] = (uint8_t)((key[r >> 1] >> ((r & 1) * 16 + c)) & 1);
+            for (int q = 0; q < 4; ++q) dst[(key[10] >> (8 * q)) & 0xff] = 0xff;
+            float f[3] = {a->ovalue[i], a->ovariance[i], (float)a->ovisit[i]};
+            memcpy(dst + 200, f, 12);
+            a->replay_n += 1;
+        }
     }
     for (int j = 0; j < a->n_oavail; ++j)
         tab_erase(&a->otab, a->ostate, a->ostate + (size_t)a->oavailable[j] * TO_OBSKEY_WORDS);
@@ -586,6 +604,13 @@ void mo_agent_export(const mo_agent *a, int32_t *child, float *score, int32_t *e
     if (obs_end) memcpy(obs_end, a->oend, M);
     if (game_recs) memcpy(game_recs, a->game, M * TO_RECORD_WORDS * 4);
     if (obs_keys) memcpy(obs_keys, a->ostate, M * TO_OBSKEY_WORDS * 4);
+}
+
+int mo_agent_replay(mo_agent *a, uint8_t *rows212, int max_rows) {   /* copy out and empty (ValueSim.py:183 memory_index = 0) */
+    int n = a->replay_n < max_rows ? a->replay_n : max_rows;
+    if (n > 0 && rows212) memcpy(rows212, a->replay_rows, (size_t)n * 212);
+    a->replay_n = 0;
+    return n;
 }
 
 void mo_agent_export_dist(const mo_agent *a, float *node_stats, float *node_dist) {

@@ -58,6 +58,7 @@ typedef struct {
     int stale_pop;         /* agent.py:229-232 erases by the freed slot's STALE game; 1 = reproduce */
     int dist_bins;         /* MO_MODE_DIST: atoms (DistValueSimOnline.py:13: 50) */
     double dist_vmin, dist_vmax;   /* value range (DistValueSimOnline.py:13: 0, 5000) */
+    int replay_min_visits, replay_cap;   /* ValueSim.py:14 min_visits_to_store / memory_size; 0 = no replay memory */
 } mo_config;
 
 typedef struct mo_agent mo_agent;
@@ -67,6 +68,7 @@ void mo_agent_update_root(mo_agent *a, const uint32_t *rec20);            /* age
 int mo_agent_mcts(mo_agent *a, int sims);                                 /* ValueSimLP.py:13-70 etc.; returns 0 or <0 on arena overflow */
 int mo_agent_get_action(mo_agent *a, float *stats21);                     /* agent.py:153-185 */
 int mo_agent_root(const mo_agent *a);
+int mo_agent_replay(mo_agent *a, uint8_t *rows212, int max_rows);   /* ValueSim.memory rows stored by remove_nodes; empties the memory */
 int mo_agent_episode(const mo_agent *a);
 long mo_agent_counter(const mo_agent *a, int which); /* 0 sims, 1 expansions, 2 evals, 3 gcs, 4 trace levels, 5 rollout steps */
 /* export in the reference's array layout (agent.py:58-88); any pointer may be NULL */

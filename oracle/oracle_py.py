@@ -44,6 +44,7 @@ class MoConfig(C.Structure):
         ("lp_end_from_obs", C.c_int), ("lp_var_gamma2", C.c_int), ("rollout_variance", C.c_double),
         ("eval_mode", C.c_int), ("weights", C.c_void_p), ("eval_cb", C.c_void_p), ("eval_ctx", C.c_void_p),
         ("search_seed", C.c_uint32), ("stale_pop", C.c_int), ("dist_bins", C.c_int), ("dist_vmin", C.c_double), ("dist_vmax", C.c_double),
+        ("replay_min_visits", C.c_int), ("replay_cap", C.c_int),
     ]
 
 
@@ -233,8 +234,9 @@ class Agent:
 
     def __init__(self, max_nodes=100000, mode=0, gamma=0.999, low=1, eval_mode=0, weights=None, eval_cb=None,
                  lp_end_from_obs=0, lp_var_gamma2=1, rollout_variance=1e3, search_seed=0, stale_pop=1,
-                 app=1, scoring=0, randomizer=0, dist_bins=50, dist_vmin=0.0, dist_vmax=5000.0):
+                 app=1, scoring=0, randomizer=0, dist_bins=50, dist_vmin=0.0, dist_vmax=5000.0, replay_min_visits=0, replay_cap=0):
         cfg = MoConfig()
+        cfg.replay_min_visits, cfg.replay_cap = replay_min_visits, replay_cap
         cfg.dist_bins, cfg.dist_vmin, cfg.dist_vmax = dist_bins, dist_vmin, dist_vmax
         self.dist_bins = dist_bins
         cfg.max_nodes, cfg.mode, cfg.gamma, cfg.low = max_nodes, mode, gamma, low
@@ -295,6 +297,12 @@ class Agent:
         lib().mo_agent_export(self.h, _p(d["child"]), _p(d["score"]), _p(d["episode"]), _p(d["n2o"]), _p(d["visit"]),
                               _p(d["value"]), _p(d["variance"]), _p(d["obs_end"]), _p(d["game"]), _p(d["obs_key"]))
         return d
+
+    def replay(self, max_rows=1 << 20):
+        rows = np.zeros((max_rows, 212), np.uint8)
+        lib().mo_agent_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        n = lib().mo_agent_replay(self.h, _p(rows), max_rows)
+        return rows[:n].copy()
 
     def export_dist(self):
         ns = np.zeros((self.M, 5), np.float32)

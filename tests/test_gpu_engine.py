@@ -179,3 +179,43 @@ def test_full_size_properties(gpu_lib):
         outs.append((stats.copy(), action.copy()))
         eng.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_replay_memory_filled_at_garbage_collection(gpu_lib, oracle):
+    """ValueSim.remove_nodes -> store_nodes(obs_available) (agents/ValueSim.py:101-159): the observations a collection frees,
+    with visit >= min_visits_to_store and not end, as 212-byte rows.  The device stores them in arbitrary order, the
+    reference in ascending index order: compared as sorted row sets."""
+    import torch
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    n, M, sims, moves, seed, minv = 6, 1500, 12, 100, 123, 3
+    recs = PT.new_games(n, ARGS, np.arange(seed, seed + n, dtype=np.uint32))
+    eng = BatchedEngine(n, max_nodes=M, mode="lp", eval_kind="synthetic", seed=seed)
+    eng.replay_enable(min_visits=minv, capacity=100000)
+    eng.set_games(recs)
+    agents = [oracle.Agent(max_nodes=M, mode=0, gamma=0.999, low=1, eval_mode=0, search_seed=search_seed(seed, g),
+                           replay_min_visits=minv, replay_cap=100000) for g in range(n)]
+    games = [oracle.Game(record=recs[g]) for g in range(n)]
+    for g in range(n):
+        agents[g].update_root(games[g].record())
+    for mv in range(moves):
+        actions, _ = eng.play_move(sims, auto_reset=True)
+        for g in range(n):
+            agents[g].mcts(sims)
+            a, _st = agents[g].get_action()
+            assert a == actions[g]
+            games[g].play(a)
+            agents[g].update_root(games[g].record())
+            if games[g].end:
+                games[g].reset()
+                agents[g].update_root(games[g].record())
+    want = np.concatenate([ag.replay() for ag in agents])
+    assert len(want) > 50 and eng.counters()["gcs"] > 0
+    buf = torch.zeros((100000, 212), dtype=torch.uint8, device="cuda")
+    cnt = eng.replay_drain_into(buf.data_ptr(), 100000)
+    got = buf[:cnt].cpu().numpy()
+    assert cnt == len(want)
+    key = lambda a: a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(key(got), key(want))
+    assert eng.replay_drain_into(buf.data_ptr(), 100000) == 0          # drained: memory_index = 0 (ValueSim.py:183)
+    eng.close()

@@ -75,6 +75,8 @@ def lib():
         L.b200_get_unique_child_obs.argtypes = [C.c_int, P, P, P, C.c_int, P, P, P]
         L.b200_get_all_childs.argtypes = [C.c_int, P, C.c_int, P]
         L.b200_collect_samples_dev.argtypes = [P, C.c_int, P, C.c_int, P]
+        L.b200_replay_enable.argtypes = [P, C.c_int, C.c_int]
+        L.b200_replay_drain_dev.argtypes = [P, P, C.c_int, P]
         L.b200_load_dist_weights.argtypes = [P, P, C.c_int]
         L.b200_distnet_forward.argtypes = [P, P, C.c_int, C.c_int, P]
         L.b200_export_dist.argtypes = [P, C.c_int, P, P]

@@ -950,6 +950,34 @@ __global__ void k_collect_samples(Arena A, int min_visits, uint8_t *out, int cap
     }
 }
 
+// Online replay memory (agents/ValueSim.py:14-37, agent.cpp:588-617): allocate `capacity` rows; k_gc appends to it.
+extern "C" int b200_replay_enable(b200_engine *e, int min_visits, int capacity) {
+    if (!e || capacity < 1 || min_visits < 0) return fail(B200_ERR_BAD_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->A.replay) return fail(B200_ERR_BAD_ARG, "replay memory already enabled");
+    if (dalloc(e, &e->A.replay, (size_t)capacity * 212) || dalloc(e, &e->A.replay_count, 1)) return B200_ERR_CUDA;
+    e->A.replay_cap = capacity; e->A.replay_min_visits = min_visits;
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+// Hand the stored rows to the trainer / the all-gather: copies min(count, capacity) rows to out_dev (DEVICE) and empties the memory
+// (memory_index = 0 after training, ValueSim.py:183 / agent.cpp:700).
+extern "C" int b200_replay_drain_dev(b200_engine *e, void *out_dev, int capacity, int32_t *count_out) {
+    if (!e || !out_dev || !count_out || !e->A.replay) return fail(B200_ERR_BAD_ARG, "replay memory not enabled / bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    int32_t n = 0;
+    CK(cudaMemcpyAsync(&n, e->A.replay_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n > e->A.replay_cap) n = e->A.replay_cap;
+    if (n > capacity) n = capacity;
+    if (n > 0) CK(cudaMemcpyAsync(out_dev, e->A.replay, (size_t)n * 212, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemsetAsync(e->A.replay_count, 0, 4, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *count_out = n;
+    return B200_OK;
+}
+
 extern "C" int b200_collect_samples_dev(b200_engine *e, int min_visits, void *out_dev, int capacity, int32_t *count_out) {
     if (!e || !out_dev || capacity < 0 || !count_out) return fail(B200_ERR_BAD_ARG, "bad argument");
     CK(cudaSetDevice(e->cfg.device));

@@ -360,6 +360,27 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
         }
         int4 *statb = A.stat + (size_t)g * M;
         uint4 *keyb = reinterpret_cast<uint4 *>(A.key + (size_t)g * M * KEY_WORDS);
+        // store_nodes (agents/ValueSim.py:122-159, agent.cpp:777-819): freed observations with visit >= min_visits_to_store and not
+        // `end` go to the replay memory before their statistics are zeroed; storing stops when the memory is full (ValueSim.py:152-154)
+        if (A.replay) {
+            for (int i = t; i < no; i += GC_THREADS) {
+                const int o = ofree[i];
+                const int4 st = statb[o];
+                if (st.x < A.replay_min_visits || st.x == 0 || st.w != 0) continue;
+                const int slot = atomicAdd(A.replay_count, 1);
+                if (slot >= A.replay_cap) { atomicSub(A.replay_count, 1); continue; }
+                uint8_t *dst = A.replay + (size_t)slot * 212;
+                const uint32_t *k = A.key + ((size_t)g * M + o) * KEY_WORDS;
+                for (int r = 0; r < 20; ++r) {
+                    const uint32_t row = (k[r >> 1] >> ((r & 1) * 16)) & 0x3ffu;
+                    for (int c = 0; c < 10; ++c) dst[r * 10 + c] = (uint8_t)((row >> c) & 1u);
+                }
+                for (int j = 0; j < 4; ++j) dst[(k[10] >> (8 * j)) & 0xffu] = 0xff;            // int8 -1: the falling piece
+                const float f[3] = {__int_as_float(st.y), __int_as_float(st.z), (float)st.x};
+                memcpy(dst + 200, f, 12);
+            }
+            __syncthreads();
+        }
         for (int i = t; i < no; i += GC_THREADS) statb[ofree[i]] = make_int4(0, 0, 0, 0);
         for (int i = t; i < no * 3; i += GC_THREADS) keyb[(size_t)ofree[i / 3] * 3 + (i % 3)] = make_uint4(0, 0, 0, 0);
         if (t == 0) {

@@ -55,6 +55,9 @@ struct Arena {
     const float *ztable;
     uint2 *req; int32_t *n_req;    // evaluation requests {game, obs | slot<<28}; n_req[0] = count, n_req[1] = games queued for k_gc
     int32_t *gc_list, *pending, *resume_a;   // [G] games waiting for a collection, what to resume, and at which child
+    // replay memory (ValueSim.memory, agents/ValueSim.py:25-30; agent.cpp:610-613): 212-byte rows {int8 state[200], f32 value,
+    // f32 variance, f32 visit}, filled by k_gc from the observations a collection frees (ValueSim.py:101-159)
+    uint8_t *replay; int32_t *replay_count; int replay_cap, replay_min_visits;
     float2 *eval_out;              // [G][8] (value, variance) per child slot; slot 7 = the leaf itself
     float *rollout_val;            // [G]
     // distributional mode (agents/core_distributional.py; BASELINE config 5): node-indexed statistics and value histograms

@@ -173,6 +173,15 @@ class BatchedEngine:
         L.check(L.lib().b200_valuenet_forward(self.h, L.ptr(s), len(s), L.ptr(v), L.ptr(var)))
         return v, var
 
+    def replay_enable(self, min_visits=25, capacity=500000):
+        """ValueSim(online=True) replay memory (agents/ValueSim.py:14-37; min_visits_to_store=25 for ValueSimLP.py:11)."""
+        L.check(L.lib().b200_replay_enable(self.h, int(min_visits), int(capacity)))
+
+    def replay_drain_into(self, dev_ptr, capacity):
+        cnt = np.zeros(1, np.int32)
+        L.check(L.lib().b200_replay_drain_dev(self.h, C.c_void_p(int(dev_ptr)), int(capacity), L.ptr(cnt)))
+        return int(cnt[0])
+
     def collect_samples_into(self, dev_ptr, capacity, min_visits):
         """ValueSim.store_nodes-style samples (agents/ValueSim.py:122-159) written to a DEVICE buffer of 212-byte rows."""
         cnt = np.zeros(1, np.int32)
