@@ -154,14 +154,17 @@ __device__ __forceinline__ void request_lp_evals(const Arena &A, const Grp &gp, 
 }
 
 // ---------------------------------------------------------------- select + expand (ValueSimLP.py:45-57 etc.)
-__global__ void __launch_bounds__(TPB) k_select_expand(Arena A) {
+__global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
+    __shared__ float s_z[ZS_N];
+    for (int i = threadIdx.x; i < ZS_N; i += TPB) s_z[i] = A.ztable[i];
+    __syncthreads();
     Grp gp;
     int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
     if (g >= A.G) return;
     int status = A.status[g];
     if (status == ST_ARENA_FULL && A.overflow_reset) reset_tree(A, gp, g, status);
     if (status != ST_OK) return;
-    ArenaAcc acc{A, g};
+    ArenaAcc acc{A, g, s_z};
     int D = 0;
     int leaf = A.mode == MODE_DIST ? dist_select_group(A, gp, g, A.root[g], D, status)
                                    : select_trace(acc, gp, A.root[g], A.low, A.trace_max, D, status);

@@ -145,8 +145,10 @@ __device__ __forceinline__ Uniq unique_children(const Grp &gp, int c, int o, flo
 // ------------------------------------------------------------------ accessors
 // The engine keeps the packed arena above; the single-call twins of agents/cppmodule/core.cpp:20-26 work on the
 // reference's own array layout (agents/agent.py:58-88).  Both run the same select / backup code through these.
+constexpr int ZS_N = 4096;   // z(n) entries staged in shared memory by k_select_expand (deep nodes have small n)
+
 struct ArenaAcc {
-    const Arena &A; int g;
+    const Arena &A; int g; const float *zs = nullptr;
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
         const int32_t *row = A.row + node_at(A, g, idx) * ROW_WORDS;
         c = row[lane]; o = row[8 + lane]; s = __int_as_float(row[16 + lane]);   // lane 7: own episode / obs / score
@@ -160,7 +162,7 @@ struct ArenaAcc {
     __device__ __forceinline__ void put_trace(int d, int idx) const { A.trace[(size_t)g * A.trace_max + d] = idx; }
     __device__ __forceinline__ int get_trace(int d) const { return A.trace[(size_t)g * A.trace_max + d]; }
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
-    __device__ __forceinline__ float z(int n) const { return ztab(A, n); }
+    __device__ __forceinline__ float z(int n) const { return (zs && n >= 0 && n < ZS_N) ? zs[n] : ztab(A, n); }
 };
 
 struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
