@@ -279,11 +279,25 @@ __device__ __forceinline__ void table_insert(const Grp &gp, uint2 *tab, int H, u
 // ------------------------------------------------------------------ new_node (agent.py:90-130)
 // `w` = packed game, held identically by all lanes.  Returns node index (0 on arena overflow); o_out/score_out are
 // the node's observation and score (what the parent's row caches for it).
-__device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, const uint32_t (&w)[REC_WORDS], int &o_out,
+// Pre-digested game: what new_node needs besides the record itself.  expand_leaf computes it once per child, in parallel
+// (lane a digests child a), instead of all eight lanes re-deriving every child's hashes and observation key in turn.
+struct Digest { uint32_t h, hk; uint32_t key[KEY_WORDS]; int end; float score; };
+
+__device__ __forceinline__ void digest_game(const uint32_t (&w)[REC_WORDS], Digest &d) {
+    d.h = fold32(hash_words(w, REC_WORDS));
+    Game gm;
+    unpack(gm, w);
+    obskey(gm, d.key);
+    d.hk = fold32(hash_words(d.key, KEY_WORDS));
+    d.end = gm.end;
+    d.score = (float)gm.score;                                              // agent.py:106 score[idx] = game.score
+}
+
+__device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, const uint32_t (&w)[REC_WORDS], const Digest &dg, int &o_out,
                                         float &score_out, int &status, bool may_suspend) {
     const int M = A.M, H = A.H;
     uint2 *ntab = A.ntab + (size_t)g * H;
-    uint32_t h = fold32(hash_words(w, REC_WORDS));
+    const uint32_t h = dg.h;
     int idx = table_find<REC_WORDS>(gp, ntab, H, A.rec, (size_t)g * M, w, h);
     int32_t *rowb = A.row + (size_t)g * M * ROW_WORDS;
     if (idx) {
@@ -310,11 +324,8 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
     gp.sync();
     table_insert(gp, ntab, H, h, idx);
     // observation (agent.py:114-128)
-    Game gm;
-    unpack(gm, w);
-    uint32_t key[KEY_WORDS];
-    obskey(gm, key);
-    uint32_t hk = fold32(hash_words(key, KEY_WORDS));
+    const uint32_t (&key)[KEY_WORDS] = dg.key;
+    const uint32_t hk = dg.hk;
     uint2 *otab = A.otab + (size_t)g * H;
     int o = table_find<KEY_WORDS>(gp, otab, H, A.key, (size_t)g * M, key, hk);
     if (!o) {
@@ -323,7 +334,7 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
         gp.sync();
         if (gp.lane == 0) {
             A.n_ofree[g] = nof - 1;
-            A.stat[node_at(A, g, o)] = make_int4(0, 0, 0, gm.end);
+            A.stat[node_at(A, g, o)] = make_int4(0, 0, 0, dg.end);
         }
         if (gp.lane >= 1 && gp.lane < 4) {
             int k = (gp.lane - 1) * 4;
@@ -335,7 +346,7 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
         gp.sync();
         table_insert(gp, otab, H, hk, o);
     }
-    float sc = (float)gm.score;                                             // agent.py:106 score[idx] = game.score
+    const float sc = dg.score;
     if (gp.lane == 7) {
         int32_t *r = rowb + (size_t)idx * ROW_WORDS;
         r[7] = A.episode[g]; r[15] = o; r[23] = __float_as_int(sc);
@@ -347,6 +358,13 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
     gp.sync();
     o_out = o; score_out = sc;
     return idx;
+}
+
+__device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, const uint32_t (&w)[REC_WORDS], int &o_out,
+                                        float &score_out, int &status, bool may_suspend) {
+    Digest dg;
+    digest_game(w, dg);
+    return new_node(A, gp, g, w, dg, o_out, score_out, status, may_suspend);
 }
 
 // ------------------------------------------------------------------ overflow policy (beyond the reference)
@@ -391,11 +409,13 @@ __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, in
 __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g, int leaf, const uint32_t (&leafrec)[REC_WORDS],
                                             int &c, int &o, float &s, int &status, int a_begin, bool may_suspend, int &a_stop) {
     uint32_t mine[REC_WORDS];
+    Digest dmine;
     {
         Game gm;
         unpack(gm, leafrec);
         play(gm, gp.lane < 7 ? gp.lane : 0);
         pack(gm, mine);
+        digest_game(mine, dmine);
     }
     c = 0; o = 0; s = 0.f;
     a_stop = N_ACTIONS;
@@ -403,8 +423,12 @@ __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g
         uint32_t w[REC_WORDS];
 #pragma unroll
         for (int q = 0; q < REC_WORDS; ++q) w[q] = gp.bcast(mine[q], a);
+        Digest dg;
+        dg.h = gp.bcast(dmine.h, a); dg.hk = gp.bcast(dmine.hk, a); dg.end = gp.bcast(dmine.end, a); dg.score = gp.bcast(dmine.score, a);
+#pragma unroll
+        for (int q = 0; q < KEY_WORDS; ++q) dg.key[q] = gp.bcast(dmine.key[q], a);
         int oo; float ss;
-        int idx = new_node(A, gp, g, w, oo, ss, status, may_suspend);
+        int idx = new_node(A, gp, g, w, dg, oo, ss, status, may_suspend);
         if (status == ST_NEED_GC) { a_stop = a; break; }     // resume at this child after k_gc
         if (gp.lane == a) { c = idx; o = oo; s = ss; }
         // agent.py:145 writes child[i] as soon as new_node returns, so a collection triggered by a later
