@@ -321,14 +321,16 @@ def run_b200(args, cfg):
                 ach = boards * CONV_FLOP / (conv_ms / 1e3) / 1e12
                 kname = "k_vn_conv" if cfg["eval"] == "net" else "k_tc_conv"
                 roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
-                        "traffic": ncu_traffic(kname), "kernel": kname, "mma_flops_issued_per_launch": boards * 2 * 128 * 16 * (64 + 32) * 18 * 2 / conv_n, "ms_per_launch": conv_ms / conv_n,
+                        "traffic": ncu_traffic(kname), "kernel": kname, "mma_flops_issued_per_launch": boards * 2 * 128 * 16 * (96 * 36 + 64 * 2) / conv_n, "ms_per_launch": conv_ms / conv_n,
                         "flops_per_launch": boards * CONV_FLOP / conv_n, "boards_per_launch": boards / conv_n,
                         "fc_kernel_tflops": boards * FC_FLOP / (fc_ms / 1e3) / 1e12 if fc_ms > 0 else None,
                         "share_of_step": conv_ms / ms, "peak_src": peaks["src"] + " bf16 dense, sustained",
                         "note": "achieved counts ALGORITHMIC conv FLOPs (SURVEY 8d: 2 884 608 per board).  fp32-faithful arithmetic (north_star 1e-5): "
                                 "eval=net is CUDA-core fp32 FMA; eval=net_tc is tcgen05 kind::f16 with every fp32 operand split into two scaled fp16 terms "
-                                "(3 products per algorithmic product, M=128 pixel tiles with 25-56% halo rows), so the tensor pipe executes "
-                                "mma_flops_issued_per_launch; the bf16 peak is the driver-measured denominator, not this kernel's attainable ceiling"}
+                                "(3 products per algorithmic product; M=128 pixel tiles on an 8-wide grid carry 25-56% halo rows; per board 2x18 MMAs of 128x96x16 "
+                                "plus 2 of 128x64x16 for conv1), so the tensor pipe executes mma_flops_issued_per_launch.  scripts/probe/mma_probe.cu "
+                                "measures SS-mode tcgen05.mma at (A+B operand bytes)/128 B/clk with a 44.7 clk floor: these small-N MMAs are shared-memory "
+                                "operand-fetch bound, not tensor-rate bound; the bf16 peak is the driver-measured denominator, not this kernel's ceiling"}
         else:
             ro_ms, ro_n = phases["rollout"]
             roof = {"bound": "hbm", "achieved": 0.0, "peak": peaks["hbm"], "unit": "GB/s", "frac": 0.0, "traffic": None, "kernel": "k_rollout",

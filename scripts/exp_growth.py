@@ -29,6 +29,6 @@ from tetris_mcts_b200 import _lib as L
 pr = np.zeros(16, np.uint64)
 L.lib().b200_debug_prof.argtypes = [L.P, L.P]
 L.check(L.lib().b200_debug_prof(eng.h, L.ptr(pr)))
-names = ['decode', 'conv1', 'wait_c2', 'epi2', 'wait_c3', 'epi3', 'iss_wait_a1', 'iss_conv2', 'iss_wait_a2', 'iss_conv3']
-tot = pr[:6].sum()
-print({n: round(float(pr[i]) / max(float(tot), 1), 3) for i, n in enumerate(names)}, 'worker cycles total', int(tot))
+names = ['S0_im2col', 'wait_c1', 'E1', 'wait_c2', 'E2', 'wait_c3', 'E3', '-', 'iss_wait_a0', 'iss_conv1', 'iss_wait_a1', 'iss_conv2', 'iss_wait_a2', 'iss_conv3']
+tot = pr[:7].sum()
+print({n: round(float(pr[i]) / max(float(tot), 1), 3) for i, n in enumerate(names)}, 'worker cycles total', int(tot), 'boards', c['eval_requests'] // 148)

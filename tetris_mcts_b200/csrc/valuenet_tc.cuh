@@ -6,14 +6,15 @@
 // a2*b2 is < 2^-22 relative).  Operands are pre-scaled by exact powers of two (activations x16, weights x64) so that the
 // low terms stay in fp16's normal range; the epilogues undo the 2^10.  Three fp16 MMAs replace one fp32 product.
 //
-//   k_tc_conv  one persistent CTA per SM, two boards in flight (ping-pong):
-//              decode obs key -> conv1 on CUDA cores (K = 9 is too small for an MMA) -> split -> smem
+//   k_tc_conv  one persistent CTA per SM, four boards in flight (software pipeline):
+//              obs key -> im2col (exact fp16) -> conv1 as one K=16 MMA per M tile -> epilogue (bias, ReLU, split) -> smem
 //              conv2 / conv3 as shift-GEMMs: activations live in shared memory channel-chunk-major
-//              ([8-channel chunk][pixel row][16 B]), so the A operand of filter tap (dy,dx) is the SAME array
-//              started (dy*W+dx) rows later — a canonical no-swizzle K-major UMMA layout with SBO = 128 B,
-//              LBO = rows*16 B.  tcgen05.mma (M=128 pixels, N=32 couts, K=16) issued by one thread, accumulators
-//              in TMEM, completion through tcgen05.commit -> mbarrier; epilogues read TMEM with tcgen05.ld, apply
-//              bias+ReLU, re-split (fp16 x2) and write the next layer's operand (or act3 to HBM in the FC kernel's tile layout).
+//              ([8-channel chunk][pixel row][16 B]) on an 8-wide pixel grid, so the A operand of filter row dy is the SAME
+//              array started dy*8 rows later — a canonical no-swizzle K-major UMMA layout with SBO = 128 B,
+//              LBO = rows*16 B; the three horizontal taps are stacked along N (N = 96) and summed by the epilogue with
+//              two lane shuffles.  tcgen05.mma (M=128 pixels, K=16) issued by one thread, accumulators in TMEM,
+//              completion through tcgen05.commit -> mbarrier; epilogues read TMEM with tcgen05.ld, apply bias+ReLU,
+//              re-split (fp16 x2) and write the next layer's operand (or act3 to HBM in the FC kernel's tile layout).
 //   k_tc_fc    [R,1792] x [1792,256]: 128-row tiles, operands streamed by cp.async.bulk (1-D TMA) into a 5-stage
 //              mbarrier ring — both operands are stored in HBM already in the canonical UMMA layout, so one bulk copy
 //              per operand block needs no tensor map; warp-specialised (producer / MMA issuer / 4 epilogue warps);
@@ -126,40 +127,54 @@ __device__ __forceinline__ void tmem_ld16_sum2(uint32_t taddr, float (&v)[16]) {
 
 // x = x1 + x2 with fp16 terms (round-to-nearest each step); eight fp32 values -> two 16-byte chunks (one per split)
 __device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2) {
-    uint32_t a[8], b[8];
+    uint32_t a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        __half h1 = __float2half_rn(x[i]);
-        __half h2 = __float2half_rn(x[i] - __half2float(h1));
-        a[i] = __half_as_ushort(h1); b[i] = __half_as_ushort(h2);
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);                 // one packed conversion per pair
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+        a[i] = *reinterpret_cast<const uint32_t *>(&h); b[i] = *reinterpret_cast<const uint32_t *>(&l);
     }
-    c1 = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
-    c2 = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
+    c1 = make_uint4(a[0], a[1], a[2], a[3]);
+    c2 = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------- conv kernel
-constexpr int TCC_WORKERS = 512;            // warps 0-15: decode, conv1, epilogues
+// Measured on B200 (scripts/probe/mma_probe.cu): a tcgen05.mma costs max(44.7, ~N/2) clk however small it is, so the
+// layers are cut into FEW, WIDE instructions.  The three horizontal taps (dx) of a 3x3 filter are stacked along N:
+//   D'[p][dx*32 + cout] = sum_{dy, cin} act[p + dy*8][cin] * W[dy][dx][cin][cout]          (A operand shifted by dy*8 rows only)
+//   out[p][cout]        = D'[p][0*32+cout] + D'[p+1][1*32+cout] + D'[p+2][2*32+cout]        (epilogue: two lane shuffles)
+// All three layers live on an 8-wide pixel grid (p = y*8 + x), so p+dx never leaves the 32-lane warp that owns the row.
+// 18 MMAs (3 dy x 2 channel halves x 3 split products, N = 96) replace the 36 narrow ones of the tap-by-tap form, and
+// conv1 (K = 9 taps, exact {-1,0,1} inputs) runs on the tensor core too from an im2col operand the workers build.
+constexpr int TCC_WORKERS = 512;            // warps 0-15: decode / im2col and the three epilogues
 constexpr int TCC_ISSUER = TCC_WORKERS / 32; // warp 16: MMA issuer (one elected lane)
-constexpr int TCC_THREADS = TCC_WORKERS + 32;
-constexpr int TCC_R1 = 152;                 // act1 rows per board: 18x8 grid = 144 (+8: tap shifts read up to row 145)
-constexpr int TCC_R2 = 144;                 // act2 rows per board: 16x6 grid = 96 (+48: M=128 tile + shifts read up to row 141)
-constexpr int TCC_WBLOCK = 2 * 64 * 16;      // one (tap, half) block: [chunk 2][n = split*32 + cout][16 B]
-constexpr int TCC_WBYTES = 18 * TCC_WBLOCK;  // one conv layer = 36864 B
-constexpr int TCC_SLOTS = 3;                // boards in flight
-constexpr int TCC_ASLOT = 2 * 4 * TCC_R1 * 16;   // operand buffer of one slot: act1 [split][chunk 4][152 rows][16 B], later overwritten
-                                                 // in place by act2 [split][chunk 4][144 rows][16 B] (conv2 has finished reading by then)
+constexpr int TCC_LOADER = TCC_ISSUER + 1; // warp 17: fetches the observation keys of the CTA's boards into a shared-memory ring
+constexpr int TCC_THREADS = TCC_WORKERS + 64;
+constexpr int TCC_R = 144;                  // activation rows per board: 18x8 grid (act1) / 16x8 grid + the dy shifts (act2)
+constexpr int TCC_WBLOCK = 2 * 2 * 96 * 16;  // one (dy, channel half) block: [weight split 2][chunk 2][n = dx*32 + cout][16 B]
+constexpr int TCC_WBYTES = 6 * TCC_WBLOCK;   // one conv layer = 36864 B
+constexpr int TCC_W1BYTES = 2 * 64 * 16;     // conv1: [chunk 2][n = split*32 + cout][16 B], k = tap (9 of 16 used)
+constexpr int TCC_SLOTS = 4;                // boards in flight
+constexpr int TCC_ASLOT = 2 * 4 * TCC_R * 16;    // operand buffer of one slot: act1 [split][chunk 4][144 rows][16 B], overwritten in
+                                                 // place by act2 (conv2 has finished reading by then)
+constexpr int TCC_IMROWS = 256;             // im2col rows per board: 144 used, two M=128 tiles
+constexpr int TCC_IMSLOT = 2 * TCC_IMROWS * 16;  // [chunk 2][256 rows][16 B] fp16
 constexpr int TCC_OFF_W2 = 0;
 constexpr int TCC_OFF_W3 = TCC_OFF_W2 + TCC_WBYTES;
-constexpr int TCC_OFF_A1 = TCC_OFF_W3 + TCC_WBYTES;
-constexpr int TCC_OFF_IN = TCC_OFF_A1 + TCC_SLOTS * TCC_ASLOT;   // 2 x 200 floats
-constexpr int TCC_OFF_W1 = TCC_OFF_IN + 2 * 200 * 4;       // 288 floats + 96 floats of biases
-constexpr int TCC_OFF_KEY = TCC_OFF_W1 + (288 + 96) * 4;   // 2 x 12 key words of the current pair
-constexpr int TCC_OFF_BAR = TCC_OFF_KEY + 2 * 12 * 4;      // 4 x TCC_SLOTS mbarriers + tmem pointer
-constexpr int TCC_SMEM = TCC_OFF_BAR + 4 * TCC_SLOTS * 8 + 16;
-constexpr int TCC_TMEM_COLS = 512;          // 3 slots x 2 layers x 64 columns (two partial sums of 32 couts) = 384 -> 512
+constexpr int TCC_OFF_W1 = TCC_OFF_W3 + TCC_WBYTES;
+constexpr int TCC_OFF_A1 = TCC_OFF_W1 + TCC_W1BYTES;
+constexpr int TCC_OFF_IM = TCC_OFF_A1 + TCC_SLOTS * TCC_ASLOT;
+constexpr int TCC_OFF_BIAS = TCC_OFF_IM + TCC_SLOTS * TCC_IMSLOT;   // 96 floats
+constexpr int TCC_OFF_KEY = TCC_OFF_BIAS + 96 * 4;                  // TCC_SLOTS x 16 key words (ring)
+constexpr int TCC_OFF_BAR = TCC_OFF_KEY + TCC_SLOTS * 16 * 4;       // 7 x TCC_SLOTS mbarriers + tmem pointer
+constexpr int TCC_SMEM = TCC_OFF_BAR + 7 * TCC_SLOTS * 8 + 16;
+constexpr int TCC_TMEM_COLS = 512;          // 4 slots x 128 columns; a slot's three accumulators reuse the same columns in turn
 constexpr int ACT3_KCHUNKS = 224;           // 1792 / 8
+static_assert(TCC_SMEM <= 227 * 1024, "k_tc_conv shared memory");
 
 struct TcWeights {
+    const uint8_t *wc1;         // TCC_W1BYTES
     const uint8_t *wc2, *wc3;   // TCC_WBYTES each, already in the shared-memory layout
     const uint8_t *wfc;         // [split 3][k16 block 112][chunk 2][n 256][16 B]
 };
@@ -169,27 +184,62 @@ __device__ __forceinline__ size_t act3_off(int split, int n_tiles, int ridx, int
     return ((((size_t)split * n_tiles + (ridx >> 7)) * ACT3_KCHUNKS + kchunk) * 128 + (ridx & 127)) * 16;
 }
 
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-
-// One 3x3 convolution layer as 36 tcgen05.mma (9 taps x 2 halves of the 32 input channels x 2 activation splits).
-// The operand fetch of an SS-mode MMA is shared-memory bound (~64 B/clk measured), so the two weight splits are stacked
-// along N: activation split 1 meets [W1;W2] (N=64), split 2 meets W1 (N=32).  The three products land in two 32-column
-// accumulator blocks (a*W1 | a*W2) that the epilogue adds.
-//   R = rows per operand chunk, WGRID = width of the pixel grid the operand is stored on (tap shift = dy*WGRID + dx)
-template <int R, int WGRID>
-__device__ __forceinline__ void issue_conv_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
-    const uint64_t a0 = umma_desc(a_addr, R * 16, 128), b0 = umma_desc(w_addr, 64 * 16, 128);
+// three 8-column accumulator slices (32 columns apart) of this thread's TMEM lane, one wait
+__device__ __forceinline__ void tmem_ld8x3(uint32_t taddr, float (&a)[8], float (&b)[8], float (&c)[8]) {
+    uint32_t r[24];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+        : "r"(taddr), "r"(taddr + 32), "r"(taddr + 64)
+        : "memory");
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); c[i] = __uint_as_float(r[16 + i]); }
+}
+
+// two 8-column accumulator slices (32 columns apart), one wait
+__device__ __forceinline__ void tmem_ld8x2(uint32_t taddr, float (&a)[8], float (&b)[8]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr), "r"(taddr + 32)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); }
+}
+
+// out[p] = D'[p][dx=0] + D'[p+1][dx=1] + D'[p+2][dx=2] for the 8 couts of this warp's chunk (see the header of this section)
+__device__ __forceinline__ void tmem_ld_conv_sum(uint32_t taddr, float (&v)[8]) {
+    float d0[8], d1[8], d2[8];
+    tmem_ld8x3(taddr, d0, d1, d2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float s1 = __shfl_down_sync(0xffffffffu, d1[e], 1), s2 = __shfl_down_sync(0xffffffffu, d2[e], 2);
+        v[e] = ((s2 + s1) + d0[e]) * TC_UNSCALE;
+    }
+}
+
+// One 3x3 layer = 18 tcgen05.mma of N = 96: for each (dy, channel half): a1*W1, a1*W2, a2*W1 into the same 96 columns.
+__device__ __forceinline__ void issue_conv_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
+    const uint64_t a0 = umma_desc(a_addr, TCC_R * 16, 128), b0 = umma_desc(w_addr, 96 * 16, 128);
+    constexpr uint32_t idesc = umma_idesc_f16(128, 96);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int sa = 0; sa < 2; ++sa) {
-                const uint32_t a_off = sa * 4 * R + 2 * h * R + (tap / 3) * WGRID + (tap % 3);   // 16-byte units
-                const uint32_t b_off = (tap * 2 + h) * (TCC_WBLOCK / 16);
-                // the first MMA (sa = 0, N = 64) initialises both accumulator blocks; everything after accumulates
-                umma_f16(tmem_d, a0 + a_off, b0 + b_off, umma_idesc_f16(128, 64 - 32 * sa), (tap | h | sa) ? 1u : 0u);
-            }
+            const uint32_t a_hi = 2 * h * TCC_R + dy * 8, a_lo = a_hi + 4 * TCC_R;          // 16-byte units
+            const uint32_t b_hi = (dy * 2 + h) * (TCC_WBLOCK / 16), b_lo = b_hi + 2 * 96;
+            umma_f16(tmem_d, a0 + a_hi, b0 + b_hi, idesc, (dy | h) ? 1u : 0u);
+            umma_f16(tmem_d, a0 + a_hi, b0 + b_lo, idesc, 1u);
+            umma_f16(tmem_d, a0 + a_lo, b0 + b_hi, idesc, 1u);
         }
     }
 }
@@ -199,26 +249,27 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
           unsigned long long *prof) {
 #define PROF_T(i) do { if (prof && do_prof) { long long _n = clock64(); pacc[i] += _n - ptick; ptick = _n; } } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
-    float *sIn = reinterpret_cast<float *>(smem + TCC_OFF_IN);
-    float *sW1 = reinterpret_cast<float *>(smem + TCC_OFF_W1);
-    float *sB = sW1 + 288;
-    uint32_t *sKey = reinterpret_cast<uint32_t *>(smem + TCC_OFF_KEY);
+    float *sB = reinterpret_cast<float *>(smem + TCC_OFF_BIAS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TCC_OFF_BAR);
-    uint64_t *bar_c2 = bars, *bar_c3 = bars + TCC_SLOTS;                       // tensor core -> workers: conv2 / conv3 of slot done
-    uint64_t *bar_a1 = bars + 2 * TCC_SLOTS, *bar_a2 = bars + 3 * TCC_SLOTS;   // workers -> issuer: act1 / act2 of slot written
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + TCC_OFF_BAR + 4 * TCC_SLOTS * 8);
+    constexpr int NS = TCC_SLOTS;
+    uint64_t *bar_c1 = bars, *bar_c2 = bars + NS, *bar_c3 = bars + 2 * NS;             // tensor core -> workers: layer of slot done
+    uint64_t *bar_a0 = bars + 3 * NS, *bar_a1 = bars + 4 * NS, *bar_a2 = bars + 5 * NS; // workers -> issuer: operand of slot written
+    uint64_t *bar_k = bars + 6 * NS;                                                    // loader -> workers: key of slot landed
+    uint32_t *sKey = reinterpret_cast<uint32_t *>(smem + TCC_OFF_KEY);
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + TCC_OFF_BAR + 7 * NS * 8);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    // ---- one-time setup: weights into smem, zeroed activations, barriers, TMEM
+    // ---- one-time setup: weights into smem, zeroed operands, barriers, TMEM
     for (int i = t; i < TCC_WBYTES / 16; i += TCC_THREADS) {
         reinterpret_cast<uint4 *>(smem + TCC_OFF_W2)[i] = reinterpret_cast<const uint4 *>(TW.wc2)[i];
         reinterpret_cast<uint4 *>(smem + TCC_OFF_W3)[i] = reinterpret_cast<const uint4 *>(TW.wc3)[i];
     }
-    for (int i = t; i < TCC_SLOTS * TCC_ASLOT / 16; i += TCC_THREADS) reinterpret_cast<uint4 *>(smem + TCC_OFF_A1)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = t; i < 288; i += TCC_THREADS) sW1[i] = W.w1[i];
+    for (int i = t; i < TCC_W1BYTES / 16; i += TCC_THREADS) reinterpret_cast<uint4 *>(smem + TCC_OFF_W1)[i] = reinterpret_cast<const uint4 *>(TW.wc1)[i];
+    for (int i = t; i < (NS * TCC_ASLOT + NS * TCC_IMSLOT) / 16; i += TCC_THREADS) reinterpret_cast<uint4 *>(smem + TCC_OFF_A1)[i] = make_uint4(0, 0, 0, 0);
     if (t < 32) { sB[t] = W.b1[t]; sB[32 + t] = W.b2[t]; sB[64 + t] = W.b3[t]; }
     if (t == 0) {
-        for (int i = 0; i < 2 * TCC_SLOTS; ++i) mbar_init(&bars[i], 1);
-        for (int i = 2 * TCC_SLOTS; i < 4 * TCC_SLOTS; ++i) mbar_init(&bars[i], TCC_WORKERS);
+        for (int i = 0; i < 3 * NS; ++i) mbar_init(&bars[i], 1);
+        for (int i = 3 * NS; i < 6 * NS; ++i) mbar_init(&bars[i], TCC_WORKERS);
+        for (int i = 6 * NS; i < 7 * NS; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
     if (warp == TCC_ISSUER) tmem_alloc<TCC_TMEM_COLS>(tmem_ptr);
@@ -229,137 +280,171 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     const uint32_t tmem_base = *tmem_ptr;
     const int n_req = *n_req_ptr;
     // Boards are handed out in runs of 8 consecutive requests (neighbouring act3 rows get written close in time); board i of
-    // this CTA's sequence lives in slot i % 3.  Three boards are in flight at different stages (software pipeline):
-    //   workers, iteration i :  S1(i) decode + conv1 | S2(i-1) conv2 epilogue | S3(i-2) conv3 epilogue
-    //   issuer               :  conv2(i) then conv3(i-1)
-    // Every MMA batch is issued about one full iteration before its result is consumed, so the tensor pipe works on one
-    // board while the CUDA cores prepare / drain two others.
+    // this CTA's sequence lives in slot i % 4.  Four boards are in flight at different stages (software pipeline):
+    //   workers, iteration i :  S0(i) im2col | E1(i-1) conv1 epilogue | E2(i-2) conv2 epilogue | E3(i-3) conv3 epilogue
+    //   issuer,  iteration i :  conv1(i) | conv2(i-1) | conv3(i-2), each as soon as the workers have written its operand
+    // Every MMA batch is consumed one worker iteration after it was issued, so the tensor pipe works on three boards while
+    // the CUDA cores prepare / drain the others.
     const int n_runs = (n_req + 7) >> 3;
     int n_local = 0;
     for (int run = blockIdx.x; run < n_runs; run += gridDim.x) n_local += min(8, n_req - run * 8);
     auto board_of = [&](int i) -> int { return ((i >> 3) * (int)gridDim.x + (int)blockIdx.x) * 8 + (i & 7); };
-    constexpr int NS = TCC_SLOTS;
     if (warp == TCC_ISSUER) {
         // ===================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t s_w2 = smem_u32(smem + TCC_OFF_W2), s_w3 = smem_u32(smem + TCC_OFF_W3);
-            const uint32_t s_act = smem_u32(smem + TCC_OFF_A1);
+            const uint32_t s_w1 = smem_u32(smem + TCC_OFF_W1), s_w2 = smem_u32(smem + TCC_OFF_W2), s_w3 = smem_u32(smem + TCC_OFF_W3);
+            const uint32_t s_act = smem_u32(smem + TCC_OFF_A1), s_im = smem_u32(smem + TCC_OFF_IM);
             const bool do_prof = blockIdx.x == 0;
-            long long pacc[12] = {0}, ptick = clock64();
-            for (int i = 0; i <= n_local; ++i) {
-                if (i < n_local) {                               // conv2 (model_vv.py:34): act1 on the 18x8 grid
+            long long pacc[16] = {0}, ptick = clock64();
+            for (int i = 0; i < n_local + 2; ++i) {
+                if (i < n_local) {                               // conv1 (model_vv.py:32): im2col [256 x 16] x W1 [16 x 64], two M tiles
                     const int slot = i % NS;
-                    mbar_wait(&bar_a1[slot], (uint32_t)(i / NS) & 1u);
-                    PROF_T(6);
-                    tc_fence_after();
-                    issue_conv_layer<TCC_R1, 8>(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
-                    umma_commit(&bar_c2[slot]);
-                    PROF_T(7);
-                }
-                if (i >= 1) {                                    // conv3 (model_vv.py:36): act2 on the compact 16x6 grid
-                    const int j = i - 1, slot = j % NS;
-                    mbar_wait(&bar_a2[slot], (uint32_t)(j / NS) & 1u);
+                    mbar_wait(&bar_a0[slot], (uint32_t)(i / NS) & 1u);
                     PROF_T(8);
                     tc_fence_after();
-                    issue_conv_layer<TCC_R2, 6>(tmem_base + slot * 128 + 64, s_act + slot * TCC_ASLOT, s_w3);
-                    umma_commit(&bar_c3[slot]);
+                    const uint64_t a0 = umma_desc(s_im + slot * TCC_IMSLOT, TCC_IMROWS * 16, 128), b0 = umma_desc(s_w1, 64 * 16, 128);
+                    umma_f16(tmem_base + slot * 128, a0, b0, umma_idesc_f16(128, 64), 0u);
+                    umma_f16(tmem_base + slot * 128 + 64, a0 + 128, b0, umma_idesc_f16(128, 64), 0u);
+                    umma_commit(&bar_c1[slot]);
                     PROF_T(9);
                 }
+                if (i >= 1 && i - 1 < n_local) {                 // conv2 (model_vv.py:34): act1 on the 18x8 grid
+                    const int j = i - 1, slot = j % NS;
+                    mbar_wait(&bar_a1[slot], (uint32_t)(j / NS) & 1u);
+                    PROF_T(10);
+                    tc_fence_after();
+                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
+                    umma_commit(&bar_c2[slot]);
+                    PROF_T(11);
+                }
+                if (i >= 2) {                                    // conv3 (model_vv.py:36): act2 on the 16x8 grid
+                    const int j = i - 2, slot = j % NS;
+                    mbar_wait(&bar_a2[slot], (uint32_t)(j / NS) & 1u);
+                    PROF_T(12);
+                    tc_fence_after();
+                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w3);
+                    umma_commit(&bar_c3[slot]);
+                    PROF_T(13);
+                }
             }
-            if (prof && do_prof) for (int i = 6; i < 10; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+            if (prof && do_prof) for (int i = 8; i < 14; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+        }
+    } else if (warp == TCC_LOADER) {
+        // ===================================================== key loader: global loads stay out of the workers' way (their
+        // proxy fences would otherwise wait for every outstanding load)
+        uint2 rqs = make_uint2(0, 0);
+        for (int i = 0; i < n_local; ++i) {
+            const int slot = i % NS;
+            if ((i & 31) == 0 && i + lane < n_local) rqs = req[board_of(i + lane)];
+            const uint32_t gx = __shfl_sync(0xffffffffu, rqs.x, i & 31), gy = __shfl_sync(0xffffffffu, rqs.y, i & 31);
+            uint32_t kw = 0;
+            if (lane < 12) kw = keys[((size_t)gx * M + (gy & 0x0fffffffu)) * KEY_WORDS + lane];
+            if (i >= NS) mbar_wait(&bar_c1[slot], (uint32_t)((i - NS) / NS) & 1u);     // conv1 of the slot's previous board done => its key was consumed
+            if (lane < 12) sKey[slot * 16 + lane] = kw;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_k[slot]);
         }
     } else {
         // ===================================================== workers (512 threads)
         const bool do_prof = blockIdx.x == 0 && t == 0;
-        long long pacc[12] = {0}, ptick = clock64();
-        auto fetch_key = [&](int i) -> uint32_t {               // key word t of this CTA's i-th board (threads 0..11)
-            if (t < 12 && i < n_local) {
-                uint2 rq = req[board_of(i)];
-                return keys[((size_t)rq.x * M + (rq.y & 0x0fffffffu)) * KEY_WORDS + t];
-            }
-            return 0u;
-        };
-        uint32_t kpre = fetch_key(0);
-        const int q = warp & 3, cq = warp >> 2, m = q * 32 + lane;
-        for (int i = 0; i < n_local + 2; ++i) {
-            // ---- S1(i): decode + conv1 -> act1 of the slot
+        long long pacc[16] = {0}, ptick = clock64();
+        const int q = warp & 3, cq = warp >> 2, m = q * 32 + lane;       // TMEM lane quadrant, 8-cout chunk, pixel row
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 8;
+        for (int i = 0; i < n_local + 3; ++i) {
+            // ---- S0(i): observation key -> im2col operand of conv1 (fp16, exact): row p = y*8 + x, k = tap = dy*3 + dx.
             if (i < n_local) {
                 const int slot = i % NS;
-                if (t < 12) sKey[t] = kpre;
-                worker_barrier();
-                kpre = fetch_key(i + 1);                         // latency hidden behind this iteration's work
-                if (t < 200) {                                   // {-1,0,1} (model_vv.py:212)
-                    const int r = t / 10, c = t - r * 10;
-                    float v = (float)((sKey[r >> 1] >> ((r & 1) * 16 + c)) & 1u);
-                    uint32_t pc = sKey[10], ci = (uint32_t)t;
-                    if ((pc & 0xffu) == ci || ((pc >> 8) & 0xffu) == ci || ((pc >> 16) & 0xffu) == ci || (pc >> 24) == ci) v = -1.f;
-                    sIn[t] = v;
-                }
-                worker_barrier();
-                PROF_T(0);
-                // conv1 (model_vv.py:32) on CUDA cores: task = (8-cout chunk, pixel of the 18x8 grid); consecutive lanes take
-                // consecutive pixels, so the 16-byte operand stores of a warp are contiguous (no bank conflicts)
-                for (int task = t; task < 576; task += TCC_WORKERS) {
-                    const int c4 = task / 144, pix = task - c4 * 144, y = pix >> 3, x = pix & 7;
-                    float acc[8];
+                const int dy = t / 144, p = t - dy * 144, y = p >> 3, x = p & 7, r = y + dy;     // t < 432: one filter row of one pixel
+                mbar_wait(&bar_k[slot], (uint32_t)(i / NS) & 1u);
+                const uint32_t rowword = sKey[slot * 16 + ((r >> 1) & 15)], pcs = sKey[slot * 16 + 10];
+                if (t < 432) {
+                    const uint32_t settled = (rowword >> ((r & 1) * 16)) >> x;
+                    uint32_t piece = 0;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] = sB[c4 * 8 + e];
+                    for (int k = 0; k < 4; ++k) {                // the falling piece's cells (sorted bytes of key word 10)
+                        const uint32_t cell = (pcs >> (8 * k)) & 0xffu, pr = (cell * 205u) >> 11, pcol = cell - pr * 10u;
+                        piece |= (pr == (uint32_t)r ? 1u : 0u) << pcol;
+                    }
+                    piece >>= x;
+                    uint8_t *row0 = smem + TCC_OFF_IM + slot * TCC_IMSLOT + p * 16;
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            float in = sIn[(y + dy) * 10 + x + dx];
-                            const float4 *w = reinterpret_cast<const float4 *>(sW1 + (dy * 3 + dx) * 32 + c4 * 8);
-                            float4 wa = w[0], wb = w[1];
-                            acc[0] = fmaf(in, wa.x, acc[0]); acc[1] = fmaf(in, wa.y, acc[1]); acc[2] = fmaf(in, wa.z, acc[2]); acc[3] = fmaf(in, wa.w, acc[3]);
-                            acc[4] = fmaf(in, wb.x, acc[4]); acc[5] = fmaf(in, wb.y, acc[5]); acc[6] = fmaf(in, wb.z, acc[6]); acc[7] = fmaf(in, wb.w, acc[7]);
-                        }
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f) * TC_SCALE_A;
-                    uint4 c1, c2;
-                    split8(acc, c1, c2);
-                    uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (c4 * TCC_R1 + pix) * 16;
-                    *reinterpret_cast<uint4 *>(base) = c1;
-                    *reinterpret_cast<uint4 *>(base + 4 * TCC_R1 * 16) = c2;
+                    for (int dx = 0; dx < 3; ++dx) {             // 1 settled, -1 falling piece, 0 empty (model_vv.py:212)
+                        const uint32_t hv = ((settled >> dx) & 1u) * 0x3C00u | ((piece >> dx) & 1u) * 0xBC00u;
+                        const int tap = dy * 3 + dx;
+                        *reinterpret_cast<uint16_t *>(row0 + (tap >> 3) * (TCC_IMROWS * 16) + (tap & 7) * 2) = (uint16_t)hv;
+                    }
                 }
                 fence_async_smem();
-                mbar_arrive(&bar_a1[slot]);
-                PROF_T(1);
+                mbar_arrive(&bar_a0[slot]);
+                PROF_T(0);
             }
-            // ---- S2(i-1): conv2 epilogue: bias + ReLU + split -> act2 (16x6 compact grid), in place of the slot's act1
+            // ---- E1(i-1): conv1 epilogue: bias + ReLU + split -> act1 (18x8 grid)
             if (i >= 1 && i - 1 < n_local) {
                 const int j = i - 1, slot = j % NS;
-                mbar_wait(&bar_c2[slot], (uint32_t)(j / NS) & 1u);
+                mbar_wait(&bar_c1[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(1);
+                tc_fence_after();
+                uint8_t *abase = smem + TCC_OFF_A1 + slot * TCC_ASLOT + cq * TCC_R * 16;
+                {
+                    float w1[8], w2[8], o[8];
+                    tmem_ld8x2(t_lane + slot * 128, w1, w2);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + sB[cq * 8 + e], 0.f) * TC_SCALE_A;
+                    uint4 c1, c2;
+                    split8(o, c1, c2);
+                    *reinterpret_cast<uint4 *>(abase + m * 16) = c1;
+                    *reinterpret_cast<uint4 *>(abase + 4 * TCC_R * 16 + m * 16) = c2;
+                }
+                if (q == 0) {                                    // rows 128..143 sit in lanes 0..15 of the second M tile
+                    float w1[8], w2[8], o[8];
+                    tmem_ld8x2(t_lane + slot * 128 + 64, w1, w2);
+                    if (lane < 16) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + sB[cq * 8 + e], 0.f) * TC_SCALE_A;
+                        uint4 c1, c2;
+                        split8(o, c1, c2);
+                        *reinterpret_cast<uint4 *>(abase + (128 + lane) * 16) = c1;
+                        *reinterpret_cast<uint4 *>(abase + 4 * TCC_R * 16 + (128 + lane) * 16) = c2;
+                    }
+                }
+                tc_fence_before();
+                fence_async_smem();
+                mbar_arrive(&bar_a1[slot]);
                 PROF_T(2);
+            }
+            // ---- E2(i-2): conv2 epilogue: dx sum + bias + ReLU + split -> act2 (16x8 grid), in place of the slot's act1
+            if (i >= 2 && i - 2 < n_local) {
+                const int j = i - 2, slot = j % NS;
+                mbar_wait(&bar_c2[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(3);
                 tc_fence_after();
                 float v[8];
-                tmem_ld8_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + cq * 8, v);
-                const int y = m >> 3, x = m & 7;
-                if (x < 6) {
+                tmem_ld_conv_sum(t_lane + slot * 128, v);
+                if ((m & 7) < 6) {
                     float o[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[32 + cq * 8 + e], 0.f) * TC_SCALE_A;
                     uint4 c1, c2;
                     split8(o, c1, c2);
-                    uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (cq * TCC_R2 + y * 6 + x) * 16;
+                    uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (cq * TCC_R + m) * 16;
                     *reinterpret_cast<uint4 *>(base) = c1;
-                    *reinterpret_cast<uint4 *>(base + 4 * TCC_R2 * 16) = c2;
+                    *reinterpret_cast<uint4 *>(base + 4 * TCC_R * 16) = c2;
                 }
                 tc_fence_before();
                 fence_async_smem();
                 mbar_arrive(&bar_a2[slot]);
-                PROF_T(3);
-            }
-            // ---- S3(i-2): conv3 epilogue: bias + ReLU + split -> act3 in HBM (FC tile layout)
-            if (i >= 2 && i - 2 < n_local) {
-                const int j = i - 2, slot = j % NS, ridx = board_of(j);
-                mbar_wait(&bar_c3[slot], (uint32_t)(j / NS) & 1u);
                 PROF_T(4);
+            }
+            // ---- E3(i-3): conv3 epilogue: dx sum + bias + ReLU + split -> act3 in HBM (FC tile layout)
+            if (i >= 3) {
+                const int j = i - 3, slot = j % NS, ridx = board_of(j);
+                mbar_wait(&bar_c3[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(5);
                 tc_fence_after();
-                const int y = m / 6, x = m - y * 6;
+                const int y = m >> 3, x = m & 7;
                 float v[8];
-                tmem_ld8_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128 + 64 + cq * 8, v);
-                if (m < 84 && x < 4) {
+                tmem_ld_conv_sum(t_lane + slot * 128, v);
+                if (y < 14 && x < 4) {
                     float o[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[64 + cq * 8 + e], 0.f) * TC_SCALE_A;
@@ -370,10 +455,10 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = c2;
                 }
                 tc_fence_before();
-                PROF_T(5);
+                PROF_T(6);
             }
         }
-        if (prof && do_prof) for (int i = 0; i < 6; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+        if (prof && do_prof) for (int i = 0; i < 7; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
     }
 #undef PROF_T
     tc_fence_before();
@@ -500,7 +585,7 @@ k_tc_fc(NetWeights W, TcWeights TW, const uint8_t *act3, int n_tiles_alloc, cons
 
 // ---------------------------------------------------------------------------------------------------- host side
 struct TcState {
-    uint8_t *d_w = nullptr;      // wc2 | wc3 | wfc
+    uint8_t *d_w = nullptr;      // wc1 | wc2 | wc3 | wfc
     TcWeights TW{};
     uint8_t *d_act3 = nullptr; size_t tiles = 0;
 };
@@ -516,24 +601,35 @@ static inline float host_half_f(uint16_t h) { __half x; memcpy(&x, &h, 2); retur
 static int tc_prepare(void **state, const float *w, cudaStream_t stream) {
     TcState *st = (TcState *)*state;
     if (!st) { st = new TcState(); *state = st; }
-    const float *c2w = w + 288 + 32, *c3w = c2w + 9216 + 32, *f1w = c3w + 9216 + 32;
+    const float *c1w = w, *c2w = w + 288 + 32, *c3w = c2w + 9216 + 32, *f1w = c3w + 9216 + 32;
     const size_t fc_bytes = (size_t)2 * TCF_KBLOCKS * TCF_B_BYTES;
-    std::vector<uint8_t> h(2 * (size_t)TCC_WBYTES + fc_bytes);
-    uint16_t *p2 = reinterpret_cast<uint16_t *>(h.data()), *p3 = reinterpret_cast<uint16_t *>(h.data() + TCC_WBYTES);
-    uint16_t *pf = reinterpret_cast<uint16_t *>(h.data() + 2 * (size_t)TCC_WBYTES);
-    for (int layer = 0; layer < 2; ++layer) {
+    std::vector<uint8_t> h(TCC_W1BYTES + 2 * (size_t)TCC_WBYTES + fc_bytes);
+    uint16_t *p1 = reinterpret_cast<uint16_t *>(h.data());
+    uint16_t *p2 = reinterpret_cast<uint16_t *>(h.data() + TCC_W1BYTES), *p3 = reinterpret_cast<uint16_t *>(h.data() + TCC_W1BYTES + TCC_WBYTES);
+    uint16_t *pf = reinterpret_cast<uint16_t *>(h.data() + TCC_W1BYTES + 2 * (size_t)TCC_WBYTES);
+    for (int c2 = 0; c2 < 2; ++c2)                               // conv1: [chunk][n = split*32 + cout][8], k = tap
+        for (int n = 0; n < 32; ++n)
+            for (int e = 0; e < 8; ++e) {
+                const int tap = 8 * c2 + e;
+                uint16_t s2[2] = {0, 0};
+                if (tap < 9) host_split2(c1w[n * 9 + tap] * TC_SCALE_W, s2);
+                for (int s = 0; s < 2; ++s) p1[((size_t)c2 * 64 + s * 32 + n) * 8 + e] = s2[s];
+            }
+    for (int layer = 0; layer < 2; ++layer) {                    // conv2/3: [(dy, half)][split][chunk][n = dx*32 + cout][8]
         const float *cw = layer ? c3w : c2w;
         uint16_t *dst = layer ? p3 : p2;
-        for (int tap = 0; tap < 9; ++tap)
+        for (int dy = 0; dy < 3; ++dy)
             for (int hh = 0; hh < 2; ++hh)
                 for (int c2 = 0; c2 < 2; ++c2)
-                    for (int n = 0; n < 32; ++n)
-                        for (int e = 0; e < 8; ++e) {
-                            int ci = 16 * hh + 8 * c2 + e;
-                            uint16_t s2[2];
-                            host_split2(cw[(n * 32 + ci) * 9 + tap] * TC_SCALE_W, s2);
-                            for (int s = 0; s < 2; ++s) dst[((((size_t)(tap * 2 + hh)) * 2 + c2) * 64 + s * 32 + n) * 8 + e] = s2[s];
-                        }
+                    for (int dx = 0; dx < 3; ++dx)
+                        for (int n = 0; n < 32; ++n)
+                            for (int e = 0; e < 8; ++e) {
+                                int ci = 16 * hh + 8 * c2 + e;
+                                uint16_t s2[2];
+                                host_split2(cw[(n * 32 + ci) * 9 + dy * 3 + dx] * TC_SCALE_W, s2);
+                                for (int s = 0; s < 2; ++s)
+                                    dst[(((((size_t)(dy * 2 + hh)) * 2 + s) * 2 + c2) * 96 + dx * 32 + n) * 8 + e] = s2[s];
+                            }
     }
     for (int j = 0; j < TCF_KBLOCKS; ++j)
         for (int c2 = 0; c2 < 2; ++c2)
@@ -547,7 +643,7 @@ static int tc_prepare(void **state, const float *w, cudaStream_t stream) {
     if (!st->d_w && cudaMalloc(&st->d_w, h.size()) != cudaSuccess) return 1;
     if (cudaMemcpyAsync(st->d_w, h.data(), h.size(), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
     if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
-    st->TW.wc2 = st->d_w; st->TW.wc3 = st->d_w + TCC_WBYTES; st->TW.wfc = st->d_w + 2 * (size_t)TCC_WBYTES;
+    st->TW.wc1 = st->d_w; st->TW.wc2 = st->d_w + TCC_W1BYTES; st->TW.wc3 = st->TW.wc2 + TCC_WBYTES; st->TW.wfc = st->TW.wc3 + TCC_WBYTES;
     if (cudaFuncSetAttribute(k_tc_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, TCC_SMEM) != cudaSuccess) return 1;
     if (cudaFuncSetAttribute(k_tc_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM) != cudaSuccess) return 1;
     return 0;
