@@ -147,10 +147,16 @@ __global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, un
 
 // After an expansion is complete: which unique children need the network (ValueSimLP.py:55-60 evaluates every unique
 // child; core.h:344 only uses results where visit == 0, so only those boards are queued).
-__device__ __forceinline__ void request_lp_evals(const Arena &A, const Grp &gp, int g, int c, int o, float s) {
-    Uniq u = unique_children(gp, c, o, s);
+__device__ __forceinline__ void request_lp_evals(const Arena &A, const Grp &gp, int g, const Uniq &u, int o) {
     bool ask = u.is_first && A.stat[node_at(A, g, o)].x == 0;
     emit_requests(A, gp, g, gp.ballot(ask), o);
+}
+
+// All seven children of `leaf` are linked: de-duplicate the list once (core.h:111-144) and cache it in the row for select.
+__device__ __forceinline__ Uniq finish_expansion(const Arena &A, const Grp &gp, int g, int leaf, int c, int o, float s) {
+    Uniq u = unique_children(gp, c, o, s);
+    A.row[node_at(A, g, leaf) * ROW_WORDS + 24 + gp.lane] = gp.lane < 7 ? (int32_t)link_word(u) : 0;
+    return u;
 }
 
 // ---------------------------------------------------------------- select + expand (ValueSimLP.py:45-57 etc.)
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     int status = A.status[g];
     if (status == ST_ARENA_FULL && A.overflow_reset) reset_tree(A, gp, g, status);
     if (status != ST_OK) return;
-    ArenaAcc acc{A, g, s_z};
+    ArenaAcc acc(A, g, s_z);
     int D = 0;
     int leaf = A.mode == MODE_DIST ? dist_select_group(A, gp, g, A.root[g], D, status)
                                    : select_trace(acc, gp, A.root[g], A.low, A.trace_max, D, status);
@@ -181,8 +187,9 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
         if (status == ST_NEED_GC) {
             suspend_for_gc(A, gp, g, PEND_EXPAND, a_stop);
             kind = LEAF_SUSPENDED; status = ST_OK;
-        } else if (status == ST_OK && A.mode == MODE_LP) {
-            request_lp_evals(A, gp, g, c, o, s);
+        } else if (status == ST_OK) {
+            Uniq u = finish_expansion(A, gp, g, leaf, c, o, s);
+            if (A.mode == MODE_LP) request_lp_evals(A, gp, g, u, o);
         }
     }
     if (gp.lane == 0) {
@@ -209,9 +216,10 @@ __global__ void __launch_bounds__(TPB) k_expand_resume(Arena A) {
     int c, o, a_stop; float s;
     expand_leaf(A, gp, g, leaf, w, c, o, s, status, A.resume_a[g], false, a_stop);
     if (status == ST_OK) {
-        ArenaAcc acc{A, g};
+        ArenaAcc acc(A, g);
         acc.children(leaf, gp.lane, c, o, s);            // children 0..resume_a-1 were linked before the collection
-        if (A.mode == MODE_LP) request_lp_evals(A, gp, g, c, o, s);
+        Uniq u = finish_expansion(A, gp, g, leaf, c, o, s);
+        if (A.mode == MODE_LP) request_lp_evals(A, gp, g, u, o);
         if (gp.lane == 0) A.leaf_kind[g] = LEAF_EXPANDED;
     } else if (gp.lane == 0) {
         A.status[g] = status;
@@ -352,9 +360,10 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
             __syncthreads();
         }
         // zero the freed rows (agent.py:234-235; node_to_obs is not in self.arrays: o[7] stays), statistics and keys
-        for (int i = t; i < nn * 6; i += GC_THREADS) {
-            int4 *r = reinterpret_cast<int4 *>(rowb + (size_t)nfree[i / 6] * ROW_WORDS) + (i % 6);
-            *r = make_int4(0, 0, 0, (i % 6) == 3 ? r->w : 0);
+        constexpr int RQ = ROW_WORDS / 4;
+        for (int i = t; i < nn * RQ; i += GC_THREADS) {
+            int4 *r = reinterpret_cast<int4 *>(rowb + (size_t)nfree[i / RQ] * ROW_WORDS) + (i % RQ);
+            *r = make_int4(0, 0, 0, (i % RQ) == 3 ? r->w : 0);
         }
         if (A.nstat) {
             float *nsb = A.nstat + (size_t)g * M * NSTAT_WORDS, *ndb = A.ndist + (size_t)g * M * A.dist_bins;
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
     const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (g >= A.G || A.status[g] != ST_OK) return;
-    ArenaAcc acc{A, g};
+    ArenaAcc acc(A, g);
     const int D = A.trace_len[g];
     const int kind = A.leaf_kind[g];
     if (kind == LEAF_SUSPENDED || D <= 0) return;
@@ -519,12 +528,16 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
             continue;
         }
         if (lane < n) st = acc.stat(o);
+        // The value chain v <- gamma*(v - score) + score (core.h:244,259) does not depend on the statistics: every lane
+        // walks it (three dependent double operations per level) and keeps the value entering its own level; the expensive
+        // Welford updates (core.h:245-258) of the whole window then run in parallel, one level per lane.
+        double vin = v;
         for (int j = 0; j < n; ++j) {
-            double vin = __shfl_sync(0xffffffffu, v, j == 0 ? 0 : j - 1);     // v after level j-1 lives in lane j-1 (lane 0 initially)
-            if (lane == j) { if (j > 0) v = vin; welford_level(st, v, var, sc, A.gamma); }
+            const double scj = (double)__shfl_sync(0xffffffffu, sc, j);
+            if (lane == j) vin = v;
+            v = __dadd_rn(__dmul_rn(A.gamma, __dsub_rn(v, scj)), scj);
         }
-        if (lane < n) acc.set_stat(o, st);
-        v = __shfl_sync(0xffffffffu, v, n - 1);
+        if (lane < n) { welford_level(st, vin, var, sc, A.gamma); acc.set_stat(o, st); }
         __syncwarp();
     }
 }
@@ -616,7 +629,7 @@ __global__ void __launch_bounds__(128) k_dist_backup(Arena A) {
 __global__ void k_root_stats(Arena A, float *stats, int32_t *action) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= A.G) return;
-    ArenaAcc acc{A, g};
+    ArenaAcc acc(A, g);
     int root = A.root[g];
     int ro; float rs;
     acc.meta(root, ro, rs);

@@ -23,7 +23,7 @@
 
 namespace b200 {
 
-constexpr int ROW_WORDS = 24;     // child row: c[8] | o[8] | s[8]
+constexpr int ROW_WORDS = 32;     // child row (one 128-byte line): c[8] | o[8] | s[8] | u[8]; u = the child list already de-duplicated (see link_word)
 constexpr int ZTABLE_N = 65536;   // z(n) table computed on the host with the reference's libm (special.h:26-33)
 
 enum : int { ST_OK = 0, ST_ARENA_FULL = 1, ST_TRACE_FULL = 2, ST_NEED_GC = 3 };
@@ -119,27 +119,36 @@ __device__ __forceinline__ void welford_level(int4 &st, double &v, double var, f
 // In: lane a (<7) holds child slot a as (c, o, s).  Out, per lane: is_first (this lane is the first occurrence of
 // its observation: the list position), rep_c / rep_s = the child that represents the observation (the one with the
 // strictly largest score, earliest on ties).
-struct Uniq { bool is_first; int rep_c; float rep_s; unsigned first_mask; };
+struct Uniq { bool is_first; int rep_c; float rep_s; unsigned first_mask; int rep_lane; };
 
 __device__ __forceinline__ Uniq unique_children(const Grp &gp, int c, int o, float s) {
     bool valid = gp.lane < 7 && c != 0;
     unsigned vmask = gp.ballot(valid);
-    int first = -1, rep_c = 0;
+    int first = -1, rep_c = 0, rep_lane = 0;
     float best = 0.f;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
         int cj = gp.bcast(c, j), oj = gp.bcast(o, j);
         float sj = gp.bcast(s, j);
         if (((vmask >> j) & 1u) && oj == o) {
-            if (first < 0) { first = j; best = sj; rep_c = cj; }
-            else if (sj > best) { best = sj; rep_c = cj; }      // strict >, core.h:139
+            if (first < 0) { first = j; best = sj; rep_c = cj; rep_lane = j; }
+            else if (sj > best) { best = sj; rep_c = cj; rep_lane = j; }      // strict >, core.h:139
         }
     }
     Uniq u;
     u.is_first = valid && first == gp.lane;
-    u.rep_c = rep_c; u.rep_s = best;
+    u.rep_c = rep_c; u.rep_s = best; u.rep_lane = rep_lane;
     u.first_mask = gp.ballot(u.is_first);
     return u;
+}
+
+// The child list of a node never changes once the node is expanded (children are linked once, the collector keeps every
+// child of a reachable node), so core.h:111-144's de-duplication is done ONCE, when the expansion completes, and cached
+// in the row: u[a] = representative child (28 bits) | lane of the representative << 28 | is_first << 31.
+// select then needs no scan at all: one extra word from the same 128-byte line.
+constexpr uint32_t LINK_NODE_MASK = 0x0fffffffu;
+__device__ __forceinline__ uint32_t link_word(const Uniq &u) {
+    return ((uint32_t)u.rep_c & LINK_NODE_MASK) | ((uint32_t)u.rep_lane << 28) | (u.is_first ? 0x80000000u : 0u);
 }
 
 // ------------------------------------------------------------------ accessors
@@ -148,19 +157,34 @@ __device__ __forceinline__ Uniq unique_children(const Grp &gp, int c, int o, flo
 constexpr int ZS_N = 4096;   // z(n) entries staged in shared memory by k_select_expand (deep nodes have small n)
 
 struct ArenaAcc {
-    const Arena &A; int g; const float *zs = nullptr;
+    const Arena &A; int g; const float *zs;
+    const int32_t *rowg; int4 *statg; int32_t *traceg;      // this game's slices of the arena (address arithmetic hoisted out of the loops)
+    __device__ __forceinline__ ArenaAcc(const Arena &A_, int g_, const float *zs_ = nullptr)
+        : A(A_), g(g_), zs(zs_), rowg(A_.row + (size_t)g_ * A_.M * ROW_WORDS), statg(A_.stat + (size_t)g_ * A_.M),
+          traceg(A_.trace + (size_t)g_ * A_.trace_max) {}
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
-        const int32_t *row = A.row + node_at(A, g, idx) * ROW_WORDS;
+        const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
         c = row[lane]; o = row[8 + lane]; s = __int_as_float(row[16 + lane]);   // lane 7: own episode / obs / score
     }
     __device__ __forceinline__ void meta(int idx, int &o, float &s) const {
-        const int32_t *row = A.row + node_at(A, g, idx) * ROW_WORDS;
+        const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
         o = row[15]; s = __int_as_float(row[23]);
     }
-    __device__ __forceinline__ int4 stat(int o) const { return A.stat[node_at(A, g, o)]; }
-    __device__ __forceinline__ void set_stat(int o, int4 st) const { A.stat[node_at(A, g, o)] = st; }
-    __device__ __forceinline__ void put_trace(int d, int idx) const { A.trace[(size_t)g * A.trace_max + d] = idx; }
-    __device__ __forceinline__ int get_trace(int d) const { return A.trace[(size_t)g * A.trace_max + d]; }
+    // one level of select: observation of this lane's child, the node's own score, the cached de-duplication
+    __device__ __forceinline__ void level(const Grp &gp, int idx, int &o, float &s_idx, Uniq &u) const {
+        const int32_t *row = rowg + (size_t)idx * ROW_WORDS + gp.lane;
+        o = row[8];
+        const float s = __int_as_float(row[16]);
+        const uint32_t lw = (uint32_t)row[24];
+        s_idx = gp.bcast(s, 7);
+        u.is_first = lw >> 31; u.rep_lane = (int)((lw >> 28) & 7u); u.rep_c = (int)(lw & LINK_NODE_MASK);
+        u.rep_s = gp.bcast(s, u.rep_lane);
+        u.first_mask = gp.ballot(u.is_first);
+    }
+    __device__ __forceinline__ int4 stat(int o) const { return statg[o]; }
+    __device__ __forceinline__ void set_stat(int o, int4 st) const { statg[o] = st; }
+    __device__ __forceinline__ void put_trace(int d, int idx) const { traceg[d] = idx; }
+    __device__ __forceinline__ int get_trace(int d) const { return traceg[d]; }
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return (zs && n >= 0 && n < ZS_N) ? zs[n] : ztab(A, n); }
 };
@@ -173,6 +197,12 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
         else { c = 0; o = n2o[idx]; s = score[idx]; }
     }
     __device__ __forceinline__ void meta(int idx, int &o, float &s) const { o = n2o[idx]; s = score[idx]; }
+    __device__ __forceinline__ void level(const Grp &gp, int idx, int &o, float &s_idx, Uniq &u) const {
+        int c; float s;
+        children(idx, gp.lane, c, o, s);
+        s_idx = gp.bcast(s, 7);
+        u = unique_children(gp, c, o, s);
+    }
     __device__ __forceinline__ int4 stat(int o) const { return make_int4(visit[o], __float_as_int(value[o]), __float_as_int(variance[o]), 0); }
     __device__ __forceinline__ void set_stat(int o, int4 st) const { visit[o] = st.x; value[o] = __int_as_float(st.y); variance[o] = __int_as_float(st.z); }
     __device__ __forceinline__ void put_trace(int d, int idx) const { trace[d] = idx; }
@@ -190,10 +220,9 @@ __device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int r
         if (D >= trace_max) { status = ST_TRACE_FULL; break; }
         if (gp.lane == 0) acc.put_trace(D, idx);
         ++D;
-        int c, o; float s;
-        acc.children(idx, gp.lane, c, o, s);
-        float s_idx = gp.bcast(s, 7);
-        Uniq u = unique_children(gp, c, o, s);
+        int o; float s_idx;
+        Uniq u;
+        acc.level(gp, idx, o, s_idx, u);
         if (u.first_mask == 0) break;                                   // core.h:200 no children: leaf
         int4 st = make_int4(0, 0, 0, 0);
         if (u.is_first) st = acc.stat(o);
@@ -211,16 +240,20 @@ __device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int r
             n += __shfl_xor_sync(gp.mask, n, 4, 8);
             float z = acc.z(n);
             float q = u.is_first ? clt_q(__int_as_float(st.y), u.rep_s, s_idx, z, __int_as_float(st.z), st.x) : 0.f;
-            pick = -1;
-            float max_q = 0.f;
+            // core.h:94-101: the first strict maximum in list order = the largest q, the lowest lane on ties, as a 3-step
+            // butterfly.  A NaN never wins a `>`; it is the answer only when it is the first entry of the list.
+            const bool cand = u.is_first && q == q;
+            float qv = cand ? q : -INFINITY;
+            int ql = cand ? gp.lane : 8 + gp.lane;                       // non-candidates lose every tie
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {                                // core.h:94-101 first strict max in list order
-                float qj = gp.bcast(q, j);
-                if ((u.first_mask >> j) & 1u) {
-                    if (pick < 0) { pick = j; max_q = qj; }
-                    else if (qj > max_q) { max_q = qj; pick = j; }
-                }
+            for (int d = 1; d < 8; d <<= 1) {
+                const float oq = __shfl_xor_sync(gp.mask, qv, d, 8);
+                const int ol = __shfl_xor_sync(gp.mask, ql, d, 8);
+                const bool take = oq > qv || (oq == qv && ol < ql);
+                qv = take ? oq : qv; ql = take ? ol : ql;
             }
+            const int first = __ffs(u.first_mask) - 1;
+            pick = ((gp.ballot(q != q) >> first) & 1u) ? first : ql;
         }
         idx = gp.bcast(u.rep_c, pick);
     }
@@ -374,7 +407,7 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
 __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, int &status) {
     const int M = A.M, H = A.H;
     int4 *rows = reinterpret_cast<int4 *>(A.row + (size_t)g * M * ROW_WORDS);
-    for (int i = gp.lane; i < M * 6; i += 8) rows[i] = make_int4(0, 0, 0, 0);
+    for (int i = gp.lane; i < M * (ROW_WORDS / 4); i += 8) rows[i] = make_int4(0, 0, 0, 0);
     int4 *statb = A.stat + (size_t)g * M;
     for (int i = gp.lane; i < M; i += 8) statb[i] = make_int4(0, 0, 0, 0);
     uint4 *keyb = reinterpret_cast<uint4 *>(A.key + (size_t)g * M * KEY_WORDS);
