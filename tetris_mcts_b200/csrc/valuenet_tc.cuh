@@ -43,8 +43,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// whole warp waits, one lane polls (32 lanes polling the same word is shared-memory traffic the MMA operand fetch competes with)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity);
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -148,9 +154,12 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2
 // 18 MMAs (3 dy x 2 channel halves x 3 split products, N = 96) replace the 36 narrow ones of the tap-by-tap form, and
 // conv1 (K = 9 taps, exact {-1,0,1} inputs) runs on the tensor core too from an im2col operand the workers build.
 constexpr int TCC_WORKERS = 512;            // warps 0-15: decode / im2col and the three epilogues
-constexpr int TCC_ISSUER = TCC_WORKERS / 32; // warp 16: MMA issuer (one elected lane)
-constexpr int TCC_LOADER = TCC_ISSUER + 1; // warp 17: fetches the observation keys of the CTA's boards into a shared-memory ring
-constexpr int TCC_THREADS = TCC_WORKERS + 64;
+constexpr int TCC_ISSUER = TCC_WORKERS / 32; // warp 16: MMA issuer of conv1 + conv2 (one elected lane)
+constexpr int TCC_ISSUER3 = TCC_ISSUER + 1; // warp 17: MMA issuer of conv3.  A 56-clk MMA costs its issuing thread ~8 dependent instructions
+                                            // (uniform-register moves + the elect loop) and that thread shares its scheduler with four busy
+                                            // worker warps: one issuer alone cannot keep the tensor pipe fed, two (on two schedulers) can.
+constexpr int TCC_LOADER = TCC_ISSUER + 2;  // warp 18: fetches the observation keys of the CTA's boards into a shared-memory ring
+constexpr int TCC_THREADS = TCC_WORKERS + 96;
 constexpr int TCC_R = 144;                  // activation rows per board: 18x8 grid (act1) / 16x8 grid + the dy shifts (act2)
 constexpr int TCC_WBLOCK = 2 * 2 * 96 * 16;  // one (dy, channel half) block: [weight split 2][chunk 2][n = dx*32 + cout][16 B]
 constexpr int TCC_WBYTES = 6 * TCC_WBLOCK;   // one conv layer = 36864 B
@@ -268,7 +277,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     if (t < 32) { sB[t] = W.b1[t]; sB[32 + t] = W.b2[t]; sB[64 + t] = W.b3[t]; }
     if (t == 0) {
         for (int i = 0; i < 3 * NS; ++i) mbar_init(&bars[i], 1);
-        for (int i = 3 * NS; i < 6 * NS; ++i) mbar_init(&bars[i], TCC_WORKERS);
+        for (int i = 3 * NS; i < 6 * NS; ++i) mbar_init(&bars[i], TCC_WORKERS / 32);      // one arrival per worker warp
         for (int i = 6 * NS; i < 7 * NS; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
@@ -281,10 +290,11 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     const int n_req = *n_req_ptr;
     // Boards are handed out in runs of 8 consecutive requests (neighbouring act3 rows get written close in time); board i of
     // this CTA's sequence lives in slot i % 4.  Four boards are in flight at different stages (software pipeline):
-    //   workers, iteration i :  S0(i) im2col | E1(i-1) conv1 epilogue | E2(i-2) conv2 epilogue | E3(i-3) conv3 epilogue
-    //   issuer,  iteration i :  conv1(i) | conv2(i-1) | conv3(i-2), each as soon as the workers have written its operand
-    // Every MMA batch is consumed one worker iteration after it was issued, so the tensor pipe works on three boards while
-    // the CUDA cores prepare / drain the others.
+    //   workers, iteration i :  S0(i) im2col | E2(i-2) conv2 epilogue | E3(i-3) conv3 epilogue | E1(i) conv1 epilogue
+    //   issuer,  iteration i :  conv2(i-1) | conv1(i) | conv3(i-2), each as soon as the workers have written its operand
+    // The order is chosen so that the tensor pipe never runs dry: conv2(i-1)'s operand was finished at the end of the
+    // previous iteration (E1 comes last), conv1(i) is short and queued behind it, conv3(i-2)'s operand (E2) is ready long
+    // before conv2 retires; the workers drain older boards (E2, E3) while conv2 runs and reach E1(i) after conv1(i) is done.
     const int n_runs = (n_req + 7) >> 3;
     int n_local = 0;
     for (int run = blockIdx.x; run < n_runs; run += gridDim.x) n_local += min(8, n_req - run * 8);
@@ -296,7 +306,16 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
             const uint32_t s_act = smem_u32(smem + TCC_OFF_A1), s_im = smem_u32(smem + TCC_OFF_IM);
             const bool do_prof = blockIdx.x == 0;
             long long pacc[16] = {0}, ptick = clock64();
-            for (int i = 0; i < n_local + 2; ++i) {
+            for (int i = 0; i < n_local + 1; ++i) {
+                if (i >= 1) {                                    // conv2 (model_vv.py:34): act1 on the 18x8 grid
+                    const int j = i - 1, slot = j % NS;
+                    mbar_wait(&bar_a1[slot], (uint32_t)(j / NS) & 1u);
+                    PROF_T(10);
+                    tc_fence_after();
+                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
+                    umma_commit(&bar_c2[slot]);
+                    PROF_T(11);
+                }
                 if (i < n_local) {                               // conv1 (model_vv.py:32): im2col [256 x 16] x W1 [16 x 64], two M tiles
                     const int slot = i % NS;
                     mbar_wait(&bar_a0[slot], (uint32_t)(i / NS) & 1u);
@@ -308,26 +327,25 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     umma_commit(&bar_c1[slot]);
                     PROF_T(9);
                 }
-                if (i >= 1 && i - 1 < n_local) {                 // conv2 (model_vv.py:34): act1 on the 18x8 grid
-                    const int j = i - 1, slot = j % NS;
-                    mbar_wait(&bar_a1[slot], (uint32_t)(j / NS) & 1u);
-                    PROF_T(10);
-                    tc_fence_after();
-                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
-                    umma_commit(&bar_c2[slot]);
-                    PROF_T(11);
-                }
-                if (i >= 2) {                                    // conv3 (model_vv.py:36): act2 on the 16x8 grid
-                    const int j = i - 2, slot = j % NS;
-                    mbar_wait(&bar_a2[slot], (uint32_t)(j / NS) & 1u);
-                    PROF_T(12);
-                    tc_fence_after();
-                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w3);
-                    umma_commit(&bar_c3[slot]);
-                    PROF_T(13);
-                }
             }
-            if (prof && do_prof) for (int i = 8; i < 14; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+            if (prof && do_prof) for (int i = 8; i < 12; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+        }
+    } else if (warp == TCC_ISSUER3) {
+        // ===================================================== second MMA issuer: conv3 (model_vv.py:36), act2 on the 16x8 grid
+        if (lane == 0) {
+            const uint32_t s_w3 = smem_u32(smem + TCC_OFF_W3), s_act = smem_u32(smem + TCC_OFF_A1);
+            const bool do_prof = blockIdx.x == 0;
+            long long pacc[16] = {0}, ptick = clock64();
+            for (int j = 0; j < n_local; ++j) {
+                const int slot = j % NS;
+                mbar_wait(&bar_a2[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(12);
+                tc_fence_after();
+                issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w3);
+                umma_commit(&bar_c3[slot]);
+                PROF_T(13);
+            }
+            if (prof && do_prof) for (int i = 12; i < 14; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
         }
     } else if (warp == TCC_LOADER) {
         // ===================================================== key loader: global loads stay out of the workers' way (their
@@ -339,7 +357,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
             const uint32_t gx = __shfl_sync(0xffffffffu, rqs.x, i & 31), gy = __shfl_sync(0xffffffffu, rqs.y, i & 31);
             uint32_t kw = 0;
             if (lane < 12) kw = keys[((size_t)gx * M + (gy & 0x0fffffffu)) * KEY_WORDS + lane];
-            if (i >= NS) mbar_wait(&bar_c1[slot], (uint32_t)((i - NS) / NS) & 1u);     // conv1 of the slot's previous board done => its key was consumed
+            if (i >= NS) mbar_wait_warp(&bar_c1[slot], (uint32_t)((i - NS) / NS) & 1u);     // conv1 of the slot's previous board done => its key was consumed
             if (lane < 12) sKey[slot * 16 + lane] = kw;
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_k[slot]);
@@ -350,12 +368,15 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
         long long pacc[16] = {0}, ptick = clock64();
         const int q = warp & 3, cq = warp >> 2, m = q * 32 + lane;       // TMEM lane quadrant, 8-cout chunk, pixel row
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 8;
+        float bias1[8], bias2[8], bias3[8];                               // this warp's 8 couts, all three layers
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { bias1[e] = sB[cq * 8 + e]; bias2[e] = sB[32 + cq * 8 + e]; bias3[e] = sB[64 + cq * 8 + e]; }
         for (int i = 0; i < n_local + 3; ++i) {
             // ---- S0(i): observation key -> im2col operand of conv1 (fp16, exact): row p = y*8 + x, k = tap = dy*3 + dx.
             if (i < n_local) {
                 const int slot = i % NS;
                 const int dy = t / 144, p = t - dy * 144, y = p >> 3, x = p & 7, r = y + dy;     // t < 432: one filter row of one pixel
-                mbar_wait(&bar_k[slot], (uint32_t)(i / NS) & 1u);
+                mbar_wait_warp(&bar_k[slot], (uint32_t)(i / NS) & 1u);
                 const uint32_t rowword = sKey[slot * 16 + ((r >> 1) & 15)], pcs = sKey[slot * 16 + 10];
                 if (t < 432) {
                     const uint32_t settled = (rowword >> ((r & 1) * 16)) >> x;
@@ -375,13 +396,60 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     }
                 }
                 fence_async_smem();
-                mbar_arrive(&bar_a0[slot]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a0[slot]);     // 32 same-address arrivals would serialise in the shared-memory pipe the MMAs read through
                 PROF_T(0);
             }
-            // ---- E1(i-1): conv1 epilogue: bias + ReLU + split -> act1 (18x8 grid)
-            if (i >= 1 && i - 1 < n_local) {
-                const int j = i - 1, slot = j % NS;
-                mbar_wait(&bar_c1[slot], (uint32_t)(j / NS) & 1u);
+            // ---- E2(i-2): conv2 epilogue: dx sum + bias + ReLU + split -> act2 (16x8 grid), in place of the slot's act1
+            if (i >= 2 && i - 2 < n_local) {
+                const int j = i - 2, slot = j % NS;
+                mbar_wait_warp(&bar_c2[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(3);
+                tc_fence_after();
+                float v[8];
+                tmem_ld_conv_sum(t_lane + slot * 128, v);
+                if ((m & 7) < 6) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + bias2[e], 0.f) * TC_SCALE_A;
+                    uint4 c1, c2;
+                    split8(o, c1, c2);
+                    uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (cq * TCC_R + m) * 16;
+                    *reinterpret_cast<uint4 *>(base) = c1;
+                    *reinterpret_cast<uint4 *>(base + 4 * TCC_R * 16) = c2;
+                }
+                tc_fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a2[slot]);     // 32 same-address arrivals would serialise in the shared-memory pipe the MMAs read through
+                PROF_T(4);
+            }
+            // ---- E3(i-3): conv3 epilogue: dx sum + bias + ReLU + split -> act3 in HBM (FC tile layout)
+            if (i >= 3) {
+                const int j = i - 3, slot = j % NS, ridx = board_of(j);
+                mbar_wait_warp(&bar_c3[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(5);
+                tc_fence_after();
+                const int y = m >> 3, x = m & 7;
+                float v[8];
+                tmem_ld_conv_sum(t_lane + slot * 128, v);
+                if (y < 14 && x < 4) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + bias3[e], 0.f) * TC_SCALE_A;
+                    uint4 c1, c2;
+                    split8(o, c1, c2);
+                    const int kc = (y * 4 + x) * 4 + cq;
+                    *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
+                    *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = c2;
+                }
+                tc_fence_before();
+                PROF_T(6);
+            }
+            // ---- E1(i): conv1 epilogue: bias + ReLU + split -> act1 (18x8 grid)
+            if (i < n_local) {
+                const int j = i, slot = j % NS;
+                mbar_wait_warp(&bar_c1[slot], (uint32_t)(j / NS) & 1u);
                 PROF_T(1);
                 tc_fence_after();
                 uint8_t *abase = smem + TCC_OFF_A1 + slot * TCC_ASLOT + cq * TCC_R * 16;
@@ -389,7 +457,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     float w1[8], w2[8], o[8];
                     tmem_ld8x2(t_lane + slot * 128, w1, w2);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + sB[cq * 8 + e], 0.f) * TC_SCALE_A;
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + bias1[e], 0.f) * TC_SCALE_A;
                     uint4 c1, c2;
                     split8(o, c1, c2);
                     *reinterpret_cast<uint4 *>(abase + m * 16) = c1;
@@ -400,7 +468,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     tmem_ld8x2(t_lane + slot * 128 + 64, w1, w2);
                     if (lane < 16) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + sB[cq * 8 + e], 0.f) * TC_SCALE_A;
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + bias1[e], 0.f) * TC_SCALE_A;
                         uint4 c1, c2;
                         split8(o, c1, c2);
                         *reinterpret_cast<uint4 *>(abase + (128 + lane) * 16) = c1;
@@ -409,53 +477,9 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                 }
                 tc_fence_before();
                 fence_async_smem();
-                mbar_arrive(&bar_a1[slot]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a1[slot]);     // 32 same-address arrivals would serialise in the shared-memory pipe the MMAs read through
                 PROF_T(2);
-            }
-            // ---- E2(i-2): conv2 epilogue: dx sum + bias + ReLU + split -> act2 (16x8 grid), in place of the slot's act1
-            if (i >= 2 && i - 2 < n_local) {
-                const int j = i - 2, slot = j % NS;
-                mbar_wait(&bar_c2[slot], (uint32_t)(j / NS) & 1u);
-                PROF_T(3);
-                tc_fence_after();
-                float v[8];
-                tmem_ld_conv_sum(t_lane + slot * 128, v);
-                if ((m & 7) < 6) {
-                    float o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[32 + cq * 8 + e], 0.f) * TC_SCALE_A;
-                    uint4 c1, c2;
-                    split8(o, c1, c2);
-                    uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (cq * TCC_R + m) * 16;
-                    *reinterpret_cast<uint4 *>(base) = c1;
-                    *reinterpret_cast<uint4 *>(base + 4 * TCC_R * 16) = c2;
-                }
-                tc_fence_before();
-                fence_async_smem();
-                mbar_arrive(&bar_a2[slot]);
-                PROF_T(4);
-            }
-            // ---- E3(i-3): conv3 epilogue: dx sum + bias + ReLU + split -> act3 in HBM (FC tile layout)
-            if (i >= 3) {
-                const int j = i - 3, slot = j % NS, ridx = board_of(j);
-                mbar_wait(&bar_c3[slot], (uint32_t)(j / NS) & 1u);
-                PROF_T(5);
-                tc_fence_after();
-                const int y = m >> 3, x = m & 7;
-                float v[8];
-                tmem_ld_conv_sum(t_lane + slot * 128, v);
-                if (y < 14 && x < 4) {
-                    float o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[64 + cq * 8 + e], 0.f) * TC_SCALE_A;
-                    uint4 c1, c2;
-                    split8(o, c1, c2);
-                    const int kc = (y * 4 + x) * 4 + cq;
-                    *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
-                    *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = c2;
-                }
-                tc_fence_before();
-                PROF_T(6);
             }
         }
         if (prof && do_prof) for (int i = 0; i < 7; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
