@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_2iss.json 2> gpurun_out/bench_2iss.err; python scripts/show_bench.py gpurun_out/bench_2iss.json; tail -3 gpurun_out/bench_2iss.err
+timeout 600 python -m pytest tests/test_gpu_valuenet.py -x -q 2>&1 | tail -3
+timeout 300 python scripts/exp_growth.py 16384 16384 200 1 net_tc 2>&1 | tail -3 | cut -c1-900

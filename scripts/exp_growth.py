@@ -29,6 +29,6 @@ from tetris_mcts_b200 import _lib as L
 pr = np.zeros(16, np.uint64)
 L.lib().b200_debug_prof.argtypes = [L.P, L.P]
 L.check(L.lib().b200_debug_prof(eng.h, L.ptr(pr)))
-names = ['S0_im2col', 'wait_c1', 'E1', 'wait_c2', 'E2', 'wait_c3', 'E3', '-', 'iss_wait_a0', 'iss_conv1', 'iss_wait_a1', 'iss_conv2', 'iss_wait_a2', 'iss_conv3']
-tot = pr[:7].sum()
+names = ['S0_arrive', 'wait_c1', 'E1', 'wait_c2', 'E2', 'wait_c3', 'E3', 'S0_wait_key', 'iss_wait_a0', 'iss_conv1', 'iss_wait_a1', 'iss_conv2', 'iss_wait_a2', 'iss_conv3', 'S0_compute', 'S0_fence']
+tot = pr[:8].sum() + pr[14:16].sum()
 print({n: round(float(pr[i]) / max(float(tot), 1), 3) for i, n in enumerate(names)}, 'worker cycles total', int(tot), 'boards', c['eval_requests'] // 148)

@@ -373,12 +373,17 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
         for (int e = 0; e < 8; ++e) { bias1[e] = sB[cq * 8 + e]; bias2[e] = sB[32 + cq * 8 + e]; bias3[e] = sB[64 + cq * 8 + e]; }
         for (int i = 0; i < n_local + 3; ++i) {
             // ---- S0(i): observation key -> im2col operand of conv1 (fp16, exact): row p = y*8 + x, k = tap = dy*3 + dx.
+            // Lanes 3k, 3k+1, 3k+2 of a warp hold the three filter rows of pixel p = 10*warp + k; lane 3k gathers them with two
+            // shuffles and writes the row's taps 0..7 as ONE 16-byte store (2-byte scatter stores were 4-way bank conflicted).
             if (i < n_local) {
                 const int slot = i % NS;
-                const int dy = t / 144, p = t - dy * 144, y = p >> 3, x = p & 7, r = y + dy;     // t < 432: one filter row of one pixel
+                const int pk = lane / 3, dy = lane - pk * 3, p = warp * 10 + pk, y = p >> 3, x = p & 7, r = y + dy;
+                const bool valid = lane < 30 && p < 144;                 // 15 warps x 10 pixels
                 mbar_wait_warp(&bar_k[slot], (uint32_t)(i / NS) & 1u);
-                const uint32_t rowword = sKey[slot * 16 + ((r >> 1) & 15)], pcs = sKey[slot * 16 + 10];
-                if (t < 432) {
+                PROF_T(7);
+                uint32_t lo = 0, hi = 0;
+                if (valid) {
+                    const uint32_t rowword = sKey[slot * 16 + (r >> 1)], pcs = sKey[slot * 16 + 10];
                     const uint32_t settled = (rowword >> ((r & 1) * 16)) >> x;
                     uint32_t piece = 0;
 #pragma unroll
@@ -387,15 +392,22 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                         piece |= (pr == (uint32_t)r ? 1u : 0u) << pcol;
                     }
                     piece >>= x;
-                    uint8_t *row0 = smem + TCC_OFF_IM + slot * TCC_IMSLOT + p * 16;
+                    uint32_t hv[3];
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {             // 1 settled, -1 falling piece, 0 empty (model_vv.py:212)
-                        const uint32_t hv = ((settled >> dx) & 1u) * 0x3C00u | ((piece >> dx) & 1u) * 0xBC00u;
-                        const int tap = dy * 3 + dx;
-                        *reinterpret_cast<uint16_t *>(row0 + (tap >> 3) * (TCC_IMROWS * 16) + (tap & 7) * 2) = (uint16_t)hv;
-                    }
+                    for (int dx = 0; dx < 3; ++dx)               // 1 settled, -1 falling piece, 0 empty (model_vv.py:212)
+                        hv[dx] = ((settled >> dx) & 1u) * 0x3C00u | ((piece >> dx) & 1u) * 0xBC00u;
+                    lo = hv[0] | (hv[1] << 16); hi = hv[2];
                 }
+                const uint32_t a_lo = __shfl_down_sync(0xffffffffu, lo, 1), a_hi = __shfl_down_sync(0xffffffffu, hi, 1);
+                const uint32_t b_lo = __shfl_down_sync(0xffffffffu, lo, 2), b_hi = __shfl_down_sync(0xffffffffu, hi, 2);
+                if (valid && dy == 0) {
+                    uint8_t *row0 = smem + TCC_OFF_IM + slot * TCC_IMSLOT + p * 16;
+                    *reinterpret_cast<uint4 *>(row0) = make_uint4(lo, hi | (a_lo << 16), (a_lo >> 16) | (a_hi << 16), b_lo);   // taps 0..7
+                    *reinterpret_cast<uint32_t *>(row0 + TCC_IMROWS * 16) = b_hi;                                              // tap 8
+                }
+                PROF_T(14);
                 fence_async_smem();
+                PROF_T(15);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_a0[slot]);     // 32 same-address arrivals would serialise in the shared-memory pipe the MMAs read through
                 PROF_T(0);
@@ -482,7 +494,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                 PROF_T(2);
             }
         }
-        if (prof && do_prof) for (int i = 0; i < 7; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+        if (prof && do_prof) for (int i = 0; i < 16; ++i) if (i < 8 || i > 13) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
     }
 #undef PROF_T
     tc_fence_before();
