@@ -345,7 +345,7 @@ def run_b200(args, cfg):
         config = dict(cfg["config"])
         config.update({"parallelism": "games sharded x%d, no data-path collective" % world,
                        "l2": "inputs larger than L2: %.1f GB of arenas per GPU; %.2f GB of activations stream through L2 every sim-step"
-                             % (G * M * 292 / 1e9, G * 7 * 1792 * 4 / 1e9)})
+                             % (G * M * 324 / 1e9, G * 7 * 1792 * 4 / 1e9)})
         out = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": config, "roofline": roof, "roofline_select_backup": roof_tree, "cpu_baseline": cpu,

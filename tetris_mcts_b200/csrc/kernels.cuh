@@ -162,6 +162,7 @@ __device__ __forceinline__ Uniq finish_expansion(const Arena &A, const Grp &gp, 
 // ---------------------------------------------------------------- select + expand (ValueSimLP.py:45-57 etc.)
 __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     __shared__ float s_z[ZS_N];
+    __shared__ __align__(16) uint32_t s_stage[GROUPS_PER_BLOCK * STAGE_GROUP_WORDS];
     for (int i = threadIdx.x; i < ZS_N; i += TPB) s_z[i] = A.ztable[i];
     __syncthreads();
     Grp gp;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
         if (A.mode == MODE_SINGLE || A.mode == MODE_DIST)   // ValueSim.py:83-88 / DistValueSimOnline.py:66-70: the leaf itself is evaluated
             emit_requests(A, gp, g, 1u << 7, A.row[node_at(A, g, leaf) * ROW_WORDS + 15]);
         int c, o, a_stop; float s;
-        expand_leaf(A, gp, g, leaf, w, c, o, s, status, 0, true, a_stop);
+        expand_leaf(A, gp, g, leaf, w, c, o, s, status, 0, true, a_stop, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS);
         if (status == ST_NEED_GC) {
             suspend_for_gc(A, gp, g, PEND_EXPAND, a_stop);
             kind = LEAF_SUSPENDED; status = ST_OK;
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
 
 // continue the expansions that had to wait for k_gc (children resume_a..6), then queue their evaluations
 __global__ void __launch_bounds__(TPB) k_expand_resume(Arena A) {
+    __shared__ __align__(16) uint32_t s_stage[GROUPS_PER_BLOCK * STAGE_GROUP_WORDS];
     Grp gp;
     int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
     if (g >= A.G) return;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(TPB) k_expand_resume(Arena A) {
     uint32_t w[REC_WORDS];
     load_rec(A.rec + node_at(A, g, leaf) * REC_WORDS, w);
     int c, o, a_stop; float s;
-    expand_leaf(A, gp, g, leaf, w, c, o, s, status, A.resume_a[g], false, a_stop);
+    expand_leaf(A, gp, g, leaf, w, c, o, s, status, A.resume_a[g], false, a_stop, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS);
     if (status == ST_OK) {
         ArenaAcc acc(A, g);
         acc.children(leaf, gp.lane, c, o, s);            // children 0..resume_a-1 were linked before the collection

@@ -154,7 +154,7 @@ __device__ __forceinline__ uint32_t link_word(const Uniq &u) {
 // ------------------------------------------------------------------ accessors
 // The engine keeps the packed arena above; the single-call twins of agents/cppmodule/core.cpp:20-26 work on the
 // reference's own array layout (agents/agent.py:58-88).  Both run the same select / backup code through these.
-constexpr int ZS_N = 4096;   // z(n) entries staged in shared memory by k_select_expand (deep nodes have small n)
+constexpr int ZS_N = 2048;   // z(n) entries staged in shared memory by k_select_expand (deep nodes have small n)
 
 struct ArenaAcc {
     const Arena &A; int g; const float *zs;
@@ -439,27 +439,42 @@ __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, in
 // ------------------------------------------------------------------ expand (agent.py:136-145)
 // lane a plays action a on the leaf's game; the seven results are then inserted in action order (first seen wins,
 // free-list order and a mid-expand garbage collection all as in the reference).  Leaves c/o/s of child a in lane a.
+// Shared-memory staging of the seven children of one expansion: lane a plays action a, digests the resulting game and parks
+// record | observation key | hashes in its slot; the insertion loop then reads child a with broadcast loads.  (Holding the
+// 36 words per lane in registers across the loop and moving them with 36 shuffles per child spilled at 64 registers.)
+constexpr int STAGE_WORDS = 36;                      // rec[20] | key[12] | h, hk, end, score
+constexpr int STAGE_GROUP_WORDS = 7 * STAGE_WORDS;   // per game in flight
+
 __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g, int leaf, const uint32_t (&leafrec)[REC_WORDS],
-                                            int &c, int &o, float &s, int &status, int a_begin, bool may_suspend, int &a_stop) {
-    uint32_t mine[REC_WORDS];
-    Digest dmine;
-    {
+                                            int &c, int &o, float &s, int &status, int a_begin, bool may_suspend, int &a_stop,
+                                            uint32_t *stage) {
+    if (gp.lane < 7) {
+        uint32_t mine[REC_WORDS];
+        Digest dm;
         Game gm;
         unpack(gm, leafrec);
-        play(gm, gp.lane < 7 ? gp.lane : 0);
+        play(gm, gp.lane);
         pack(gm, mine);
-        digest_game(mine, dmine);
+        digest_game(mine, dm);
+        uint4 *dst = reinterpret_cast<uint4 *>(stage + gp.lane * STAGE_WORDS);
+#pragma unroll
+        for (int q = 0; q < REC_WORDS / 4; ++q) dst[q] = make_uint4(mine[4 * q], mine[4 * q + 1], mine[4 * q + 2], mine[4 * q + 3]);
+#pragma unroll
+        for (int q = 0; q < KEY_WORDS / 4; ++q) dst[5 + q] = make_uint4(dm.key[4 * q], dm.key[4 * q + 1], dm.key[4 * q + 2], dm.key[4 * q + 3]);
+        dst[8] = make_uint4(dm.h, dm.hk, (uint32_t)dm.end, __float_as_uint(dm.score));
     }
+    gp.sync();
     c = 0; o = 0; s = 0.f;
     a_stop = N_ACTIONS;
     for (int a = a_begin; a < N_ACTIONS; ++a) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(stage + a * STAGE_WORDS);
         uint32_t w[REC_WORDS];
-#pragma unroll
-        for (int q = 0; q < REC_WORDS; ++q) w[q] = gp.bcast(mine[q], a);
         Digest dg;
-        dg.h = gp.bcast(dmine.h, a); dg.hk = gp.bcast(dmine.hk, a); dg.end = gp.bcast(dmine.end, a); dg.score = gp.bcast(dmine.score, a);
 #pragma unroll
-        for (int q = 0; q < KEY_WORDS; ++q) dg.key[q] = gp.bcast(dmine.key[q], a);
+        for (int q = 0; q < REC_WORDS / 4; ++q) { const uint4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+#pragma unroll
+        for (int q = 0; q < KEY_WORDS / 4; ++q) { const uint4 v = src[5 + q]; dg.key[4 * q] = v.x; dg.key[4 * q + 1] = v.y; dg.key[4 * q + 2] = v.z; dg.key[4 * q + 3] = v.w; }
+        { const uint4 v = src[8]; dg.h = v.x; dg.hk = v.y; dg.end = (int)v.z; dg.score = __uint_as_float(v.w); }
         int oo; float ss;
         int idx = new_node(A, gp, g, w, dg, oo, ss, status, may_suspend);
         if (status == ST_NEED_GC) { a_stop = a; break; }     // resume at this child after k_gc
