@@ -9,7 +9,9 @@ G, M, sims = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 moves = int(sys.argv[4]); ev = sys.argv[5] if len(sys.argv) > 5 else 'net'
 eng = BatchedEngine(G, max_nodes=M, mode='lp', eval_kind=ev, weights=init_weights(0), overflow_reset=True)
 eng.set_games(PT.new_games(G, (1, 0, 0), np.arange(123, 123 + G, dtype=np.uint32)))
-eng.set_timing(True)
+import os
+TIMING = os.environ.get('NO_TIMING') != '1'
+eng.set_timing(TIMING)
 prev = eng.counters()
 for mv in range(moves):
     t = time.time()
@@ -32,3 +34,9 @@ L.check(L.lib().b200_debug_prof(eng.h, L.ptr(pr)))
 names = ['S0_arrive', 'wait_c1', 'E1', 'wait_c2', 'E2', 'wait_c3', 'E3', 'S0_wait_key', 'iss_wait_a0', 'iss_conv1', 'iss_wait_a1', 'iss_conv2', 'iss_wait_a2', 'iss_conv3', 'S0_compute', 'S0_fence']
 tot = pr[:8].sum() + pr[14:16].sum()
 print({n: round(float(pr[i]) / max(float(tot), 1), 3) for i, n in enumerate(names)}, 'worker cycles total', int(tot), 'boards', c['eval_requests'] // 148)
+
+pt = np.zeros(8, np.uint64)
+L.lib().b200_debug_prof_tree.argtypes = [L.P, L.P]
+L.check(L.lib().b200_debug_prof_tree(eng.h, L.ptr(pt)))
+tt = float(pt[:4].sum())
+print('k_select_expand sampled groups', int(pt[4]), {n: round(float(pt[i]) / max(tt, 1), 3) for i, n in enumerate(['select', 'leaf_load', 'expand', 'finish+evalreq'])}, 'mean clk/group', int(tt / max(float(pt[4]), 1)))

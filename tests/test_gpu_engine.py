@@ -181,6 +181,42 @@ def test_full_size_properties(gpu_lib):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
+def test_graph_replay_equals_direct_launches(gpu_lib):
+    """b200_run_sims replays one captured simulation step (CUDA graph) when phase timing is off and launches the
+    kernels one by one when it is on; requests and counters are aggregated per CTA in k_select_expand.  Both paths must
+    give the same statistics, actions, arenas and counters (including a garbage collection and the replay memory,
+    which changes the captured kernel arguments after the first capture)."""
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    from tetris_mcts_b200.model.model_vv import init_weights
+    n, M, sims, moves = 96, 1024, 25, 14
+    recs = PT.new_games(n, ARGS, np.arange(7, 7 + n, dtype=np.uint32))
+    for kind, w in (("synthetic", None), ("net_tc", init_weights(3))):
+        res = []
+        for timing in (False, True):
+            eng = BatchedEngine(n, max_nodes=M, mode="lp", eval_kind=kind, weights=w, seed=5, overflow_reset=True)
+            eng.set_timing(timing)
+            eng.set_games(recs)
+            out = []
+            for mv in range(moves):
+                if mv == 3:
+                    eng.replay_enable(min_visits=2, capacity=50000)
+                actions, stats = eng.play_move(sims, auto_reset=True)
+                out.append((actions.copy(), stats.copy()))
+            c = eng.counters()
+            assert c["sims"] == n * sims * moves and c["gcs"] > 0
+            res.append((out, c, eng.export_game(n // 2), eng.get_games().copy()))
+            eng.close()
+        (o0, c0, e0, g0), (o1, c1, e1, g1) = res
+        for (a0, s0), (a1, s1) in zip(o0, o1):
+            assert np.array_equal(a0, a1) and np.array_equal(s0, s1)
+        for k in ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "new_nodes"):
+            assert c0[k] == c1[k], k
+        for k in e0:
+            assert np.array_equal(e0[k], e1[k]), k
+        assert np.array_equal(g0, g1)
+
+
 def test_replay_memory_filled_at_garbage_collection(gpu_lib, oracle):
     """ValueSim.remove_nodes -> store_nodes(obs_available) (agents/ValueSim.py:101-159): the observations a collection frees,
     with visit >= min_visits_to_store and not end, as 212-byte rows.  The device stores them in arbitrary order, the

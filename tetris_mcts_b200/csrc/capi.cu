@@ -62,7 +62,16 @@ struct b200_engine {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // sampling
     uint8_t *d_samples = nullptr; int sample_cap = 0; int32_t *d_sample_count = nullptr;
+    // one simulation step captured as a CUDA graph (replayed when phase timing is off: ~7 launches + 1 memset per step, 500 steps/move)
+    cudaGraphExec_t step_exec = nullptr; bool step_graph_failed = false;
+    uint64_t step_launches[PH_N] = {0};
 };
+
+// kernel arguments of the captured step changed (weights, replay memory, ...): capture again at the next run_sims
+static void drop_step_graph(b200_engine *e) {
+    if (e->step_exec) { cudaStreamSynchronize(e->stream); cudaGraphExecDestroy(e->step_exec); e->step_exec = nullptr; }
+    e->step_graph_failed = false;
+}
 
 template <typename T>
 static int dalloc(b200_engine *e, T **p, size_t n, bool zero = true) {
@@ -170,7 +179,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     rc |= dalloc(e, &A.req, G * 8); rc |= dalloc(e, &A.n_req, 2);
     rc |= dalloc(e, &A.gc_list, G); rc |= dalloc(e, &A.pending, G); rc |= dalloc(e, &A.resume_a, G);
     rc |= dalloc(e, &A.eval_out, G * 8); rc |= dalloc(e, &A.rollout_val, G);
-    rc |= dalloc(e, &A.counters, 32);
+    rc |= dalloc(e, &A.counters, 48);
     if (cfg->mode == MODE_DIST) {
         A.dist_bins = cfg->dist_bins; A.dist_vmin = cfg->dist_vmin; A.dist_vmax = cfg->dist_vmax;
         rc |= dalloc(e, &A.nstat, GM * NSTAT_WORDS); rc |= dalloc(e, &A.ndist, GM * (size_t)A.dist_bins); rc |= dalloc(e, &A.dist_eval, G * (size_t)A.dist_bins);
@@ -203,6 +212,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
 extern "C" int b200_engine_destroy(b200_engine *e) {
     if (!e) return B200_OK;
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->step_exec) cudaGraphExecDestroy(e->step_exec);
 #ifdef B200_WITH_TC
     tc_destroy(e->tc_state);
 #endif
@@ -262,6 +272,7 @@ extern "C" int b200_load_weights(b200_engine *e, const float *w) {
     }
 #endif
     e->have_weights = true;
+    drop_step_graph(e);
     return B200_OK;
 }
 
@@ -279,7 +290,9 @@ static int launch_net(b200_engine *e, const uint2 *req, const int32_t *n_req, co
 #ifdef B200_WITH_TC
     if (e->cfg.eval_kind == B200_EVAL_NET_TC) {
         TcState *st = (TcState *)e->tc_state;
+        const uint8_t *act3_before = st->d_act3;
         if (tc_ensure_act3(st, max_rows, e->stream)) return fail(B200_ERR_CUDA, "act3 (tensor-core layout) allocation failed");
+        if (act3_before && st->d_act3 != act3_before) drop_step_graph(e);   // a larger standalone batch moved the activation buffer
         {
             PhaseTimer t(e, PH_CONV);
             k_tc_conv<<<e->n_sm, TCC_THREADS, TCC_SMEM, e->stream>>>(e->W, st->TW, req, n_req, keys, M, st->d_act3, (int)st->tiles,
@@ -293,7 +306,11 @@ static int launch_net(b200_engine *e, const uint2 *req, const int32_t *n_req, co
         return B200_OK;
     }
 #endif
-    if (ensure_act3(e, max_rows)) return B200_ERR_CUDA;
+    {
+        const float *act3_before = e->d_act3;
+        if (ensure_act3(e, max_rows)) return B200_ERR_CUDA;
+        if (act3_before && e->d_act3 != act3_before) drop_step_graph(e);
+    }
     {
         PhaseTimer t(e, PH_CONV);
         k_vn_conv<<<e->n_sm, VN_THREADS, VN_SMEM_BYTES, e->stream>>>(e->W, req, n_req, keys, M, e->d_act3);
@@ -322,14 +339,17 @@ extern "C" int b200_load_dist_weights(b200_engine *e, const float *w, int atoms)
     CK(cudaFuncSetAttribute(k_dn_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_CONV_SMEM));
     CK(cudaFuncSetAttribute(k_dn_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_FC_SMEM));
     e->have_dist_weights = true;
+    drop_step_graph(e);
     return B200_OK;
 }
 
 static int launch_distnet_on(b200_engine *e, const uint2 *req, const int32_t *n_req, const uint32_t *keys, int M, float *out, size_t max_rows) {
     if (!e->have_dist_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_dist_weights was not called");
     if (e->dn_rows < max_rows) {
+        const bool had = e->d_dn_act != nullptr;
         if (dalloc(e, &e->d_dn_act, max_rows * 2048, false)) return B200_ERR_CUDA;
         e->dn_rows = max_rows;
+        if (had) drop_step_graph(e);
     }
     {
         PhaseTimer t(e, PH_CONV);
@@ -416,47 +436,82 @@ extern "C" int b200_get_games(b200_engine *e, uint32_t *recs) {
 }
 
 // ---------------------------------------------------------------------------------------------------- simulations
+// One simulation step of every game: select+expand -> (collect garbage, resume) -> evaluate -> backup.
+static int enqueue_step(b200_engine *e) {
+    const Arena &A = e->A;
+    const int G = A.G;
+    CK(cudaMemsetAsync(A.n_req, 0, 2 * sizeof(int32_t), e->stream));
+    {
+        PhaseTimer t(e, PH_SELECT);
+        Arena Ap = A;
+        Ap.prof = e->timing ? A.counters + 32 : nullptr;
+        k_select_expand<<<blocks_groups(G), TPB, 0, e->stream>>>(Ap);
+    }
+    {   // remove_nodes for the games that ran out of free slots in this step, then the rest of their expansion
+        PhaseTimer t(e, PH_GC);
+        k_gc<<<gc_blocks(e), GC_THREADS, 0, e->stream>>>(A);
+        k_expand_resume<<<blocks_groups(G), TPB, 0, e->stream>>>(A);
+    }
+    if (A.mode == MODE_VANILLA) {
+        PhaseTimer t(e, PH_ROLLOUT);
+        k_rollout<<<(G + 63) / 64, 64, 0, e->stream>>>(A);
+    } else if (A.mode == MODE_DIST) {
+        if (e->cfg.eval_kind == B200_EVAL_SYNTHETIC) {
+            PhaseTimer t(e, PH_SYNTH);
+            k_eval_synthetic_dist<<<(G + 127) / 128, 128, 0, e->stream>>>(A);
+        } else {
+            int rc = launch_distnet(e);
+            if (rc) return rc;
+        }
+    } else if (e->cfg.eval_kind == B200_EVAL_SYNTHETIC) {
+        PhaseTimer t(e, PH_SYNTH);
+        k_eval_synthetic<<<(G * 7 + 255) / 256 < 1184 ? (G * 7 + 255) / 256 : 1184, 256, 0, e->stream>>>(A);
+    } else {
+        int rc = launch_net(e, A.req, A.n_req, A.key, A.M, A.eval_out, (size_t)G * (A.mode == MODE_LP ? 7 : 1));
+        if (rc) return rc;
+    }
+    {
+        PhaseTimer t(e, PH_BACKUP);
+        if (A.mode == MODE_DIST) k_dist_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
+        else k_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
+    }
+    return B200_OK;
+}
+
+// Capture one step (same launches, same arguments every step: all sizes are read on the device) and replay it.  The first
+// step of an engine runs directly so that lazily allocated buffers (activations) exist before the capture.
+static void capture_step(b200_engine *e) {
+    uint64_t before[PH_N];
+    for (int i = 0; i < PH_N; ++i) before[i] = e->phase_launches[i];
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); e->step_graph_failed = true; return; }
+    int rc = enqueue_step(e);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    for (int i = 0; i < PH_N; ++i) { e->step_launches[i] = e->phase_launches[i] - before[i]; e->phase_launches[i] = before[i]; }
+    if (rc == B200_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&e->step_exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    e->step_exec = nullptr; e->step_graph_failed = true;    // direct launches from now on
+}
+
 extern "C" int b200_run_sims(b200_engine *e, int sims) {
     if (!e || sims < 0) return fail(B200_ERR_BAD_ARG, "bad argument");
     CK(cudaSetDevice(e->cfg.device));
     const Arena &A = e->A;
-    const int G = A.G;
     const bool need_net = A.mode != MODE_VANILLA && e->cfg.eval_kind != B200_EVAL_SYNTHETIC;
     if (need_net && !(A.mode == MODE_DIST ? e->have_dist_weights : e->have_weights)) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
     for (int s = 0; s < sims; ++s) {
-        CK(cudaMemsetAsync(A.n_req, 0, 2 * sizeof(int32_t), e->stream));
-        {
-            PhaseTimer t(e, PH_SELECT);
-            k_select_expand<<<blocks_groups(G), TPB, 0, e->stream>>>(A);
+        if (!e->timing && e->step_exec) {
+            CK(cudaGraphLaunch(e->step_exec, e->stream));
+            for (int i = 0; i < PH_N; ++i) e->phase_launches[i] += e->step_launches[i];
+            continue;
         }
-        {   // remove_nodes for the games that ran out of free slots in this step, then the rest of their expansion
-            PhaseTimer t(e, PH_GC);
-            k_gc<<<gc_blocks(e), GC_THREADS, 0, e->stream>>>(A);
-            k_expand_resume<<<blocks_groups(G), TPB, 0, e->stream>>>(A);
-        }
-        if (A.mode == MODE_VANILLA) {
-            PhaseTimer t(e, PH_ROLLOUT);
-            k_rollout<<<(G + 63) / 64, 64, 0, e->stream>>>(A);
-        } else if (A.mode == MODE_DIST) {
-            if (e->cfg.eval_kind == B200_EVAL_SYNTHETIC) {
-                PhaseTimer t(e, PH_SYNTH);
-                k_eval_synthetic_dist<<<(G + 127) / 128, 128, 0, e->stream>>>(A);
-            } else {
-                int rc = launch_distnet(e);
-                if (rc) return rc;
-            }
-        } else if (e->cfg.eval_kind == B200_EVAL_SYNTHETIC) {
-            PhaseTimer t(e, PH_SYNTH);
-            k_eval_synthetic<<<(G * 7 + 255) / 256 < 1184 ? (G * 7 + 255) / 256 : 1184, 256, 0, e->stream>>>(A);
-        } else {
-            int rc = launch_net(e, A.req, A.n_req, A.key, A.M, A.eval_out, (size_t)G * (A.mode == MODE_LP ? 7 : 1));
-            if (rc) return rc;
-        }
-        {
-            PhaseTimer t(e, PH_BACKUP);
-            if (A.mode == MODE_DIST) k_dist_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
-            else k_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
-        }
+        int rc = enqueue_step(e);
+        if (rc) return rc;
+        if (!e->timing && !e->step_exec && !e->step_graph_failed) capture_step(e);
     }
     CK(cudaGetLastError());
     return B200_OK;
@@ -521,6 +576,14 @@ extern "C" int b200_debug_prof(b200_engine *e, uint64_t *out16) {   // clock64 p
     if (!e || !out16) return fail(B200_ERR_BAD_ARG, "null argument");
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaMemcpyAsync(out16, e->A.counters + 16, 16 * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_debug_prof_tree(b200_engine *e, uint64_t *out8) {   // clock64 sums of sampled groups of k_select_expand (timing mode)
+    if (!e || !out8) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(out8, e->A.counters + 32, 8 * 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return B200_OK;
 }
@@ -957,6 +1020,7 @@ extern "C" int b200_replay_enable(b200_engine *e, int min_visits, int capacity) 
     if (e->A.replay) return fail(B200_ERR_BAD_ARG, "replay memory already enabled");
     if (dalloc(e, &e->A.replay, (size_t)capacity * 212) || dalloc(e, &e->A.replay_count, 1)) return B200_ERR_CUDA;
     e->A.replay_cap = capacity; e->A.replay_min_visits = min_visits;
+    drop_step_graph(e);
     CK(cudaStreamSynchronize(e->stream));
     return B200_OK;
 }

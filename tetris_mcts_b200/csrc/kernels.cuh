@@ -160,43 +160,97 @@ __device__ __forceinline__ Uniq finish_expansion(const Arena &A, const Grp &gp, 
 }
 
 // ---------------------------------------------------------------- select + expand (ValueSimLP.py:45-57 etc.)
-__global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
-    __shared__ float s_z[ZS_N];
-    __shared__ __align__(16) uint32_t s_stage[GROUPS_PER_BLOCK * STAGE_GROUP_WORDS];
-    for (int i = threadIdx.x; i < ZS_N; i += TPB) s_z[i] = A.ztable[i];
-    __syncthreads();
-    Grp gp;
-    int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
-    if (g >= A.G) return;
+// What one group hands to the CTA-level epilogue of k_select_expand: its evaluation request (per lane) and its counters.
+struct GroupOut { bool ask; int my_o; int sims, D, expanded, new_nodes; };
+
+__device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &gp, int g, const float *s_z, uint32_t *stage, GroupOut &out) {
     int status = A.status[g];
     if (status == ST_ARENA_FULL && A.overflow_reset) reset_tree(A, gp, g, status);
     if (status != ST_OK) return;
     ArenaAcc acc(A, g, s_z);
     int D = 0;
+    const bool do_prof = A.prof && (g & 63) == 0 && gp.lane == 0;
+    long long ptick = do_prof ? clock64() : 0;
+#define TREE_PROF(i) do { if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[i], (unsigned long long)(_n - ptick)); ptick = _n; } } while (0)
     int leaf = A.mode == MODE_DIST ? dist_select_group(A, gp, g, A.root[g], D, status)
                                    : select_trace(acc, gp, A.root[g], A.low, A.trace_max, D, status);
     if (status != ST_OK) { if (gp.lane == 0) A.status[g] = status; return; }
+    TREE_PROF(0);
     uint32_t w[REC_WORDS];
     load_rec(A.rec + node_at(A, g, leaf) * REC_WORDS, w);
     bool ended = (w[10] >> 21) & 1u;
     int kind = ended ? LEAF_TERMINAL : LEAF_EXPANDED;
+    if (do_prof) ptick += (long long)(w[10] & 0u);   // the leaf record has landed
+    TREE_PROF(1);
     if (!ended) {
-        if (A.mode == MODE_SINGLE || A.mode == MODE_DIST)   // ValueSim.py:83-88 / DistValueSimOnline.py:66-70: the leaf itself is evaluated
-            emit_requests(A, gp, g, 1u << 7, A.row[node_at(A, g, leaf) * ROW_WORDS + 15]);
+        if (A.mode == MODE_SINGLE || A.mode == MODE_DIST) {   // ValueSim.py:83-88 / DistValueSimOnline.py:66-70: the leaf itself is evaluated
+            out.my_o = A.row[node_at(A, g, leaf) * ROW_WORDS + 15];
+            out.ask = gp.lane == 7;
+        }
         int c, o, a_stop; float s;
-        expand_leaf(A, gp, g, leaf, w, c, o, s, status, 0, true, a_stop, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS);
+        expand_leaf(A, gp, g, leaf, w, c, o, s, status, 0, true, a_stop, stage, &out.new_nodes);
         if (status == ST_NEED_GC) {
             suspend_for_gc(A, gp, g, PEND_EXPAND, a_stop);
             kind = LEAF_SUSPENDED; status = ST_OK;
         } else if (status == ST_OK) {
+            TREE_PROF(2);
+            out.expanded = 1;
             Uniq u = finish_expansion(A, gp, g, leaf, c, o, s);
-            if (A.mode == MODE_LP) request_lp_evals(A, gp, g, u, o);
+            if (A.mode == MODE_LP) {                          // request_lp_evals, queued by the CTA epilogue
+                out.ask = u.is_first && A.stat[node_at(A, g, o)].x == 0;
+                out.my_o = o;
+            }
         }
     }
     if (gp.lane == 0) {
         A.trace_len[g] = D; A.leaf_kind[g] = kind;
         if (status != ST_OK) A.status[g] = status;
-        atomicAdd(&A.counters[0], 1ull); atomicAdd(&A.counters[4], (unsigned long long)D);
+    }
+    out.sims = 1; out.D = D;
+    TREE_PROF(3);
+    if (do_prof) atomicAdd(&A.prof[4], 1ull);
+#undef TREE_PROF
+}
+
+// One launch = one simulation step of every game.  The per-group part is latency bound (pointer chase), so everything that
+// would serialise the groups on one address is aggregated per CTA at the end: ONE atomicAdd on the request counter and one per
+// statistics counter per CTA (before: ~10 same-address atomics per game per launch, 160 k per launch on two cache lines).
+__global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
+    __shared__ float s_z[ZS_N];
+    __shared__ __align__(16) uint32_t s_stage[GROUPS_PER_BLOCK * STAGE_GROUP_WORDS];
+    __shared__ unsigned s_cnt[4];          // sims, trace levels, expansions, new nodes of this CTA
+    __shared__ int s_wreq[TPB / 32 + 1];   // requests per warp, then the CTA's base in the request list
+    for (int i = threadIdx.x; i < ZS_N; i += TPB) s_z[i] = A.ztable[i];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    Grp gp;
+    const int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
+    GroupOut out{false, 0, 0, 0, 0, 0};
+    if (g < A.G) select_expand_group(A, gp, g, s_z, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS, out);
+    __syncwarp();
+    const unsigned askmask = __ballot_sync(0xffffffffu, out.ask);
+    if ((threadIdx.x & 31) == 0) s_wreq[threadIdx.x >> 5] = __popc(askmask);
+    if (gp.lane == 0 && out.sims) {
+        atomicAdd(&s_cnt[0], 1u); atomicAdd(&s_cnt[1], (unsigned)out.D);
+        if (out.expanded) atomicAdd(&s_cnt[2], 1u);
+        if (out.new_nodes) atomicAdd(&s_cnt[3], (unsigned)out.new_nodes);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < TPB / 32; ++i) tot += s_wreq[i];
+        s_wreq[TPB / 32] = tot ? atomicAdd(A.n_req, tot) : 0;
+        if (tot) atomicAdd(&A.counters[2], (unsigned long long)tot);
+        if (s_cnt[0]) { atomicAdd(&A.counters[0], (unsigned long long)s_cnt[0]); atomicAdd(&A.counters[4], (unsigned long long)s_cnt[1]); }
+        if (s_cnt[2]) atomicAdd(&A.counters[1], (unsigned long long)s_cnt[2]);
+        if (s_cnt[3]) atomicAdd(&A.counters[6], (unsigned long long)s_cnt[3]);
+    }
+    __syncthreads();
+    if (out.ask) {
+        int pos = s_wreq[TPB / 32] + __popc(askmask & ((1u << (threadIdx.x & 31)) - 1u));
+        for (int i = 0; i < (int)(threadIdx.x >> 5); ++i) pos += s_wreq[i];
+        A.req[pos] = make_uint2((uint32_t)g, (uint32_t)out.my_o | ((uint32_t)gp.lane << 28));
     }
 }
 
@@ -216,7 +270,7 @@ __global__ void __launch_bounds__(TPB) k_expand_resume(Arena A) {
     uint32_t w[REC_WORDS];
     load_rec(A.rec + node_at(A, g, leaf) * REC_WORDS, w);
     int c, o, a_stop; float s;
-    expand_leaf(A, gp, g, leaf, w, c, o, s, status, A.resume_a[g], false, a_stop, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS);
+    expand_leaf(A, gp, g, leaf, w, c, o, s, status, A.resume_a[g], false, a_stop, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS, nullptr);
     if (status == ST_OK) {
         ArenaAcc acc(A, g);
         acc.children(leaf, gp.lane, c, o, s);            // children 0..resume_a-1 were linked before the collection
@@ -446,11 +500,16 @@ __global__ void k_rollout(Arena A) {
 
 // ---------------------------------------------------------------- backup (core.h:226-381), one warp per game
 // The reference walks the trace leaf -> root with two dependent gathers per level.  Here the 32 lanes of a warp fetch
-// 32 levels at once (node meta, then statistics: three memory latencies per 32 levels instead of per level), the
-// Welford recurrence then runs lane to lane in registers in exactly the reference's order (same welford_level code,
-// v carried in double), and the statistics are written back in parallel.  If an observation occurs twice among the
-// levels in flight (statistics are shared between nodes, agent.py:116-128) the warp falls back to the scalar walk.
-__global__ void __launch_bounds__(128) k_backup(Arena A) {
+// 32 levels at once (node meta, then statistics), the Welford recurrence then runs in exactly the reference's order
+// (same welford_level code, v carried in double), and the statistics are written back in parallel.  If an observation
+// occurs twice among the levels in flight (statistics are shared between nodes, agent.py:116-128) the warp falls back
+// to the scalar walk.  Everything the backup never writes (trace, row fields, evaluator outputs) is loaded as early as
+// possible: the first window's node fields together with the leaf's child row, the next window's while the current one
+// is folded, so that only the statistics loads sit on the dependent chain (a DRAM access is ~2.4 k clk here).
+#ifndef B200_BACKUP_MINB
+#define B200_BACKUP_MINB 9      // resident 128-thread blocks per SM the register budget is cut for (9 = what 56 registers give)
+#endif
+__global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
     const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (g >= A.G || A.status[g] != ST_OK) return;
@@ -458,16 +517,23 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
     const int D = A.trace_len[g];
     const int kind = A.leaf_kind[g];
     if (kind == LEAF_SUSPENDED || D <= 0) return;
-    const int leaf = acc.get_trace(D - 1);
-    int lo; float leaf_score;
-    acc.meta(leaf, lo, leaf_score);
+    // ---- early loads: trace entries of the first window, then their node fields + the leaf's child row + evaluator outputs
+    const int n0 = D < 32 ? D : 32;
+    int tidx = 0;
+    if (lane < n0) tidx = acc.get_trace(D - 1 - lane);
+    const int leaf = __shfl_sync(0xffffffffu, tidx, 0);
+    const bool lp_children = A.mode == MODE_LP && kind == LEAF_EXPANDED;
+    int wo = -1 - lane; float wsc = 0.f;                      // this lane's level of the current window: observation, score
+    if (lane < n0) acc.meta(tidx, D - 1 - lane, wo, wsc);
+    int c = 0, o = 0; float s = 0.f;
+    float2 ev = make_float2(0.f, 0.f);
+    if (lp_children && lane < 8) { acc.children(leaf, lane, c, o, s); ev = A.eval_out[(size_t)g * 8 + lane]; }
+    const float leaf_score = __shfl_sync(0xffffffffu, wsc, 0);
     double v = (double)leaf_score, var = 0.0;
     if (A.mode == MODE_LP) {
         if (kind == LEAF_EXPANDED) {
             // core.h:340-366: initialise unvisited unique children, then average score + gamma*value and the variances
             Grp gp;                                   // lanes 0-7 of the warp form the group that holds the 7 child slots
-            int c = 0, o = 0; float s = 0.f;
-            if (lane < 8) acc.children(leaf, lane, c, o, s);
             double v_tmp = 0.0, var_tmp = 0.0;
             int k = 0;
             if (lane < 8) {
@@ -476,9 +542,8 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
                 if (u.is_first) {
                     st = acc.stat(o);
                     if (st.x == 0) {                                           // core.h:344-353
-                        float2 e = A.eval_out[(size_t)g * 8 + lane];
                         bool cend = A.lp_end_from_obs ? (st.w != 0) : false;
-                        st.x = 1; st.y = __float_as_int(cend ? 0.f : e.x); st.z = __float_as_int(cend ? 0.f : e.y);
+                        st.x = 1; st.y = __float_as_int(cend ? 0.f : ev.x); st.z = __float_as_int(cend ? 0.f : ev.y);
                         acc.set_stat(o, st);
                     }
                 }
@@ -512,10 +577,17 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
     // ---- core.h:244-259 along the trace, 32 levels per round
     for (int top = D - 1; top >= 0; top -= 32) {
         const int n = top + 1 < 32 ? top + 1 : 32;      // levels top, top-1, ..., top-n+1 -> lanes 0..n-1
-        int o = -1 - lane; float sc = 0.f; int4 st = make_int4(0, 0, 0, 0);
-        if (lane < n) { acc.meta(acc.get_trace(top - lane), o, sc); }
-        bool dup = __popc(__match_any_sync(0xffffffffu, o)) > 1;
-        if (__any_sync(0xffffffffu, dup)) {             // shared observation inside the window: scalar walk for this window
+        const int o = wo; const float sc = wsc;
+        int4 st = make_int4(0, 0, 0, 0);
+        const bool dup = __popc(__match_any_sync(0xffffffffu, o)) > 1;
+        const bool any_dup = __any_sync(0xffffffffu, dup);
+        if (!any_dup && lane < n) st = acc.stat(o, top - lane);
+        {   // the next window's node fields, in flight while this window is folded
+            const int ntop = top - 32;
+            wo = -1 - lane; wsc = 0.f;
+            if (ntop >= 0 && lane <= ntop) acc.meta(acc.get_trace(ntop - lane), ntop - lane, wo, wsc);
+        }
+        if (any_dup) {                                  // shared observation inside the window: scalar walk for this window
             if (lane == 0) {
                 for (int i = top; i > top - n; --i) {
                     int oo; float ss;
@@ -529,7 +601,6 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
             __syncwarp();
             continue;
         }
-        if (lane < n) st = acc.stat(o);
         // The value chain v <- gamma*(v - score) + score (core.h:244,259) does not depend on the statistics: every lane
         // walks it (three dependent double operations per level) and keeps the value entering its own level; the expensive
         // Welford updates (core.h:245-258) of the whole window then run in parallel, one level per lane.
@@ -539,7 +610,7 @@ __global__ void __launch_bounds__(128) k_backup(Arena A) {
             if (lane == j) vin = v;
             v = __dadd_rn(__dmul_rn(A.gamma, __dsub_rn(v, scj)), scj);
         }
-        if (lane < n) { welford_level(st, vin, var, sc, A.gamma); acc.set_stat(o, st); }
+        if (lane < n) { welford_level(st, vin, var, sc, A.gamma); acc.set_stat(o, st, top - lane); }
         __syncwarp();
     }
 }

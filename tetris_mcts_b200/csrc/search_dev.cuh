@@ -63,6 +63,7 @@ struct Arena {
     // distributional mode (agents/core_distributional.py; BASELINE config 5): node-indexed statistics and value histograms
     float *nstat; float *ndist; float *dist_eval; int dist_bins; double dist_vmin, dist_vmax;   // [G][M][8], [G][M][bins], [G][bins]
     unsigned long long *counters;  // [8] 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels 5 rollout steps 6 new nodes
+    unsigned long long *prof;      // timing mode only: clock64 sums of k_select_expand {select, leaf load, expand, finish, groups sampled}
 };
 
 // ------------------------------------------------------------------ group helpers
@@ -151,6 +152,56 @@ __device__ __forceinline__ uint32_t link_word(const Uniq &u) {
     return ((uint32_t)u.rep_c & LINK_NODE_MASK) | ((uint32_t)u.rep_lane << 28) | (u.is_first ? 0x80000000u : 0u);
 }
 
+// ------------------------------------------------------------------ cache-warming loads (see warm_expand)
+#ifndef B200_WARM_EXPAND
+#define B200_WARM_EXPAND 1
+#endif
+#ifndef B200_WARM_SELECT
+#define B200_WARM_SELECT 0
+#endif
+// L2 residency hints (performance only).  One simulation step streams ~200 MB of activations (conv -> fc) and ~20 MB of new
+// nodes through the 126 MB L2, so without hints nothing of the trees survives from one step to the next although every step
+// re-walks the same top levels.  The first B200_L2_HOT_LEVELS levels of every game's walk (row line + statistics, ~3.7 MB per
+// level at 16384 games) are loaded / stored with an evict_last policy, the activation stream with evict_first.
+#ifndef B200_L2_HOT_LEVELS
+#define B200_L2_HOT_LEVELS 16
+#endif
+__device__ __forceinline__ uint64_t l2_policy(bool keep) {
+    uint64_t last, normal;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(last));
+    asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(normal));
+    return keep ? last : normal;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int32_t ldg_hint(const int32_t *p, uint64_t pol) {
+    int32_t v;
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 ldg_hint(const int4 *p, uint64_t pol) {
+    int4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg_hint(int4 *p, int4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ uint32_t touch32(const void *p) {
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 touch64(const void *p) {
+    uint2 v;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 // ------------------------------------------------------------------ accessors
 // The engine keeps the packed arena above; the single-call twins of agents/cppmodule/core.cpp:20-26 work on the
 // reference's own array layout (agents/agent.py:58-88).  Both run the same select / backup code through these.
@@ -171,18 +222,55 @@ struct ArenaAcc {
         o = row[15]; s = __int_as_float(row[23]);
     }
     // one level of select: observation of this lane's child, the node's own score, the cached de-duplication
-    __device__ __forceinline__ void level(const Grp &gp, int idx, int &o, float &s_idx, Uniq &u) const {
+    __device__ __forceinline__ void level(const Grp &gp, int idx, int depth, int &o, float &s_idx, Uniq &u) const {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS + gp.lane;
+#if B200_L2_HOT_LEVELS > 0
+        const uint64_t pol = l2_policy(depth < B200_L2_HOT_LEVELS);
+        o = ldg_hint(row + 8, pol);
+        const float s = __int_as_float(ldg_hint(row + 16, pol));
+        const uint32_t lw = (uint32_t)ldg_hint(row + 24, pol);
+#else
         o = row[8];
         const float s = __int_as_float(row[16]);
         const uint32_t lw = (uint32_t)row[24];
+#endif
         s_idx = gp.bcast(s, 7);
         u.is_first = lw >> 31; u.rep_lane = (int)((lw >> 28) & 7u); u.rep_c = (int)(lw & LINK_NODE_MASK);
         u.rep_s = gp.bcast(s, u.rep_lane);
         u.first_mask = gp.ballot(u.is_first);
+#if B200_WARM_SELECT
+        if (u.is_first) {   // start fetching every candidate child's row while the statistics are loaded and compared
+            const int32_t *cr = rowg + (size_t)u.rep_c * ROW_WORDS;
+            touch32(cr + 8); touch32(cr + 16); touch32(cr + 24);
+        }
+#endif
     }
     __device__ __forceinline__ int4 stat(int o) const { return statg[o]; }
     __device__ __forceinline__ void set_stat(int o, int4 st) const { statg[o] = st; }
+    // the same, for a node at `depth` of the current walk (see B200_L2_HOT_LEVELS)
+    __device__ __forceinline__ int4 stat(int o, int depth) const {
+#if B200_L2_HOT_LEVELS > 0
+        return ldg_hint(statg + o, l2_policy(depth < B200_L2_HOT_LEVELS));
+#else
+        return statg[o];
+#endif
+    }
+    __device__ __forceinline__ void set_stat(int o, int4 st, int depth) const {
+#if B200_L2_HOT_LEVELS > 0
+        stg_hint(statg + o, st, l2_policy(depth < B200_L2_HOT_LEVELS));
+#else
+        statg[o] = st;
+#endif
+    }
+    __device__ __forceinline__ void meta(int idx, int depth, int &o, float &s) const {
+        const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
+#if B200_L2_HOT_LEVELS > 0
+        const uint64_t pol = l2_policy(depth < B200_L2_HOT_LEVELS);
+        o = ldg_hint(row + 15, pol); s = __int_as_float(ldg_hint(row + 23, pol));
+#else
+        o = row[15]; s = __int_as_float(row[23]);
+#endif
+    }
     __device__ __forceinline__ void put_trace(int d, int idx) const { traceg[d] = idx; }
     __device__ __forceinline__ int get_trace(int d) const { return traceg[d]; }
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
@@ -197,13 +285,13 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
         else { c = 0; o = n2o[idx]; s = score[idx]; }
     }
     __device__ __forceinline__ void meta(int idx, int &o, float &s) const { o = n2o[idx]; s = score[idx]; }
-    __device__ __forceinline__ void level(const Grp &gp, int idx, int &o, float &s_idx, Uniq &u) const {
+    __device__ __forceinline__ void level(const Grp &gp, int idx, int, int &o, float &s_idx, Uniq &u) const {
         int c; float s;
         children(idx, gp.lane, c, o, s);
         s_idx = gp.bcast(s, 7);
         u = unique_children(gp, c, o, s);
     }
-    __device__ __forceinline__ int4 stat(int o) const { return make_int4(visit[o], __float_as_int(value[o]), __float_as_int(variance[o]), 0); }
+    __device__ __forceinline__ int4 stat(int o, int = 0) const { return make_int4(visit[o], __float_as_int(value[o]), __float_as_int(variance[o]), 0); }
     __device__ __forceinline__ void set_stat(int o, int4 st) const { visit[o] = st.x; value[o] = __int_as_float(st.y); variance[o] = __int_as_float(st.z); }
     __device__ __forceinline__ void put_trace(int d, int idx) const { trace[d] = idx; }
     __device__ __forceinline__ int get_trace(int d) const { return trace[d]; }
@@ -222,10 +310,10 @@ __device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int r
         ++D;
         int o; float s_idx;
         Uniq u;
-        acc.level(gp, idx, o, s_idx, u);
+        acc.level(gp, idx, D - 1, o, s_idx, u);
         if (u.first_mask == 0) break;                                   // core.h:200 no children: leaf
         int4 st = make_int4(0, 0, 0, 0);
-        if (u.is_first) st = acc.stat(o);
+        if (u.is_first) st = acc.stat(o, D);                            // the children live one level below
         unsigned lowmask = gp.ballot(u.is_first && st.x < low);          // core.h:65-77
         int pick;
         if (lowmask) {
@@ -326,8 +414,9 @@ __device__ __forceinline__ void digest_game(const uint32_t (&w)[REC_WORDS], Dige
     d.score = (float)gm.score;                                              // agent.py:106 score[idx] = game.score
 }
 
+// n_new: where to count a created node (group-uniform register, flushed by the caller); nullptr = count in A.counters[6] here.
 __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, const uint32_t (&w)[REC_WORDS], const Digest &dg, int &o_out,
-                                        float &score_out, int &status, bool may_suspend) {
+                                        float &score_out, int &status, bool may_suspend, int *n_new = nullptr) {
     const int M = A.M, H = A.H;
     uint2 *ntab = A.ntab + (size_t)g * H;
     const uint32_t h = dg.h;
@@ -384,8 +473,9 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
         int32_t *r = rowb + (size_t)idx * ROW_WORDS;
         r[7] = A.episode[g]; r[15] = o; r[23] = __float_as_int(sc);
     }
+    if (n_new) *n_new += 1;
     if (gp.lane == 0) {
-        atomicAdd(&A.counters[6], 1ull);
+        if (!n_new) atomicAdd(&A.counters[6], 1ull);
         if (A.nstat) A.nstat[node_at(A, g, idx) * NSTAT_WORDS + 2] = sc;   // node_stats[idx][2] = reward (core_distributional.py:86,112)
     }
     gp.sync();
@@ -442,12 +532,43 @@ __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, in
 // Shared-memory staging of the seven children of one expansion: lane a plays action a, digests the resulting game and parks
 // record | observation key | hashes in its slot; the insertion loop then reads child a with broadcast loads.  (Holding the
 // 36 words per lane in registers across the loop and moving them with 36 shuffles per child spilled at 64 registers.)
+// Cache warming (performance hint only; results discarded, so exactness is untouched).  One expansion is seven new_node calls in
+// the reference's order, each a chain of dependent probes (node table -> record compare -> free list -> observation table ->
+// key compare ...); at 16384 games the arenas span ~80 GB, every first touch is a DRAM access (~2.4 k clk measured) and the chain
+// was ~50 of them per expansion.  Before the ordered loop, lane a touches everything child a's new_node will read first: its two
+// table slots, then (on a hash match) the candidate record / row / key; lane 7 touches the counters and the free-list tails.  The
+// ordered loop then runs on L1/L2 hits.  Real loads (volatile asm) are used: a prefetch instruction may be dropped.
+__device__ __forceinline__ void warm_expand(const Arena &A, const Grp &gp, int g, uint32_t h, uint32_t hk) {
+#if B200_WARM_EXPAND
+    const int M = A.M, H = A.H;
+    if (gp.lane < 7) {
+        const uint2 e1 = touch64(A.ntab + (size_t)g * H + (h & (uint32_t)(H - 1)));
+        const uint2 e2 = touch64(A.otab + (size_t)g * H + (hk & (uint32_t)(H - 1)));
+        if (e1.y != 0u && e1.y != 0xffffffffu && e1.x == h) {       // probable transposition: its record (80 B) and its row's own fields
+            const uint32_t *r = A.rec + ((size_t)g * M + e1.y) * REC_WORDS;
+            touch32(r); touch32(r + REC_WORDS - 1);
+            touch32(A.row + ((size_t)g * M + e1.y) * ROW_WORDS + 15);
+        }
+        if (e2.y != 0u && e2.y != 0xffffffffu && e2.x == hk) {      // probable known observation: its key (48 B)
+            const uint32_t *k = A.key + ((size_t)g * M + e2.y) * KEY_WORDS;
+            touch32(k); touch32(k + KEY_WORDS - 1);
+        }
+    } else {
+        const int nf = (int)touch32(A.n_nfree + g), nof = (int)touch32(A.n_ofree + g);
+        touch32(A.episode + g);
+        if (nf > 0) { touch32(A.nfree + (size_t)g * M + nf - 1); if (nf > 7) touch32(A.nfree + (size_t)g * M + nf - 7); }
+        if (nof > 0) { touch32(A.ofree + (size_t)g * M + nof - 1); if (nof > 7) touch32(A.ofree + (size_t)g * M + nof - 7); }
+    }
+#endif
+}
+
 constexpr int STAGE_WORDS = 36;                      // rec[20] | key[12] | h, hk, end, score
 constexpr int STAGE_GROUP_WORDS = 7 * STAGE_WORDS;   // per game in flight
 
 __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g, int leaf, const uint32_t (&leafrec)[REC_WORDS],
                                             int &c, int &o, float &s, int &status, int a_begin, bool may_suspend, int &a_stop,
-                                            uint32_t *stage) {
+                                            uint32_t *stage, int *n_new) {
+    uint32_t wh = 0, whk = 0;
     if (gp.lane < 7) {
         uint32_t mine[REC_WORDS];
         Digest dm;
@@ -462,7 +583,9 @@ __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g
 #pragma unroll
         for (int q = 0; q < KEY_WORDS / 4; ++q) dst[5 + q] = make_uint4(dm.key[4 * q], dm.key[4 * q + 1], dm.key[4 * q + 2], dm.key[4 * q + 3]);
         dst[8] = make_uint4(dm.h, dm.hk, (uint32_t)dm.end, __float_as_uint(dm.score));
+        wh = dm.h; whk = dm.hk;
     }
+    warm_expand(A, gp, g, wh, whk);
     gp.sync();
     c = 0; o = 0; s = 0.f;
     a_stop = N_ACTIONS;
@@ -476,7 +599,7 @@ __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g
         for (int q = 0; q < KEY_WORDS / 4; ++q) { const uint4 v = src[5 + q]; dg.key[4 * q] = v.x; dg.key[4 * q + 1] = v.y; dg.key[4 * q + 2] = v.z; dg.key[4 * q + 3] = v.w; }
         { const uint4 v = src[8]; dg.h = v.x; dg.hk = v.y; dg.end = (int)v.z; dg.score = __uint_as_float(v.w); }
         int oo; float ss;
-        int idx = new_node(A, gp, g, w, dg, oo, ss, status, may_suspend);
+        int idx = new_node(A, gp, g, w, dg, oo, ss, status, may_suspend, n_new);
         if (status == ST_NEED_GC) { a_stop = a; break; }     // resume at this child after k_gc
         if (gp.lane == a) { c = idx; o = oo; s = ss; }
         // agent.py:145 writes child[i] as soon as new_node returns, so a collection triggered by a later
@@ -488,7 +611,7 @@ __device__ __forceinline__ void expand_leaf(const Arena &A, const Grp &gp, int g
         gp.sync();
         if (status != ST_OK) break;
     }
-    if (gp.lane == 0 && status == ST_OK) atomicAdd(&A.counters[1], 1ull);
+    if (!n_new && gp.lane == 0 && status == ST_OK) atomicAdd(&A.counters[1], 1ull);   // with n_new the caller counts the expansion too
 }
 
 // ------------------------------------------------------------------ backup (core.h:226-260), one thread

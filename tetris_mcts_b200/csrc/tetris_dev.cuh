@@ -83,6 +83,38 @@ __device__ __forceinline__ bool collides(const uint32_t (&w)[10], uint32_t shape
     return hit;
 }
 
+// SPEC §3.2 hard drop: how many rows the piece at the LEGAL position (px, py) falls.  Closed form of the reference-style loop
+// `while (!collides(px, py + 1)) ++py` (one dependent collision test of ~80 instructions per row fallen; the hard-drop lane made
+// every expansion wait): for each of the four shape rows r, bit y of hit[r] says that board row y has a locked cell under that
+// shape row's cells; the first set bit below row py + r (or the floor) bounds the fall of that row, the piece falls the minimum.
+// The board rows are walked with static indices only (no dynamic row select), four independent chains.
+__device__ __forceinline__ int drop_distance(const uint32_t (&w)[10], uint32_t shape, int px, int py) {
+    uint32_t mm[4], hit[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t m = (shape >> (4 * r)) & 0xfu;
+        mm[r] = px < 0 ? (m >> (-px)) : (m << px);     // legal position: no cell is shifted off the board
+        hit[r] = 0u;
+    }
+#pragma unroll
+    for (int y = 0; y < 20; ++y) {
+        const uint32_t row = (y & 1) ? (w[y >> 1] >> 16) : (w[y >> 1] & 0xffffu);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) hit[r] |= (row & mm[r]) ? (1u << y) : 0u;
+    }
+    int d = 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (mm[r]) {
+            const int br = py + r;                                   // >= 0 for a non-empty shape row at a legal position
+            const uint32_t below = hit[r] >> (br + 1);               // rows br+1 .. 19
+            const int free_rows = below ? (__ffs((int)below) - 1) : (19 - br);
+            d = free_rows < d ? free_rows : d;
+        }
+    }
+    return d;
+}
+
 __device__ __forceinline__ uint32_t rng_next(uint32_t &s) {   // SPEC §4 xorshift32
     s ^= s << 13; s ^= s >> 17; s ^= s << 5;
     return s;
@@ -133,8 +165,8 @@ __device__ __forceinline__ void play(Game &g, int action) {
     if (g.end) return;
     uint32_t shape = shape_of(g.piece, g.rot);
     if (action == 5) {   // hard drop
-        int d = 0;
-        while (!collides(g.w, shape, g.px, g.py + 1)) { g.py += 1; ++d; }
+        const int d = drop_distance(g.w, shape, g.px, g.py);
+        g.py += d;
         if (g.scoring == 0) g.score += 2 * d;
         g.dropcnt = 0;
         lock_piece(g);
@@ -194,16 +226,18 @@ __device__ __forceinline__ void obskey(const Game &g, uint32_t (&k)[KEY_WORDS]) 
     for (int r = 0; r < 4; ++r) {       // row-major scan of the box yields ascending row*10+col
         uint32_t m = (shape >> (4 * r)) & 0xfu;
         int br = g.py + r;
+        if (m) {                        // clear the whole shape row at once (one pass over the board words per row, not per cell)
+            const uint32_t mm = (g.px < 0) ? (m >> (-g.px)) : (m << g.px);
+            const uint32_t bits = (br & 1) ? (mm << 16) : mm;
+            const int wi = br >> 1;
+#pragma unroll
+            for (int q = 0; q < 10; ++q) k[q] &= (wi == q) ? ~bits : 0xffffffffu;
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if ((m >> c) & 1u) {
-                int bc = g.px + c;
-                cells |= (uint32_t)(br * 10 + bc) << (8 * n);
+                cells |= (uint32_t)(br * 10 + g.px + c) << (8 * n);
                 ++n;
-                uint32_t bit = (br & 1) ? (0x10000u << bc) : (1u << bc);
-                int wi = br >> 1;
-#pragma unroll
-                for (int q = 0; q < 10; ++q) k[q] &= (wi == q) ? ~bit : 0xffffffffu;
             }
         }
     }

@@ -59,6 +59,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same with an L2 eviction policy (search_dev.cuh: l2_policy_stream): act3 is written once and read once
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+#ifndef B200_L2_STREAM_ACT3
+#define B200_L2_STREAM_ACT3 1
+#endif
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -452,8 +460,14 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     uint4 c1, c2;
                     split8(o, c1, c2);
                     const int kc = (y * 4 + x) * 4 + cq;
+#if B200_L2_STREAM_ACT3
+                    const uint64_t pol = l2_policy_stream();
+                    stg_hint(reinterpret_cast<int4 *>(act3 + act3_off(0, n_tiles, ridx, kc)), make_int4((int)c1.x, (int)c1.y, (int)c1.z, (int)c1.w), pol);
+                    stg_hint(reinterpret_cast<int4 *>(act3 + act3_off(1, n_tiles, ridx, kc)), make_int4((int)c2.x, (int)c2.y, (int)c2.z, (int)c2.w), pol);
+#else
                     *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
                     *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = c2;
+#endif
                 }
                 tc_fence_before();
                 PROF_T(6);
@@ -550,7 +564,11 @@ k_tc_fc(NetWeights W, TcWeights TW, const uint8_t *act3, int n_tiles_alloc, cons
                     uint8_t *dst = smem + stage * TCF_STAGE;
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
+#if B200_L2_STREAM_ACT3
+                        bulk_g2s_hint(dst + s * TCF_A_BYTES, act3 + (((size_t)s * n_tiles_alloc + tile) * ACT3_KCHUNKS + 2 * j) * 2048, TCF_A_BYTES, &full[stage], l2_policy_stream());
+#else
                         bulk_g2s(dst + s * TCF_A_BYTES, act3 + (((size_t)s * n_tiles_alloc + tile) * ACT3_KCHUNKS + 2 * j) * 2048, TCF_A_BYTES, &full[stage]);
+#endif
                         bulk_g2s(dst + 2 * TCF_A_BYTES + s * TCF_B_BYTES, TW.wfc + ((size_t)s * TCF_KBLOCKS + j) * TCF_B_BYTES, TCF_B_BYTES, &full[stage]);
                     }
                     if (++stage == TCF_STAGES) { stage = 0; ph ^= 1; }
