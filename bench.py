@@ -237,6 +237,7 @@ def run_b200(args, cfg):
     eng = BatchedEngine(G, max_nodes=M, mode=cfg["mode"], eval_kind=cfg["eval"], weights=init_weights(0) if cfg["mode"] in ("lp", "single") else None,
                         dist_weights=dist_w, env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank, device=local_rank, rollout_variance=1e3, overflow_reset=True)
     eng.set_games(recs)
+    eng.set_gc_headroom(cfg["gc_headroom"])
     for _ in range(args.warmup):
         eng.play_move(sims, auto_reset=True, want_stats=False)
     eng.sync()
@@ -372,6 +373,7 @@ def run_b200(args, cfg):
         e2 = BatchedEngine(G2, max_nodes=8192, mode="vanilla", eval_kind="synthetic", env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank,
                            device=local_rank, rollout_variance=1e3, overflow_reset=True)
         e2.set_games(PT.new_games(G2, ENV_ARGS, D.shard_seeds(BASE_SEED, G2 * world, rank, world)))
+        e2.set_gc_headroom(8192 * 5 // 32)
         for _ in range(max(args.warmup, 3)):
             e2.play_move(sims2, auto_reset=True, want_stats=False)
         k0 = e2.counters()
@@ -406,6 +408,7 @@ def main():
     ap.add_argument("--games-per-gpu", type=int, default=None)
     ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--max-nodes", type=int, default=None)
+    ap.add_argument("--gc-headroom", type=int, default=None, help="collect between moves every game with fewer free slots (default 5/32 of max_nodes; 0 = lazy collection only)")
     ap.add_argument("--eval", default=os.environ.get("B200_EVAL", "net_tc"), choices=["net", "net_tc", "synthetic"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -423,11 +426,16 @@ def main():
     else:
         G, sims, M, mode = args.games_per_gpu or 16384, args.sims or 500, args.max_nodes or 16384, "lp"
         name = "BASELINE configs[2]: ValueSimLP + value net, %d games/GPU, %d sims/move" % (G, sims)
-    cfg = dict(games_per_gpu=G, sims=sims, max_nodes=M, mode=mode, eval=args.eval, workload_key=args.workload,
+    headroom = args.gc_headroom if args.gc_headroom is not None else M * 5 // 32
+    cfg = dict(games_per_gpu=G, sims=sims, max_nodes=M, mode=mode, eval=args.eval, workload_key=args.workload, gc_headroom=headroom,
                config={"workload": name, "games_per_gpu": G, "sims_per_move": sims, "max_nodes": M, "evaluator": args.eval if mode != "vanilla" else "rollout",
                        "env_args": "((20,10),1,0,0)", "weights": "default-init distribution, numpy PCG64 seed 0",
-                       "arena_overflow": "reference semantics up to max_nodes per game; a game whose reachable set fills its arena (reference: IndexError) "
-                                         "drops its tree and re-roots (counters_per_step.tree_resets)"})
+                       "garbage_collection": "TreeAgent.remove_nodes() between moves for every game with fewer than %d free slots, batched over the games "
+                                             "(b200_set_gc_headroom; reference equivalent: the driver calling agent.remove_nodes(), agents/agent.py:246-257), "
+                                             "plus the reference's own call inside new_node when a free list runs dry in the middle of a move" % headroom,
+                       "arena_overflow": "reference semantics up to max_nodes per game; a game whose reachable set fills its arena (a collection recovers fewer "
+                                         "than max_nodes/8 slots; the reference then collects at nearly every expansion and dies with IndexError) drops its tree "
+                                         "and re-roots (counters_per_step.tree_resets)"})
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

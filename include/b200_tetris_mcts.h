@@ -75,6 +75,13 @@ int b200_set_games(b200_engine *e, const uint32_t *recs);
 int b200_get_games(b200_engine *e, uint32_t *recs);
 int b200_update_root(b200_engine *e, int auto_reset);
 
+/* --- TreeAgent.remove_nodes (agents/agent.py:246-257; a public method, also reached from new_node :96-97 when the free list is
+ * empty): collect every game that has fewer than min_free free node slots (INT_MAX: every game), as one batched launch.
+ * b200_set_gc_headroom(n > 0) makes b200_update_root do that after re-rooting (the driver calling remove_nodes() between moves
+ * whenever len(agent.available) < n); 0 (default) = only the reference's own call site, inside new_node. */
+int b200_remove_nodes(b200_engine *e, int min_free);
+int b200_set_gc_headroom(b200_engine *e, int min_free);
+
 /* --- TreeAgent.mcts (agents/ValueSimLP.py:13, ValueSim.py:52, Vanilla.py:17): `sims` simulations on every game */
 int b200_run_sims(b200_engine *e, int sims);
 

@@ -588,6 +588,9 @@ int mo_agent_get_action(mo_agent *a, float *stats) {
 }
 
 int mo_agent_root(const mo_agent *a) { return a->root; }
+/* TreeAgent.remove_nodes() is a public method (agents/agent.py:246-257): a caller may collect between moves */
+void mo_agent_remove_nodes(mo_agent *a) { remove_nodes(a); }
+int mo_agent_n_free(const mo_agent *a) { return a->n_avail; }   /* len(self.available), agents/agent.py:72 */
 int mo_agent_episode(const mo_agent *a) { return a->episode; }
 long mo_agent_counter(const mo_agent *a, int w) { return (w >= 0 && w < 6) ? a->counters[w] : -1; }
 

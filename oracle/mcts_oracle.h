@@ -68,6 +68,8 @@ void mo_agent_update_root(mo_agent *a, const uint32_t *rec20);            /* age
 int mo_agent_mcts(mo_agent *a, int sims);                                 /* ValueSimLP.py:13-70 etc.; returns 0 or <0 on arena overflow */
 int mo_agent_get_action(mo_agent *a, float *stats21);                     /* agent.py:153-185 */
 int mo_agent_root(const mo_agent *a);
+void mo_agent_remove_nodes(mo_agent *a);                                 /* agent.py:246-257, called explicitly */
+int mo_agent_n_free(const mo_agent *a);                                   /* len(self.available) */
 int mo_agent_replay(mo_agent *a, uint8_t *rows212, int max_rows);   /* ValueSim.memory rows stored by remove_nodes; empties the memory */
 int mo_agent_episode(const mo_agent *a);
 long mo_agent_counter(const mo_agent *a, int which); /* 0 sims, 1 expansions, 2 evals, 3 gcs, 4 trace levels, 5 rollout steps */

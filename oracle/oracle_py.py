@@ -281,6 +281,15 @@ class Agent:
         a = lib().mo_agent_get_action(self.h, _p(st))
         return a, st
 
+    def remove_nodes(self):                                           # agents/agent.py:246-257, called explicitly
+        lib().mo_agent_remove_nodes.argtypes = [C.c_void_p]
+        lib().mo_agent_remove_nodes(self.h)
+
+    @property
+    def n_free(self):                                                 # len(self.available)
+        lib().mo_agent_n_free.argtypes = [C.c_void_p]
+        return lib().mo_agent_n_free(self.h)
+
     @property
     def root(self):
         return lib().mo_agent_root(self.h)

@@ -1,13 +1,10 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 ( timeout 600 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
-for v in base we we_ws we_st default we_l2_8 we_l2_32 we_l2_b12 we_l2_b16; do
-  echo "=== variant $v"
-  if [ $v = default ]; then unset B200_TETRIS_LIB; else export B200_TETRIS_LIB=$GRAFT_REPO_ROOT/build/variants/lib_$v.so; fi
-  timeout 300 python scripts/exp_growth.py 16384 16384 500 4 net_tc 2>&1 | grep -E "^move|^\{'select|k_select" | cut -c1-400
-done 2>&1 | tee gpurun_out/exp_variants.log
-unset B200_TETRIS_LIB
-echo "=== default, no timing (graph replay)"
-NO_TIMING=1 timeout 300 python scripts/exp_growth.py 16384 16384 500 4 net_tc 2>&1 | grep -E "^move" | cut -c1-200 | tee -a gpurun_out/exp_variants.log
-echo "=== default lib, M=4096 (footprint sensitivity)" | tee -a gpurun_out/exp_variants.log
-timeout 300 python scripts/exp_growth.py 16384 4096 500 4 net_tc 2>&1 | grep -E "^move|^\{'select|k_select" | cut -c1-400 | tee -a gpurun_out/exp_variants.log
+for h in 0 2560; do
+  echo "=== gc_headroom $h, 16 moves, no timing"
+  GC_HEADROOM=$h NO_TIMING=1 timeout 300 python scripts/exp_growth.py 16384 16384 500 16 net_tc 2>&1 | grep -E "^move" | cut -c1-200
+done 2>&1 | tee gpurun_out/exp_gc.log
+echo "=== timing, 4 moves" | tee -a gpurun_out/exp_gc.log
+timeout 300 python scripts/exp_growth.py 16384 16384 500 4 net_tc 2>&1 | grep -E "^\{'select|k_select|S0_arrive" | cut -c1-700 | tee -a gpurun_out/exp_gc.log
+timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_gc.json 2> gpurun_out/bench_r1_gc.err; python scripts/show_bench.py gpurun_out/bench_r1_gc.json; tail -3 gpurun_out/bench_r1_gc.err

@@ -1,5 +1,5 @@
 """Arena growth + first timings (development aid)."""
-import sys, time
+import os, sys, time
 import numpy as np
 sys.path.insert(0, '.')
 from tetris_mcts_b200 import pyTetris as PT
@@ -9,6 +9,7 @@ G, M, sims = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 moves = int(sys.argv[4]); ev = sys.argv[5] if len(sys.argv) > 5 else 'net'
 eng = BatchedEngine(G, max_nodes=M, mode='lp', eval_kind=ev, weights=init_weights(0), overflow_reset=True)
 eng.set_games(PT.new_games(G, (1, 0, 0), np.arange(123, 123 + G, dtype=np.uint32)))
+eng.set_gc_headroom(int(os.environ.get('GC_HEADROOM', '0')))
 import os
 TIMING = os.environ.get('NO_TIMING') != '1'
 eng.set_timing(TIMING)
@@ -38,5 +39,5 @@ print({n: round(float(pr[i]) / max(float(tot), 1), 3) for i, n in enumerate(name
 pt = np.zeros(8, np.uint64)
 L.lib().b200_debug_prof_tree.argtypes = [L.P, L.P]
 L.check(L.lib().b200_debug_prof_tree(eng.h, L.ptr(pt)))
-tt = float(pt[:4].sum())
-print('k_select_expand sampled groups', int(pt[4]), {n: round(float(pt[i]) / max(tt, 1), 3) for i, n in enumerate(['select', 'leaf_load', 'expand', 'finish+evalreq'])}, 'mean clk/group', int(tt / max(float(pt[4]), 1)))
+tt = float(pt[:4].sum() + pt[5])
+print('k_select_expand sampled groups', int(pt[4]), {n: round(float(pt[i]) / max(tt, 1), 3) for i, n in enumerate(['select', 'leaf_load', 'expand', 'finish+evalreq', '-', 'fused_backup']) if n != '-'}, 'mean clk/group', int(tt / max(float(pt[4]), 1)))

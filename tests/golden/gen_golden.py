@@ -132,6 +132,51 @@ def gen_agent(pt):
     print("agent_golden: %d cases" % len(cases))
 
 
+def gen_agent_explicit_gc(pt):
+    """The reference's own ValueSimLP with TreeAgent.remove_nodes() (agents/agent.py:246-257, a public method) called by the
+    driver between moves whenever fewer than `headroom` slots are free: the collection policy the batched engine offers as
+    b200_set_gc_headroom / b200_remove_nodes (one batched collection per move instead of one per overflowing expansion)."""
+    from agents.ValueSimLP import ValueSimLP
+    out = {}
+    cases = [dict(M=6000, sims=40, moves=45, seed=77, headroom=2500), dict(M=5000, sims=30, moves=40, seed=9, headroom=100000)]
+    for i, cs in enumerate(cases):
+        p = "g%d_" % i
+        game = pt.Tetris((20, 10), 1, 0, 0)
+        game.seed(cs["seed"])
+        ag = ValueSimLP(sims=cs["sims"], env=pt.Tetris, env_args=((20, 10), 1, 0, 0), benchmark=False, online=False, min_visit=40)
+        ag.max_nodes = cs["M"]
+        ag.init_array()
+        ag.model.inference = synthetic_inference
+        out[p + "start"] = np.array(game.get_record(), np.uint32)
+        ag.update_root(game)
+        acts, stats, collected = [], [], []
+        for mv in range(cs["moves"]):
+            a = ag.play()
+            acts.append(int(a))
+            stats.append(ag.get_stats())
+            game.play(a)
+            ag.update_root(game)
+            if game.end:
+                game.reset()
+                ag.update_root(game)
+            if len(ag.available) < cs["headroom"]:          # the driver's policy; remove_nodes itself is the reference's
+                ag.remove_nodes()
+                collected.append(mv)
+        out[p + "M"], out[p + "sims"], out[p + "headroom"] = cs["M"], cs["sims"], cs["headroom"]
+        out[p + "actions"], out[p + "stats"] = np.array(acts, np.int32), np.stack(stats).astype(np.float32)
+        out[p + "collected"] = np.array(collected, np.int32)
+        for k in ("child", "score", "episode"):
+            out[p + k] = ag.arrays[k]
+        out[p + "n2o"] = ag.node_to_obs
+        for k in ("visit", "value", "variance"):
+            out[p + k] = ag.obs_arrays[k]
+        out[p + "root"] = ag.root
+        out[p + "n_free"] = len(ag.available)
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, "agent_gc_golden.npz"), **out)
+    print("agent_gc_golden: %d cases, collections at moves %s" % (len(cases), [list(out["g%d_collected" % i])[:8] for i in range(len(cases))]))
+
+
 def gen_dist():
     """Outputs of the reference's own numba cores (agents/core_distributional.py) on seeded inputs."""
     import agents.core_distributional as R
@@ -177,8 +222,11 @@ if __name__ == "__main__":
     pt, core = O.mount_reference()
     if "--dist" in sys.argv:
         gen_dist()
+    elif "--agent-gc" in sys.argv:
+        gen_agent_explicit_gc(pt)
     else:
         gen_core(core)
         gen_valuenet()
         gen_agent(pt)
+        gen_agent_explicit_gc(pt)
         gen_dist()

@@ -69,6 +69,37 @@ def test_agent_golden(oracle):
             assert ag.counter(3) > 0, "the GC case must collect garbage"
 
 
+def test_agent_explicit_remove_nodes_golden(oracle):
+    """TreeAgent.remove_nodes() called by the driver between moves (agents/agent.py:246-257 is a public method): the C agent
+    with the same calls vs the reference's own ValueSimLP (tests/golden/gen_golden.py: gen_agent_explicit_gc).  This is the
+    collection policy the engine batches over all games (b200_set_gc_headroom / b200_remove_nodes)."""
+    z = np.load(os.path.join(GOLD, "agent_gc_golden.npz"))
+    for case in range(int(z["n_cases"])):
+        p = "g%d_" % case
+        ag = oracle.Agent(max_nodes=int(z[p + "M"]), mode=0, gamma=0.999, low=1, eval_mode=0)
+        g = oracle.Game(record=z[p + "start"])
+        ag.update_root(g.record())
+        collected = []
+        for mv, act in enumerate(z[p + "actions"]):
+            ag.mcts(int(z[p + "sims"]))
+            a, st = ag.get_action()
+            assert a == act and np.array_equal(st, z[p + "stats"][mv]), (case, mv)
+            g.play(a)
+            ag.update_root(g.record())
+            if g.end:
+                g.reset()
+                ag.update_root(g.record())
+            if ag.n_free < int(z[p + "headroom"]):
+                ag.remove_nodes()
+                collected.append(mv)
+        assert np.array_equal(np.array(collected, np.int32), z[p + "collected"])
+        assert ag.n_free == int(z[p + "n_free"])
+        ex = ag.export()
+        for k in ("child", "score", "n2o", "visit", "value", "variance", "episode"):
+            assert np.array_equal(ex[k], z[p + k]), (case, k)
+        assert ag.root == int(z[p + "root"])
+
+
 def test_env_spec_examples(oracle):
     """Hand-checkable rules of SPEC_PYTETRIS.md §2-4."""
     g = oracle.Game(1, 0, 0, seed=7)

@@ -181,6 +181,106 @@ def test_full_size_properties(gpu_lib):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
+GOLD_GC = os.path.join(os.path.dirname(__file__), "golden", "agent_gc_golden.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLD_GC), reason="golden vectors not generated")
+def test_explicit_remove_nodes_against_reference_python_agent_golden(gpu_lib):
+    """The driver calling TreeAgent.remove_nodes() between moves whenever fewer than `headroom` slots are free
+    (agents/agent.py:246-257 is a public method): b200_set_gc_headroom makes update_root do exactly that, batched.  Per-move
+    statistics, actions and the final arrays against the reference's own ValueSimLP + agent.py (gen_agent_explicit_gc)."""
+    from tetris_mcts_b200.engine import BatchedEngine
+    z = np.load(GOLD_GC)
+    for case in range(int(z["n_cases"])):
+        p = "g%d_" % case
+        M, sims, headroom = int(z[p + "M"]), int(z[p + "sims"]), int(z[p + "headroom"])
+        eng = BatchedEngine(1, max_nodes=M, mode="lp", eval_kind="synthetic")
+        eng.set_games(z[p + "start"][None, :].astype(np.uint32))
+        eng.set_gc_headroom(headroom)                                   # the driver's policy starts after the first update_root
+        gcs_at = []
+        for mv, act in enumerate(z[p + "actions"]):
+            g0 = eng.counters()["gcs"]
+            eng.run_sims(sims)
+            stats, action = eng.get_stats()
+            assert action[0] == act and np.array_equal(stats[0], z[p + "stats"][mv]), (case, mv)
+            g1 = eng.counters()["gcs"]
+            eng.env_step(None)
+            eng.update_root(True)
+            if eng.counters()["gcs"] > g1:
+                gcs_at.append(mv)
+            assert g1 == g0, "no collection inside a move in these cases"
+        ex = eng.export_game(0)
+        for k in ("child", "score", "n2o", "visit", "value", "variance", "episode"):
+            assert np.array_equal(ex[k], z[p + k]), (case, k)
+        assert ex["root"] == int(z[p + "root"])
+        assert gcs_at == list(z[p + "collected"]), (case, gcs_at)
+        eng.close()
+
+
+def test_batched_remove_nodes_many_games_exact(gpu_lib, oracle):
+    """The same policy on many games at once (one k_gc launch for all of them) + an explicit collect-everything call, against
+    oracle agents that make the same remove_nodes() calls."""
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    n, M, sims, moves, seed, headroom = 40, 2600, 24, 36, 555, 900
+    recs = PT.new_games(n, ARGS, np.arange(seed, seed + n, dtype=np.uint32))
+    eng = BatchedEngine(n, max_nodes=M, mode="lp", eval_kind="synthetic", seed=seed)
+    eng.set_gc_headroom(headroom)
+    eng.set_games(recs)
+    agents = [oracle.Agent(max_nodes=M, mode=0, gamma=0.999, low=1, eval_mode=0, search_seed=search_seed(seed, g)) for g in range(n)]
+    games = [oracle.Game(record=recs[g]) for g in range(n)]
+    for g in range(n):
+        agents[g].update_root(games[g].record())
+    for mv in range(moves):
+        actions, stats = eng.play_move(sims, auto_reset=True)
+        for g in range(n):
+            agents[g].mcts(sims)
+            a, st = agents[g].get_action()
+            assert a == actions[g] and np.array_equal(st, stats[g]), (mv, g)
+            games[g].play(a)
+            agents[g].update_root(games[g].record())
+            if games[g].end:
+                games[g].reset()
+                agents[g].update_root(games[g].record())
+            if agents[g].n_free < headroom:
+                agents[g].remove_nodes()
+        if mv == 10:                                            # TreeAgent.remove_nodes() on every game
+            eng.remove_nodes()
+            for g in range(n):
+                agents[g].remove_nodes()
+    assert eng.counters()["gcs"] == sum(ag.counter(3) for ag in agents) > n
+    for g in (0, n // 2, n - 1):
+        ex, want = eng.export_game(g), agents[g].export()
+        for k in ("child", "score", "n2o", "visit", "value", "variance", "episode"):
+            assert np.array_equal(ex[k], want[k]), (g, k)
+    eng.close()
+
+
+def test_overflow_reset_drops_trees_that_collection_cannot_shrink(gpu_lib):
+    """overflow_reset (a policy beyond the reference, used by bench.py): when a collection recovers fewer than max_nodes/8 slots
+    the whole thread block of k_gc clears the arena and the next kernel re-roots at the live game.  Invariants: no error status,
+    trees are dropped (counter), every game keeps simulating (root visits grow by `sims` per move), and the run is deterministic."""
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    n, M, sims, moves = 256, 512, 40, 30
+    recs = PT.new_games(n, ARGS, np.arange(31, 31 + n, dtype=np.uint32))
+    outs = []
+    for rep in range(2):
+        eng = BatchedEngine(n, max_nodes=M, mode="lp", eval_kind="synthetic", overflow_reset=True)
+        eng.set_gc_headroom(200)
+        eng.set_games(recs)
+        acts = []
+        for mv in range(moves):
+            a, st = eng.play_move(sims, auto_reset=True)
+            assert st[:, 0].sum(axis=1).min() >= 1                      # every root has visited children
+            acts.append(a.copy())
+        c = eng.counters()
+        assert (eng.status() == 0).all() and c["tree_resets"] > 0 and c["gcs"] > 0 and c["sims"] == n * sims * moves
+        outs.append((np.stack(acts), eng.get_games().copy()))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_graph_replay_equals_direct_launches(gpu_lib):
     """b200_run_sims replays one captured simulation step (CUDA graph) when phase timing is off and launches the
     kernels one by one when it is on; requests and counters are aggregated per CTA in k_select_expand.  Both paths must

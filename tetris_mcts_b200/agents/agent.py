@@ -142,8 +142,8 @@ class TreeAgent(Agent):                                          # agents/agent.
         o = s["n2o"][s["root"] if node is None else node]
         return s["value"][o], s["variance"][o]
 
-    def remove_nodes(self):
-        pass   # collection runs on the device exactly where the reference calls it (agents/agent.py:96-97 -> k_gc)
+    def remove_nodes(self):                                       # agents/agent.py:246-257 (also run on the device where new_node needs it, :96-97)
+        self._eng.remove_nodes()
 
     def counters(self):
         return self._eng.counters()

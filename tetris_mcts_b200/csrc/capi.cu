@@ -63,6 +63,7 @@ struct b200_engine {
     // sampling
     uint8_t *d_samples = nullptr; int sample_cap = 0; int32_t *d_sample_count = nullptr;
     // one simulation step captured as a CUDA graph (replayed when phase timing is off: ~7 launches + 1 memset per step, 500 steps/move)
+    int gc_headroom = 0;           // b200_set_gc_headroom: collect between moves every game with fewer free slots than this
     cudaGraphExec_t step_exec = nullptr; bool step_graph_failed = false;
     uint64_t step_launches[PH_N] = {0};
 };
@@ -161,7 +162,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     int H = 16; while (H < 2 * A.M) H <<= 1;
     A.H = H; A.trace_max = cfg->trace_max > 0 ? cfg->trace_max : 512;
     A.mode = cfg->mode; A.low = cfg->low; A.lp_end_from_obs = cfg->lp_end_from_obs; A.lp_var_gamma2 = cfg->lp_var_gamma2;
-    A.stale_pop = cfg->stale_pop; A.eval_kind = cfg->eval_kind; A.overflow_reset = cfg->overflow_reset; A.gamma = cfg->gamma; A.rollout_variance = cfg->rollout_variance;
+    A.stale_pop = cfg->stale_pop; A.eval_kind = cfg->eval_kind; A.overflow_reset = cfg->overflow_reset; A.gc_min_gain = cfg->overflow_reset ? cfg->max_nodes / 8 : 0; A.gamma = cfg->gamma; A.rollout_variance = cfg->rollout_variance;
     size_t GM = (size_t)A.G * A.M, G = (size_t)A.G;
     int rc = 0;
     rc |= dalloc(e, &A.row, GM * ROW_WORDS);
@@ -397,10 +398,30 @@ static int check_status(b200_engine *e) {   // cheap: max over the status array 
     CK(cudaMemcpyAsync(st.data(), e->A.status, st.size() * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     for (int g = 0; g < e->A.G; ++g)
-        if (st[g] != ST_OK && !(st[g] == ST_ARENA_FULL && e->A.overflow_reset)) {
+        if (st[g] != ST_OK && !((st[g] == ST_ARENA_FULL || st[g] == ST_RESET_DONE) && e->A.overflow_reset)) {
             int code = st[g] == ST_ARENA_FULL ? B200_ERR_ARENA_FULL : B200_ERR_TRACE_FULL;
             return fail(code, "game " + std::to_string(g) + (st[g] == ST_ARENA_FULL ? ": arena full after garbage collection (raise max_nodes)" : ": trace longer than trace_max"));
         }
+    return B200_OK;
+}
+
+// TreeAgent.remove_nodes() (agents/agent.py:246-257) for every game with fewer than min_free free node slots, as ONE batched k_gc
+extern "C" int b200_remove_nodes(b200_engine *e, int min_free) {
+    if (!e || min_free < 0) return fail(B200_ERR_BAD_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    {
+        PhaseTimer t(e, PH_GC);
+        CK(cudaMemsetAsync(e->A.n_req + 1, 0, sizeof(int32_t), e->stream));
+        k_gc_request<<<(e->A.G + 127) / 128, 128, 0, e->stream>>>(e->A, min_free);
+        k_gc<<<gc_blocks(e), GC_THREADS, 0, e->stream>>>(e->A);
+    }
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_set_gc_headroom(b200_engine *e, int min_free) {
+    if (!e || min_free < 0) return fail(B200_ERR_BAD_ARG, "bad argument");
+    e->gc_headroom = min_free;
     return B200_OK;
 }
 
@@ -413,6 +434,10 @@ extern "C" int b200_update_root(b200_engine *e, int auto_reset) {
         k_update_root<<<blocks_groups(e->A.G), TPB, 0, e->stream>>>(e->A, auto_reset, e->d_game_stats, 0);
         k_gc<<<gc_blocks(e), GC_THREADS, 0, e->stream>>>(e->A);                 // games whose free list ran dry (usually none)
         k_update_root<<<blocks_groups(e->A.G), TPB, 0, e->stream>>>(e->A, auto_reset, e->d_game_stats, 1);
+    }
+    if (e->gc_headroom > 0) {
+        int rc = b200_remove_nodes(e, e->gc_headroom);
+        if (rc) return rc;
     }
     CK(cudaGetLastError());
     return B200_OK;
@@ -470,7 +495,7 @@ static int enqueue_step(b200_engine *e) {
         int rc = launch_net(e, A.req, A.n_req, A.key, A.M, A.eval_out, (size_t)G * (A.mode == MODE_LP ? 7 : 1));
         if (rc) return rc;
     }
-    {
+    if (A.mode == MODE_DIST || !B200_FUSED_BACKUP) {   // otherwise the next k_select_expand (or run_sims' final k_backup) folds this step's traces
         PhaseTimer t(e, PH_BACKUP);
         if (A.mode == MODE_DIST) k_dist_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
         else k_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
@@ -512,6 +537,10 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
         int rc = enqueue_step(e);
         if (rc) return rc;
         if (!e->timing && !e->step_exec && !e->step_graph_failed) capture_step(e);
+    }
+    if (B200_FUSED_BACKUP && A.mode != MODE_DIST && sims > 0) {   // the last simulation's traces (the others were folded by the next step's k_select_expand)
+        PhaseTimer t(e, PH_BACKUP);
+        k_backup<<<(A.G + 3) / 4, 128, 0, e->stream>>>(A);
     }
     CK(cudaGetLastError());
     return B200_OK;
@@ -560,7 +589,8 @@ extern "C" int b200_status(b200_engine *e, int32_t *status) {
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaMemcpyAsync(status, e->A.status, (size_t)e->A.G * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    for (int g = 0; g < e->A.G; ++g) status[g] = status[g] == ST_OK ? 0 : (status[g] == ST_ARENA_FULL ? B200_ERR_ARENA_FULL : B200_ERR_TRACE_FULL);
+    for (int g = 0; g < e->A.G; ++g)
+        status[g] = (status[g] == ST_OK || status[g] == ST_RESET_DONE) ? 0 : (status[g] == ST_ARENA_FULL ? B200_ERR_ARENA_FULL : B200_ERR_TRACE_FULL);
     return B200_OK;
 }
 

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, un
         if (A.pending[g] != PEND_ROOT) return;
         gp.sync();
         if (gp.lane == 0) A.pending[g] = PEND_NONE;
-    } else if (status == ST_ARENA_FULL && A.overflow_reset) {
+    } else if ((status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) {
         reset_tree(A, gp, g, status);   // re-roots at the live game
     }
     if (status != ST_OK) return;
@@ -160,17 +160,24 @@ __device__ __forceinline__ Uniq finish_expansion(const Arena &A, const Grp &gp, 
 }
 
 // ---------------------------------------------------------------- select + expand (ValueSimLP.py:45-57 etc.)
+template <int NL> __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask, int lane);   // defined with k_backup below
+
 // What one group hands to the CTA-level epilogue of k_select_expand: its evaluation request (per lane) and its counters.
 struct GroupOut { bool ask; int my_o; int sims, D, expanded, new_nodes; };
 
 __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &gp, int g, const float *s_z, uint32_t *stage, GroupOut &out) {
     int status = A.status[g];
-    if (status == ST_ARENA_FULL && A.overflow_reset) reset_tree(A, gp, g, status);
+    const bool do_prof = A.prof && (g & 63) == 0 && gp.lane == 0;
+    long long ptick = do_prof ? clock64() : 0;
+#if B200_FUSED_BACKUP
+    // the previous simulation of this game is folded into the statistics first (k_backup's work, see backup_game)
+    if (status == ST_OK && A.mode != MODE_DIST) backup_game<8>(A, g, gp.mask, gp.lane);
+    if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[5], (unsigned long long)(_n - ptick)); ptick = _n; }
+#endif
+    if ((status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) reset_tree(A, gp, g, status);
     if (status != ST_OK) return;
     ArenaAcc acc(A, g, s_z);
     int D = 0;
-    const bool do_prof = A.prof && (g & 63) == 0 && gp.lane == 0;
-    long long ptick = do_prof ? clock64() : 0;
 #define TREE_PROF(i) do { if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[i], (unsigned long long)(_n - ptick)); ptick = _n; } } while (0)
     int leaf = A.mode == MODE_DIST ? dist_select_group(A, gp, g, A.root[g], D, status)
                                    : select_trace(acc, gp, A.root[g], A.low, A.trace_max, D, status);
@@ -456,8 +463,40 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
             atomicAdd(&A.counters[3], 1ull);
             if (nn == 0) A.status[g] = ST_ARENA_FULL;        // reference: IndexError at agent.py:99 / UB at agent.cpp:227-231
         }
+        // overflow_reset policy (beyond the reference, bench only): a collection that recovers fewer than gc_min_gain slots means the
+        // reachable set itself fills the arena; the reference would collect again at almost every expansion from here on (a
+        // whole-arena sweep for a handful of slots) and then die.  The tree is dropped here, by the whole block, and the next
+        // k_select_expand / k_update_root only re-roots it (ST_RESET_DONE).
+        if (A.overflow_reset && nn < A.gc_min_gain) {
+            __syncthreads();
+            int4 *rows = reinterpret_cast<int4 *>(rowb);
+            for (int i = t; i < M * (ROW_WORDS / 4); i += GC_THREADS) rows[i] = make_int4(0, 0, 0, 0);
+            for (int i = t; i < M; i += GC_THREADS) statb[i] = make_int4(0, 0, 0, 0);
+            for (int i = t; i < M * 3; i += GC_THREADS) keyb[i] = make_uint4(0, 0, 0, 0);
+            for (int i = t; i < H; i += GC_THREADS) { ntab[i] = make_uint2(0, 0); otab[i] = make_uint2(0, 0); }
+            if (A.nstat) {
+                float *nsb = A.nstat + (size_t)g * M * NSTAT_WORDS, *ndb = A.ndist + (size_t)g * M * A.dist_bins;
+                for (int i = t; i < M * NSTAT_WORDS; i += GC_THREADS) nsb[i] = 0.f;
+                for (size_t i = t; i < (size_t)M * A.dist_bins; i += GC_THREADS) ndb[i] = 0.f;
+            }
+            for (int i = t; i < M - 1; i += GC_THREADS) { nfree[i] = i + 1; ofree[i] = i + 1; }
+            if (t == 0) {
+                A.n_nfree[g] = M - 1; A.n_ofree[g] = M - 1;
+                A.status[g] = ST_RESET_DONE;
+                atomicAdd(&A.counters[7], 1ull);
+            }
+        }
         __syncthreads();
     }
+}
+
+// remove_nodes() called by the driver (TreeAgent.remove_nodes is a public method, agents/agent.py:246-257): queue every game whose
+// free list is shorter than min_free for ONE batched k_gc launch (all SMs busy), instead of one nearly empty k_gc launch per
+// simulation step in which some game happens to run dry (a single collection is a ~1 ms latency chain the whole step waits for).
+__global__ void k_gc_request(Arena A, int min_free) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= A.G || A.status[g] != ST_OK || A.pending[g] != PEND_NONE) return;
+    if (A.n_nfree[g] < min_free) A.gc_list[atomicAdd(A.n_req + 1, 1)] = g;
 }
 
 // ---------------------------------------------------------------- test evaluator (shared definition with oracle/mcts_oracle.c)
@@ -498,42 +537,45 @@ __global__ void k_rollout(Arena A) {
     atomicAdd(&A.counters[5], (unsigned long long)steps);
 }
 
-// ---------------------------------------------------------------- backup (core.h:226-381), one warp per game
-// The reference walks the trace leaf -> root with two dependent gathers per level.  Here the 32 lanes of a warp fetch
-// 32 levels at once (node meta, then statistics), the Welford recurrence then runs in exactly the reference's order
-// (same welford_level code, v carried in double), and the statistics are written back in parallel.  If an observation
-// occurs twice among the levels in flight (statistics are shared between nodes, agent.py:116-128) the warp falls back
+// ---------------------------------------------------------------- backup (core.h:226-381)
+// The reference walks the trace leaf -> root with two dependent gathers per level.  Here NL lanes fetch NL levels at
+// once (node meta, then statistics), the Welford recurrence then runs in exactly the reference's order (same
+// welford_level code, v carried in double), and the statistics are written back in parallel.  If an observation
+// occurs twice among the levels in flight (statistics are shared between nodes, agent.py:116-128) the lanes fall back
 // to the scalar walk.  Everything the backup never writes (trace, row fields, evaluator outputs) is loaded as early as
 // possible: the first window's node fields together with the leaf's child row, the next window's while the current one
 // is folded, so that only the statistics loads sit on the dependent chain (a DRAM access is ~2.4 k clk here).
-#ifndef B200_BACKUP_MINB
-#define B200_BACKUP_MINB 9      // resident 128-thread blocks per SM the register budget is cut for (9 = what 56 registers give)
-#endif
-__global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
-    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (g >= A.G || A.status[g] != ST_OK) return;
+//
+// Two callers, one code path:
+//   NL = 8   the game's 8-lane group at the START of k_select_expand: the backup of simulation s runs fused in front of the
+//            selection of simulation s+1 of the same game.  Games are independent, so no grid-wide barrier (kernel boundary)
+//            is needed between a game's backup and its next descent; the separate k_backup launch per step cost a three-wave
+//            kernel whose tail every step waited for.
+//   NL = 32  k_backup, one warp per game: after the LAST simulation of b200_run_sims (and in distributional mode's twin).
+// leaf_kind[g] is set to LEAF_DONE once the trace is folded, which makes the two callers idempotent.
+template <int NL>
+__device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask, int lane) {
     ArenaAcc acc(A, g);
     const int D = A.trace_len[g];
     const int kind = A.leaf_kind[g];
-    if (kind == LEAF_SUSPENDED || D <= 0) return;
+    if (kind == LEAF_SUSPENDED || kind == LEAF_DONE || D <= 0) return;
     // ---- early loads: trace entries of the first window, then their node fields + the leaf's child row + evaluator outputs
-    const int n0 = D < 32 ? D : 32;
+    const int n0 = D < NL ? D : NL;
     int tidx = 0;
     if (lane < n0) tidx = acc.get_trace(D - 1 - lane);
-    const int leaf = __shfl_sync(0xffffffffu, tidx, 0);
+    const int leaf = __shfl_sync(mask, tidx, 0, NL);
     const bool lp_children = A.mode == MODE_LP && kind == LEAF_EXPANDED;
     int wo = -1 - lane; float wsc = 0.f;                      // this lane's level of the current window: observation, score
     if (lane < n0) acc.meta(tidx, D - 1 - lane, wo, wsc);
     int c = 0, o = 0; float s = 0.f;
     float2 ev = make_float2(0.f, 0.f);
     if (lp_children && lane < 8) { acc.children(leaf, lane, c, o, s); ev = A.eval_out[(size_t)g * 8 + lane]; }
-    const float leaf_score = __shfl_sync(0xffffffffu, wsc, 0);
+    const float leaf_score = __shfl_sync(mask, wsc, 0, NL);
     double v = (double)leaf_score, var = 0.0;
     if (A.mode == MODE_LP) {
         if (kind == LEAF_EXPANDED) {
             // core.h:340-366: initialise unvisited unique children, then average score + gamma*value and the variances
-            Grp gp;                                   // lanes 0-7 of the warp form the group that holds the 7 child slots
+            Grp gp;                                   // lanes 0-7 form the group that holds the 7 child slots
             double v_tmp = 0.0, var_tmp = 0.0;
             int k = 0;
             if (lane < 8) {
@@ -557,13 +599,13 @@ __global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
                     }
                 }
             }
-            k = __shfl_sync(0xffffffffu, k, 0);
-            v_tmp = __shfl_sync(0xffffffffu, v_tmp, 0);
-            var_tmp = __shfl_sync(0xffffffffu, var_tmp, 0);
+            k = __shfl_sync(mask, k, 0, NL);
+            v_tmp = __shfl_sync(mask, v_tmp, 0, NL);
+            var_tmp = __shfl_sync(mask, var_tmp, 0, NL);
             v = __ddiv_rn(v_tmp, (double)k);                                   // core.h:364
             if (A.lp_var_gamma2) var = __dmul_rn(var_tmp, __ddiv_rn(__dmul_rn(A.gamma, A.gamma), (double)k));   // core.h:365
             else { var = __ddiv_rn(var_tmp, (double)k); v = (double)(float)v; var = (double)(float)var; }        // agent.cpp:557-562
-            __syncwarp();
+            __syncwarp(mask);
         }
     } else if (A.mode == MODE_SINGLE) {
         if (kind == LEAF_EXPANDED) {
@@ -574,16 +616,16 @@ __global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
     } else if (kind == LEAF_EXPANDED) {
         v = (double)A.rollout_val[g]; var = A.rollout_variance;                // Vanilla.py:53-54
     }
-    // ---- core.h:244-259 along the trace, 32 levels per round
-    for (int top = D - 1; top >= 0; top -= 32) {
-        const int n = top + 1 < 32 ? top + 1 : 32;      // levels top, top-1, ..., top-n+1 -> lanes 0..n-1
+    // ---- core.h:244-259 along the trace, NL levels per round
+    for (int top = D - 1; top >= 0; top -= NL) {
+        const int n = top + 1 < NL ? top + 1 : NL;      // levels top, top-1, ..., top-n+1 -> lanes 0..n-1
         const int o = wo; const float sc = wsc;
         int4 st = make_int4(0, 0, 0, 0);
-        const bool dup = __popc(__match_any_sync(0xffffffffu, o)) > 1;
-        const bool any_dup = __any_sync(0xffffffffu, dup);
+        const bool dup = __popc(__match_any_sync(mask, o)) > 1;
+        const bool any_dup = __any_sync(mask, dup);
         if (!any_dup && lane < n) st = acc.stat(o, top - lane);
         {   // the next window's node fields, in flight while this window is folded
-            const int ntop = top - 32;
+            const int ntop = top - NL;
             wo = -1 - lane; wsc = 0.f;
             if (ntop >= 0 && lane <= ntop) acc.meta(acc.get_trace(ntop - lane), ntop - lane, wo, wsc);
         }
@@ -597,8 +639,8 @@ __global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
                     acc.set_stat(oo, s2);
                 }
             }
-            v = __shfl_sync(0xffffffffu, v, 0);
-            __syncwarp();
+            v = __shfl_sync(mask, v, 0, NL);
+            __syncwarp(mask);
             continue;
         }
         // The value chain v <- gamma*(v - score) + score (core.h:244,259) does not depend on the statistics: every lane
@@ -606,13 +648,24 @@ __global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
         // Welford updates (core.h:245-258) of the whole window then run in parallel, one level per lane.
         double vin = v;
         for (int j = 0; j < n; ++j) {
-            const double scj = (double)__shfl_sync(0xffffffffu, sc, j);
+            const double scj = (double)__shfl_sync(mask, sc, j, NL);
             if (lane == j) vin = v;
             v = __dadd_rn(__dmul_rn(A.gamma, __dsub_rn(v, scj)), scj);
         }
         if (lane < n) { welford_level(st, vin, var, sc, A.gamma); acc.set_stat(o, st, top - lane); }
-        __syncwarp();
+        __syncwarp(mask);
     }
+    if (lane == 0) A.leaf_kind[g] = LEAF_DONE;
+    __syncwarp(mask);
+}
+
+#ifndef B200_BACKUP_MINB
+#define B200_BACKUP_MINB 9      // resident 128-thread blocks per SM the register budget is cut for (9 = what 56 registers give)
+#endif
+__global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
+    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (g >= A.G || A.status[g] != ST_OK) return;
+    backup_game<32>(A, g, 0xffffffffu, threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------- distributional mode (config 5): evaluator + backup

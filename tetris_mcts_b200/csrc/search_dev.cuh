@@ -26,8 +26,12 @@ namespace b200 {
 constexpr int ROW_WORDS = 32;     // child row (one 128-byte line): c[8] | o[8] | s[8] | u[8]; u = the child list already de-duplicated (see link_word)
 constexpr int ZTABLE_N = 65536;   // z(n) table computed on the host with the reference's libm (special.h:26-33)
 
-enum : int { ST_OK = 0, ST_ARENA_FULL = 1, ST_TRACE_FULL = 2, ST_NEED_GC = 3 };
-enum : int { LEAF_TERMINAL = 0, LEAF_EXPANDED = 1, LEAF_SUSPENDED = 2 };
+enum : int { ST_OK = 0, ST_ARENA_FULL = 1, ST_TRACE_FULL = 2, ST_NEED_GC = 3, ST_RESET_DONE = 4 };   // RESET_DONE: k_gc dropped the tree (overflow_reset), only the re-rooting is left
+enum : int { LEAF_TERMINAL = 0, LEAF_EXPANDED = 1, LEAF_SUSPENDED = 2, LEAF_DONE = 3 };   // DONE: the trace has been backed up
+#ifndef B200_FUSED_BACKUP
+#define B200_FUSED_BACKUP 0   // 1: the backup of a game's previous simulation runs at the start of k_select_expand (kernels.cuh: backup_game);
+                              // exact (59 GPU tests) but measured 4 % slower than the separate warp-per-game k_backup on B200, so off
+#endif
 enum : int { PEND_NONE = 0, PEND_EXPAND = 1, PEND_ROOT = 2 };
 enum : int { MODE_LP = 0, MODE_SINGLE = 1, MODE_VANILLA = 2, MODE_DIST = 3 };
 constexpr int NSTAT_WORDS = 8;    // node_stats row: {visit, mean, reward, variance, M2, -, -, -} (agents/core_distributional.py:109-124)
@@ -44,6 +48,7 @@ constexpr int NSTAT_WORDS = 8;    // node_stats row: {visit, mean, reward, varia
 struct Arena {
     int G, M, H, trace_max;
     int mode, low, lp_end_from_obs, lp_var_gamma2, stale_pop, eval_kind, overflow_reset;
+    int gc_min_gain;               // overflow_reset only: a collection that leaves fewer free slots than this drops the tree (see k_gc)
     double gamma, rollout_variance;
     int32_t *row; int4 *stat; uint32_t *rec; uint32_t *key;
     uint2 *ntab, *otab;
@@ -157,7 +162,7 @@ __device__ __forceinline__ uint32_t link_word(const Uniq &u) {
 #define B200_WARM_EXPAND 1
 #endif
 #ifndef B200_WARM_SELECT
-#define B200_WARM_SELECT 0
+#define B200_WARM_SELECT 1   // measured -1 % on k_select_expand (B200, 16384 games)
 #endif
 // L2 residency hints (performance only).  One simulation step streams ~200 MB of activations (conv -> fc) and ~20 MB of new
 // nodes through the 126 MB L2, so without hints nothing of the trees survives from one step to the next although every step
@@ -496,22 +501,24 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
 // first move of an episode.  Never taken when the arena is sized like the reference's (tests run with it off).
 __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, int &status) {
     const int M = A.M, H = A.H;
-    int4 *rows = reinterpret_cast<int4 *>(A.row + (size_t)g * M * ROW_WORDS);
-    for (int i = gp.lane; i < M * (ROW_WORDS / 4); i += 8) rows[i] = make_int4(0, 0, 0, 0);
-    int4 *statb = A.stat + (size_t)g * M;
-    for (int i = gp.lane; i < M; i += 8) statb[i] = make_int4(0, 0, 0, 0);
-    uint4 *keyb = reinterpret_cast<uint4 *>(A.key + (size_t)g * M * KEY_WORDS);
-    for (int i = gp.lane; i < M * 3; i += 8) keyb[i] = make_uint4(0, 0, 0, 0);
-    uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
-    for (int i = gp.lane; i < H; i += 8) { ntab[i] = make_uint2(0, 0); otab[i] = make_uint2(0, 0); }
-    if (A.nstat) {
-        float *ns = A.nstat + (size_t)g * M * NSTAT_WORDS, *nd = A.ndist + (size_t)g * M * A.dist_bins;
-        for (int i = gp.lane; i < M * NSTAT_WORDS; i += 8) ns[i] = 0.f;
-        for (size_t i = gp.lane; i < (size_t)M * A.dist_bins; i += 8) nd[i] = 0.f;
+    if (status != ST_RESET_DONE) {        // (k_gc has already cleared the arena with a whole thread block in that case)
+        int4 *rows = reinterpret_cast<int4 *>(A.row + (size_t)g * M * ROW_WORDS);
+        for (int i = gp.lane; i < M * (ROW_WORDS / 4); i += 8) rows[i] = make_int4(0, 0, 0, 0);
+        int4 *statb = A.stat + (size_t)g * M;
+        for (int i = gp.lane; i < M; i += 8) statb[i] = make_int4(0, 0, 0, 0);
+        uint4 *keyb = reinterpret_cast<uint4 *>(A.key + (size_t)g * M * KEY_WORDS);
+        for (int i = gp.lane; i < M * 3; i += 8) keyb[i] = make_uint4(0, 0, 0, 0);
+        uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
+        for (int i = gp.lane; i < H; i += 8) { ntab[i] = make_uint2(0, 0); otab[i] = make_uint2(0, 0); }
+        if (A.nstat) {
+            float *ns = A.nstat + (size_t)g * M * NSTAT_WORDS, *nd = A.ndist + (size_t)g * M * A.dist_bins;
+            for (int i = gp.lane; i < M * NSTAT_WORDS; i += 8) ns[i] = 0.f;
+            for (size_t i = gp.lane; i < (size_t)M * A.dist_bins; i += 8) nd[i] = 0.f;
+        }
+        int32_t *nfree = A.nfree + (size_t)g * M, *ofree = A.ofree + (size_t)g * M;
+        for (int i = gp.lane; i < M - 1; i += 8) { nfree[i] = i + 1; ofree[i] = i + 1; }
+        if (gp.lane == 0) { A.n_nfree[g] = M - 1; A.n_ofree[g] = M - 1; atomicAdd(&A.counters[7], 1ull); }
     }
-    int32_t *nfree = A.nfree + (size_t)g * M, *ofree = A.ofree + (size_t)g * M;
-    for (int i = gp.lane; i < M - 1; i += 8) { nfree[i] = i + 1; ofree[i] = i + 1; }
-    if (gp.lane == 0) { A.n_nfree[g] = M - 1; A.n_ofree[g] = M - 1; atomicAdd(&A.counters[7], 1ull); }
     gp.sync();
     status = ST_OK;
     uint32_t w[REC_WORDS];

@@ -65,7 +65,7 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 #ifndef B200_L2_STREAM_ACT3
-#define B200_L2_STREAM_ACT3 1
+#define B200_L2_STREAM_ACT3 0   // measured on B200: k_tc_fc -5 %, but the tree kernels that follow +13 % (net loss); kept as a switch
 #endif
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -173,6 +173,8 @@ constexpr int TCC_WBLOCK = 2 * 2 * 96 * 16;  // one (dy, channel half) block: [w
 constexpr int TCC_WBYTES = 6 * TCC_WBLOCK;   // one conv layer = 36864 B
 constexpr int TCC_W1BYTES = 2 * 64 * 16;     // conv1: [chunk 2][n = split*32 + cout][16 B], k = tap (9 of 16 used)
 constexpr int TCC_SLOTS = 4;                // boards in flight
+constexpr int TCC_KEYS_AHEAD = 4;           // observation keys the loader warp keeps in flight (registers)
+constexpr int TCC_RUN = 4;                  // consecutive requests handed to a CTA at a time (a power of two)
 constexpr int TCC_ASLOT = 2 * 4 * TCC_R * 16;    // operand buffer of one slot: act1 [split][chunk 4][144 rows][16 B], overwritten in
                                                  // place by act2 (conv2 has finished reading by then)
 constexpr int TCC_IMROWS = 256;             // im2col rows per board: 144 used, two M=128 tiles
@@ -296,17 +298,18 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int n_req = *n_req_ptr;
-    // Boards are handed out in runs of 8 consecutive requests (neighbouring act3 rows get written close in time); board i of
+    // Boards are handed out in runs of TCC_RUN consecutive requests (neighbouring act3 rows get written close in time; short runs keep
+    // the CTAs' board counts within TCC_RUN of each other: with runs of 8 the last CTAs had 4 % more work); board i of
     // this CTA's sequence lives in slot i % 4.  Four boards are in flight at different stages (software pipeline):
     //   workers, iteration i :  S0(i) im2col | E2(i-2) conv2 epilogue | E3(i-3) conv3 epilogue | E1(i) conv1 epilogue
     //   issuer,  iteration i :  conv2(i-1) | conv1(i) | conv3(i-2), each as soon as the workers have written its operand
     // The order is chosen so that the tensor pipe never runs dry: conv2(i-1)'s operand was finished at the end of the
     // previous iteration (E1 comes last), conv1(i) is short and queued behind it, conv3(i-2)'s operand (E2) is ready long
     // before conv2 retires; the workers drain older boards (E2, E3) while conv2 runs and reach E1(i) after conv1(i) is done.
-    const int n_runs = (n_req + 7) >> 3;
+    const int n_runs = (n_req + TCC_RUN - 1) / TCC_RUN;
     int n_local = 0;
-    for (int run = blockIdx.x; run < n_runs; run += gridDim.x) n_local += min(8, n_req - run * 8);
-    auto board_of = [&](int i) -> int { return ((i >> 3) * (int)gridDim.x + (int)blockIdx.x) * 8 + (i & 7); };
+    for (int run = blockIdx.x; run < n_runs; run += gridDim.x) n_local += min(TCC_RUN, n_req - run * TCC_RUN);
+    auto board_of = [&](int i) -> int { return ((i / TCC_RUN) * (int)gridDim.x + (int)blockIdx.x) * TCC_RUN + (i % TCC_RUN); };
     if (warp == TCC_ISSUER) {
         // ===================================================== MMA issuer
         if (lane == 0) {
@@ -357,18 +360,29 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
         }
     } else if (warp == TCC_LOADER) {
         // ===================================================== key loader: global loads stay out of the workers' way (their
-        // proxy fences would otherwise wait for every outstanding load)
+        // proxy fences would otherwise wait for every outstanding load).  A key is a random 48-byte read from an arena of tens
+        // of GB (~2.4 k clk); TCC_KEYS_AHEAD of them are kept in flight so that the loader never paces the workers.
         uint2 rqs = make_uint2(0, 0);
-        for (int i = 0; i < n_local; ++i) {
-            const int slot = i % NS;
+        uint32_t kq[TCC_KEYS_AHEAD];
+        auto fetch = [&](int i) -> uint32_t {                       // whole warp; board i of this CTA (i < n_local)
             if ((i & 31) == 0 && i + lane < n_local) rqs = req[board_of(i + lane)];
             const uint32_t gx = __shfl_sync(0xffffffffu, rqs.x, i & 31), gy = __shfl_sync(0xffffffffu, rqs.y, i & 31);
-            uint32_t kw = 0;
-            if (lane < 12) kw = keys[((size_t)gx * M + (gy & 0x0fffffffu)) * KEY_WORDS + lane];
-            if (i >= NS) mbar_wait_warp(&bar_c1[slot], (uint32_t)((i - NS) / NS) & 1u);     // conv1 of the slot's previous board done => its key was consumed
-            if (lane < 12) sKey[slot * 16 + lane] = kw;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_k[slot]);
+            return lane < 12 ? keys[((size_t)gx * M + (gy & 0x0fffffffu)) * KEY_WORDS + lane] : 0u;
+        };
+#pragma unroll
+        for (int j = 0; j < TCC_KEYS_AHEAD; ++j) kq[j] = j < n_local ? fetch(j) : 0u;
+        for (int i0 = 0; i0 < n_local; i0 += TCC_KEYS_AHEAD) {
+#pragma unroll
+            for (int j = 0; j < TCC_KEYS_AHEAD; ++j) {
+                const int i = i0 + j;
+                if (i >= n_local) break;
+                const int slot = i % NS;
+                if (i >= NS) mbar_wait_warp(&bar_c1[slot], (uint32_t)((i - NS) / NS) & 1u);     // conv1 of the slot's previous board done => its key was consumed
+                if (lane < 12) sKey[slot * 16 + lane] = kq[j];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_k[slot]);
+                if (i + TCC_KEYS_AHEAD < n_local) kq[j] = fetch(i + TCC_KEYS_AHEAD);
+            }
         }
     } else {
         // ===================================================== workers (512 threads)

@@ -88,6 +88,14 @@ class BatchedEngine:
         L.check(L.lib().b200_get_games(self.h, L.ptr(recs)))
         return recs
 
+    def remove_nodes(self, min_free=2**31 - 1):
+        """TreeAgent.remove_nodes() (agents/agent.py:246-257) on every game with fewer than min_free free slots, batched."""
+        L.check(L.lib().b200_remove_nodes(self.h, int(min_free)))
+
+    def set_gc_headroom(self, min_free):
+        """update_root() then collects every game with fewer than min_free free slots (0 = the reference's lazy collection only)."""
+        L.check(L.lib().b200_set_gc_headroom(self.h, int(min_free)))
+
     def update_root(self, auto_reset=False):
         L.check(L.lib().b200_update_root(self.h, int(auto_reset)))
 
