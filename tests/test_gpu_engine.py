@@ -354,4 +354,7 @@ def test_replay_memory_filled_at_garbage_collection(gpu_lib, oracle):
     key = lambda a: a[np.lexsort(a.T[::-1])]
     assert np.array_equal(key(got), key(want))
     assert eng.replay_drain_into(buf.data_ptr(), 100000) == 0          # drained: memory_index = 0 (ValueSim.py:183)
+    from tetris_mcts_b200 import replay                                 # the same rows as ValueSim.memory arrays (ValueSim.py:25-30)
+    states, values, variance, weights = replay.rows_to_memory(got)
+    assert states.shape == (cnt, 1, 20, 10) and set(np.unique(states)) <= {-1.0, 0.0, 1.0} and (weights >= minv).all()
     eng.close()

@@ -1,6 +1,8 @@
 """agents.ValueSim — agents/ValueSim.py:12-99 (leaf itself evaluated, gamma=0.999, max_nodes=100000)."""
 from sys import stderr
 
+import numpy as np
+
 from .agent import TreeAgent
 from ..model.model_vv import init_weights
 
@@ -14,9 +16,25 @@ class ValueSim(TreeAgent):
         kwargs.pop("max_nodes", None)
         super().__init__(max_nodes=100000, gamma=gamma, low=1, weights=init_weights(0) if weights is None else weights, **kwargs)   # ValueSim.py:16
         self.online, self.min_visits_to_store = online, min_visits_to_store
-        if online and not self.benchmark:
-            print('online training (ValueSim.py:101-185) is outside the accelerated path (SURVEY 8f): samples can be drawn with '
-                  'BatchedEngine.collect_samples_into, no optimiser step is run here', **perr)
+        if online and not self.benchmark:                         # ValueSim.py:21-37: the replay memory lives on the device (k_gc fills it)
+            self._eng.replay_enable(min_visits=min_visits_to_store, capacity=memory_size)
+            print('online: samples are stored as in ValueSim.store_nodes (ValueSim.py:122-159); train_nodes() returns / dumps them, the '
+                  'optimiser step itself is outside the accelerated path (SURVEY 8f.2)', **perr)
+
+    def train_nodes(self, dump_data=True, path='./data/dump'):    # ValueSim.py:161-185, the data half: drain the stored samples
+        """Returns ValueSim.memory[:d_size] (states, values, variance, weights) and writes the reference's dump file
+        (ValueSim.py:176-177).  The optimiser step itself (model.train_data) is outside the accelerated path."""
+        import torch
+        from .. import replay
+        if not (self.online and not self.benchmark):
+            return replay.rows_to_memory(np.zeros((0, replay.SAMPLE_BYTES), np.uint8))
+        cap = 500000
+        buf = torch.zeros((cap, replay.SAMPLE_BYTES), dtype=torch.uint8, device="cuda")
+        n = self._eng.replay_drain_into(buf.data_ptr(), cap)
+        rows = buf[:n].cpu().numpy()
+        if dump_data and n:
+            replay.dump(path, rows)
+        return replay.rows_to_memory(rows)
 
     def evaluate_state(self, state):                              # ValueSim.py:46-50
         v, var = self._eng.valuenet(state[None])
