@@ -2,7 +2,14 @@
 import csv, subprocess, sys
 from collections import defaultdict
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
-out = []
+out = ["# ncu evidence, round 1 (build: final state of the round; commands: scripts/gpu_final.sh)",
+       "",
+       "Both captures run `bench.py --steps 1 --warmup 1 --sims 150|100` (16384 games): the FIRST two moves of every game, where the trees are",
+       "shallow (mean trace length 18-27 levels instead of the 65 of the default bench window, moves 4-9).  The tree kernels are therefore",
+       "cheaper here than in the bench line: events inside the same early window give select+expand 16 %, k_tc_conv 60 %, k_tc_fc 11 %,",
+       "backup 3 % (`phases_ms_per_step` of the bench line printed by the ncu --set full run, gpurun_out/ncu_full.log), against 15 / 70 / 11 / 3 %",
+       "in the serialised, cold-cache launch list below; in the default bench window the shares are 36 / 43 / 8 / 9 % (profiles/bench_r1_final.json).",
+       ""]
 rows = list(csv.reader(open("gpurun_out/launches_%s.csv" % tag)))
 h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[h]; ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -35,3 +42,20 @@ for r in rows[2:]:
             out.append("- %s = %s %s" % (w, r[hdr.index(w)], units[hdr.index(w)]))
 open("profiles/ncu_summary_%s.md" % tag, "w").write("\n".join(out) + "\n")
 print("\n".join(out))
+
+# per-launch DRAM traffic of the captured kernels -> profiles/ncu_traffic_<tag>.json (read by bench.py: roofline.traffic)
+import json
+scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+traffic = {}
+for r in rows[2:]:
+    name = r[hdr.index("Kernel Name")].split("(")[0]
+    def val(metric):
+        i = hdr.index(metric)
+        return float(r[i].replace(",", "")), units[i]
+    rd, ru = val("dram__bytes_read.sum"); wr, wu = val("dram__bytes_write.sum")
+    dur, du = val("gpu__time_duration.sum")
+    tp, _ = val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+    traffic[name] = {"dram_bytes": rd * scale.get(ru, 1.0) + wr * scale.get(wu, 1.0), "tensor_pipe_pct": tp,
+                     "duration_ms_under_ncu": dur * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(du, 1e-3)}
+traffic["_source"] = "profiles/ncu_summary_%s.md: ncu --set full --clock-control none, bench.py --steps 1 --warmup 1 --sims 100 (16384 games), one launch per kernel (scripts/gpu_final.sh)" % tag
+json.dump(traffic, open("profiles/ncu_traffic_%s.json" % tag, "w"), indent=1)
