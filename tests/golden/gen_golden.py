@@ -5,6 +5,9 @@
   agent_golden.npz    per-move statistics of the reference's own agents/ValueSimLP.py + agents/agent.py driving
                       the oracle env (the only non-reference part: pyTetris is absent upstream) with the synthetic
                       evaluator patched onto the agent instance (no reference file is modified)
+  agent_gc_golden.npz the same agent with the driver calling agent.remove_nodes() between moves (public method)
+  agent_modes_golden.npz  the reference's own agents/ValueSim.py and agents/Vanilla.py (the other two mcts loops); their
+                      rand() / randint draw from the oracle's xorshift stream (oracle/rand_shim.c, LD_PRELOAD)
 Run:  python tests/golden/gen_golden.py      (needs /root/reference and `make -C oracle`)"""
 import os
 import sys
@@ -177,6 +180,62 @@ def gen_agent_explicit_gc(pt):
     print("agent_gc_golden: %d cases, collections at moves %s" % (len(cases), [list(out["g%d_collected" % i])[:8] for i in range(len(cases))]))
 
 
+def gen_agent_modes(pt):
+    """The reference's own agents/ValueSim.py (leaf evaluated, check_low with low=1 draws rand()) and agents/Vanilla.py (random
+    rollouts via random.randint, check_low with low=5) on the oracle env.  Their random source is redirected to the oracle's
+    per-agent xorshift stream without touching a reference file: the process runs with oracle/_ref/librandshim.so LD_PRELOADed
+    (the reference's compiled core.cpp calls its rand()), and the module attribute Vanilla.randint is pointed at the same stream."""
+    import ctypes
+    shim = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "librandshim.so"))
+    shim.shim_next.restype = ctypes.c_uint32
+    shim.shim_seed.argtypes = [ctypes.c_uint32]
+    if ctypes.CDLL(None).rand != shim.rand and "librandshim" not in os.environ.get("LD_PRELOAD", ""):
+        raise RuntimeError("run with LD_PRELOAD=oracle/_ref/librandshim.so (gen_golden.py --agent-modes re-executes itself that way)")
+    import agents.Vanilla as RV
+    from agents.ValueSim import ValueSim
+    RV.randint = lambda a, b: a + int(shim.shim_next() % (b - a + 1))        # Vanilla.py:52 randint(0, n_actions - 1)
+    out = {}
+    cases = [dict(kind="single", M=6000, sims=40, moves=30, seed=123, search_seed=0x1234567),
+             dict(kind="vanilla", M=6000, sims=60, moves=30, seed=321, search_seed=0x7654321),
+             dict(kind="single", M=1500, sims=30, moves=40, seed=5, search_seed=99)]       # with garbage collection
+    for i, cs in enumerate(cases):
+        p = "m%d_" % i
+        game = pt.Tetris((20, 10), 1, 0, 0)
+        game.seed(cs["seed"])
+        if cs["kind"] == "single":
+            ag = ValueSim(sims=cs["sims"], env=pt.Tetris, env_args=((20, 10), 1, 0, 0), benchmark=False, online=False, min_visit=40)
+            ag.model.inference = synthetic_inference
+        else:
+            ag = RV.Vanilla(sims=cs["sims"], env=pt.Tetris, env_args=((20, 10), 1, 0, 0), benchmark=False, online=False, min_visit=40)
+        ag.max_nodes = cs["M"]
+        ag.init_array()
+        shim.shim_seed(cs["search_seed"])
+        out[p + "start"] = np.array(game.get_record(), np.uint32)
+        ag.update_root(game)
+        acts, stats = [], []
+        for mv in range(cs["moves"]):
+            a = ag.play()
+            acts.append(int(a))
+            stats.append(ag.get_stats())
+            game.play(a)
+            ag.update_root(game)
+            if game.end:
+                game.reset()
+                ag.update_root(game)
+        out[p + "mode"] = 1 if cs["kind"] == "single" else 2
+        out[p + "M"], out[p + "sims"], out[p + "search_seed"] = cs["M"], cs["sims"], cs["search_seed"]
+        out[p + "actions"], out[p + "stats"] = np.array(acts, np.int32), np.stack(stats).astype(np.float32)
+        for k in ("child", "score", "episode"):
+            out[p + k] = ag.arrays[k]
+        out[p + "n2o"] = ag.node_to_obs
+        for k in ("visit", "value", "variance"):
+            out[p + k] = ag.obs_arrays[k]
+        out[p + "root"] = ag.root
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, "agent_modes_golden.npz"), **out)
+    print("agent_modes_golden: %d cases (ValueSim.py, Vanilla.py, ValueSim.py with collections)" % len(cases))
+
+
 def gen_dist():
     """Outputs of the reference's own numba cores (agents/core_distributional.py) on seeded inputs."""
     import agents.core_distributional as R
@@ -219,14 +278,24 @@ def gen_dist():
 
 if __name__ == "__main__":
     O.build(ref=True)
+    shim_path = os.path.join(ROOT, "oracle", "_ref", "librandshim.so")
+    if "--agent-modes" in sys.argv and "librandshim" not in os.environ.get("LD_PRELOAD", ""):
+        # the ValueSim.py / Vanilla.py goldens need the reference's rand() on the oracle's stream: re-execute with the shim preloaded
+        # (only this generator: the other goldens are produced with the process's ordinary libc)
+        os.environ["LD_PRELOAD"] = shim_path + (":" + os.environ["LD_PRELOAD"] if os.environ.get("LD_PRELOAD") else "")
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     pt, core = O.mount_reference()
     if "--dist" in sys.argv:
         gen_dist()
     elif "--agent-gc" in sys.argv:
         gen_agent_explicit_gc(pt)
+    elif "--agent-modes" in sys.argv:
+        gen_agent_modes(pt)
     else:
         gen_core(core)
         gen_valuenet()
         gen_agent(pt)
         gen_agent_explicit_gc(pt)
         gen_dist()
+        import subprocess
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-modes"], check=True)

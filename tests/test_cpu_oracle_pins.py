@@ -100,6 +100,37 @@ def test_agent_explicit_remove_nodes_golden(oracle):
         assert ag.root == int(z[p + "root"])
 
 
+def test_agent_modes_golden(oracle):
+    """The other two mcts loops: the C agent in MODE_SINGLE / MODE_VANILLA vs the reference's own agents/ValueSim.py and
+    agents/Vanilla.py, whose rand() (check_low, core.h:62,76) and randint (Vanilla.py:52) were served from the oracle's xorshift
+    stream when the golden was generated (oracle/rand_shim.c, gen_agent_modes) — exact, including a case with collections."""
+    z = np.load(os.path.join(GOLD, "agent_modes_golden.npz"))
+    for case in range(int(z["n_cases"])):
+        p = "m%d_" % case
+        mode = int(z[p + "mode"])
+        ag = oracle.Agent(max_nodes=int(z[p + "M"]), mode=mode, gamma=0.999 if mode == 1 else 0.99, low=1 if mode == 1 else 5,
+                          eval_mode=0, search_seed=int(z[p + "search_seed"]))
+        g = oracle.Game(record=z[p + "start"])
+        ag.update_root(g.record())
+        for mv, act in enumerate(z[p + "actions"]):
+            ag.mcts(int(z[p + "sims"]))
+            a, st = ag.get_action()
+            assert a == act and np.array_equal(st, z[p + "stats"][mv]), (case, mv)
+            g.play(a)
+            ag.update_root(g.record())
+            if g.end:
+                g.reset()
+                ag.update_root(g.record())
+        ex = ag.export()
+        for k in ("child", "score", "n2o", "visit", "value", "variance", "episode"):
+            assert np.array_equal(ex[k], z[p + k]), (case, k)
+        assert ag.root == int(z[p + "root"])
+        if case == 1:
+            assert ag.counter(5) > 1000, "the Vanilla case must roll out"
+        if case == 2:
+            assert ag.counter(3) > 0, "the small-arena case must collect garbage"
+
+
 def test_env_spec_examples(oracle):
     """Hand-checkable rules of SPEC_PYTETRIS.md §2-4."""
     g = oracle.Game(1, 0, 0, seed=7)

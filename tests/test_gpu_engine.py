@@ -157,6 +157,35 @@ def test_against_reference_python_agent_golden(gpu_lib):
         eng.close()
 
 
+GOLD_MODES = os.path.join(os.path.dirname(__file__), "golden", "agent_modes_golden.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLD_MODES), reason="golden vectors not generated")
+def test_against_reference_valuesim_and_vanilla_golden(gpu_lib):
+    """The other two mcts loops straight against the reference's own agents/ValueSim.py and agents/Vanilla.py (golden generated with
+    their rand() / randint served from the xorshift stream the engine uses per game: oracle/rand_shim.c, gen_agent_modes):
+    check_low picks, rollouts, leaf evaluation, collections — per-move statistics, actions and the final arrays, exact."""
+    from tetris_mcts_b200.engine import BatchedEngine
+    z = np.load(GOLD_MODES)
+    for case in range(int(z["n_cases"])):
+        p = "m%d_" % case
+        mode = {1: "single", 2: "vanilla"}[int(z[p + "mode"])]
+        seed = (int(z[p + "search_seed"]) - 0x9E3779B9) & 0xffffffff          # k_init_arena: srng[g] = seed + 0x9E3779B9 * (g + 1)
+        eng = BatchedEngine(1, max_nodes=int(z[p + "M"]), mode=mode, eval_kind="synthetic", seed=seed)
+        eng.set_games(z[p + "start"][None, :].astype(np.uint32))
+        for mv, act in enumerate(z[p + "actions"]):
+            eng.run_sims(int(z[p + "sims"]))
+            stats, action = eng.get_stats()
+            assert action[0] == act and np.array_equal(stats[0], z[p + "stats"][mv]), (case, mv)
+            eng.env_step(None)
+            eng.update_root(True)
+        ex = eng.export_game(0)
+        for k in ("child", "score", "n2o", "visit", "value", "variance", "episode"):
+            assert np.array_equal(ex[k], z[p + k]), (case, k)
+        assert ex["root"] == int(z[p + "root"])
+        eng.close()
+
+
 def test_full_size_properties(gpu_lib):
     """BASELINE config sizes are too large for the oracle; check size-independent invariants instead:
     every simulation adds exactly one visit to the root observation, child visits never exceed the root's,
