@@ -6,6 +6,7 @@
                       the oracle env (the only non-reference part: pyTetris is absent upstream) with the synthetic
                       evaluator patched onto the agent instance (no reference file is modified)
   agent_gc_golden.npz the same agent with the driver calling agent.remove_nodes() between moves (public method)
+  agent_cpp_golden.npz  actions / game records of the reference's own C++ agent twin (agents/cppmodule/agent.cpp compiled unchanged)
   agent_modes_golden.npz  the reference's own agents/ValueSim.py and agents/Vanilla.py (the other two mcts loops); their
                       rand() / randint draw from the oracle's xorshift stream (oracle/rand_shim.c, LD_PRELOAD)
 Run:  python tests/golden/gen_golden.py      (needs /root/reference and `make -C oracle`)"""
@@ -236,6 +237,44 @@ def gen_agent_modes(pt):
     print("agent_modes_golden: %d cases (ValueSim.py, Vanilla.py, ValueSim.py with collections)" % len(cases))
 
 
+def gen_agent_cpp(pt):
+    """The reference's own C++ agent twin (agents/cppmodule/agent.cpp compiled unchanged -> oracle/_ref/agent*.so): MCTSAgent with
+    leaf parallelisation and the synthetic evaluator as its Python callback.  Its LP backup differs from the Python path in two
+    places (`end` read from the observation, agent.cpp:538; variance averaged without gamma^2, agent.cpp:558) — the
+    flags lp_end_from_obs / lp_var_gamma2 of oracle and engine.  The module only exposes play(), so the pinned quantities are
+    the action and the game record after every move (arena large enough that its remove_nodes, defective per SURVEY N2, never runs)."""
+    agent_mod = O.load_ref_module("agent")
+
+    def evaluator(obs):                                   # agent.cpp:430-434: char[k,1,20,10] -> [values, variances]
+        v, var = synthetic_inference(np.asarray(obs).astype(np.int8))
+        return [v[:, 0].tolist(), var[:, 0].tolist()]
+
+    out = {}
+    cases = [dict(sims=60, moves=50, seed=123), dict(sims=25, moves=120, seed=4242)]
+    for i, cs in enumerate(cases):
+        p = "c%d_" % i
+        game = pt.Tetris((20, 10), 1, 0, 0)
+        game.seed(cs["seed"])
+        ag = agent_mod.MCTSAgent(cs["sims"], 100000, True, 0.999, True, evaluator, 0, True)   # sims, max_nodes, projection, gamma, benchmark, eval, type, LP
+        out[p + "start"] = np.array(game.get_record(), np.uint32)
+        ag.update_root(game)
+        acts, recs = [], []
+        for mv in range(cs["moves"]):
+            a = ag.play()
+            acts.append(int(a))
+            game.play(a)
+            recs.append(np.array(game.get_record(), np.uint32))
+            ag.update_root(game)
+            if game.end:
+                game.reset()
+                ag.update_root(game)
+        out[p + "sims"] = cs["sims"]
+        out[p + "actions"], out[p + "records"] = np.array(acts, np.int32), np.stack(recs)
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(HERE, "agent_cpp_golden.npz"), **out)
+    print("agent_cpp_golden: %d cases, %s moves" % (len(cases), [c["moves"] for c in cases]))
+
+
 def gen_dist():
     """Outputs of the reference's own numba cores (agents/core_distributional.py) on seeded inputs."""
     import agents.core_distributional as R
@@ -291,11 +330,14 @@ if __name__ == "__main__":
         gen_agent_explicit_gc(pt)
     elif "--agent-modes" in sys.argv:
         gen_agent_modes(pt)
+    elif "--agent-cpp" in sys.argv:
+        gen_agent_cpp(pt)
     else:
         gen_core(core)
         gen_valuenet()
         gen_agent(pt)
         gen_agent_explicit_gc(pt)
+        gen_agent_cpp(pt)
         gen_dist()
         import subprocess
         subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-modes"], check=True)

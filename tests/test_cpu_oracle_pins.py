@@ -131,6 +131,45 @@ def test_agent_modes_golden(oracle):
             assert ag.counter(3) > 0, "the small-arena case must collect garbage"
 
 
+def test_agent_cpp_golden(oracle):
+    """The reference's C++ agent twin (agents/cppmodule/agent.cpp, compiled unchanged, leaf-parallel MCTSAgent) vs the C agent with
+    lp_end_from_obs=1 (agent.cpp:538) and lp_var_gamma2=0 (agent.cpp:558): the flags the engine exposes for that behaviour
+    (SURVEY N1).  The module exposes play() only: the action and the game record after every move must agree."""
+    z = np.load(os.path.join(GOLD, "agent_cpp_golden.npz"))
+    for case in range(int(z["n_cases"])):
+        p = "c%d_" % case
+        ag = oracle.Agent(max_nodes=100000, mode=0, gamma=0.999, low=1, eval_mode=0, lp_end_from_obs=1, lp_var_gamma2=0)
+        g = oracle.Game(record=z[p + "start"])
+        ag.update_root(g.record())
+        for mv, act in enumerate(z[p + "actions"]):
+            ag.mcts(int(z[p + "sims"]))
+            a, _ = ag.get_action()
+            assert a == act, (case, mv)
+            g.play(a)
+            assert np.array_equal(g.record(), z[p + "records"][mv]), (case, mv)
+            ag.update_root(g.record())
+            if g.end:
+                g.reset()
+                ag.update_root(g.record())
+    # the Python-path flags give a different game on the same seed: the golden does discriminate between the two variants
+    ag = oracle.Agent(max_nodes=100000, mode=0, gamma=0.999, low=1, eval_mode=0)
+    g = oracle.Game(record=z["c1_start"])
+    ag.update_root(g.record())
+    same = True
+    for mv, act in enumerate(z["c1_actions"]):
+        ag.mcts(int(z["c1_sims"]))
+        a, _ = ag.get_action()
+        if a != act:
+            same = False
+            break
+        g.play(a)
+        ag.update_root(g.record())
+        if g.end:
+            g.reset()
+            ag.update_root(g.record())
+    assert not same
+
+
 def test_env_spec_examples(oracle):
     """Hand-checkable rules of SPEC_PYTETRIS.md §2-4."""
     g = oracle.Game(1, 0, 0, seed=7)
