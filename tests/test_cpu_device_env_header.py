@@ -15,10 +15,10 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
-@pytest.fixture(scope="module")
-def host_env(tmp_path_factory):
+@pytest.fixture(scope="module", params=[(), ("-DB200_PLAY_UNIFIED=0",)], ids=["default", "branchy-step"])
+def host_env(request, tmp_path_factory):
     so = str(tmp_path_factory.mktemp("hostenv") / "host_env.so")
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(ROOT, "tetris_mcts_b200", "csrc"),
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", *request.param, "-I", os.path.join(ROOT, "tetris_mcts_b200", "csrc"),
                     os.path.join(HERE, "host_env_shim.cpp"), "-o", so], check=True)
     return C.CDLL(so)
 
@@ -34,6 +34,8 @@ def test_device_header_steps_like_the_oracle(host_env, env_args):
     for step in range(300):
         p = [0.1, 0.1, 0.1, 0.1, 0.1, 0.35, 0.15] if step % 2 else [1 / 7] * 7   # every other step is rich in hard drops
         a = rng.choice(7, size=n, p=p).astype(np.int32)
+        if step % 10 == 3:
+            a[::9] = 7                                                              # VanillaC.py:7 draws randint(0, 7): an id outside 0..6 is a no-op
         want = O.play_records(recs, a)
         got = recs.copy()
         host_env.host_play_records(got.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p), n)

@@ -161,9 +161,43 @@ __device__ __forceinline__ void lock_piece(Game &g) {   // SPEC §3.3
 }
 
 // One environment step (SPEC §3).  The reference entry point is Tetris.play(action).
+// In an expansion the seven lanes of a group play the seven different actions, so every action-specific branch is executed
+// serially by the warp.  The step is therefore written with ONE collision test for all shifting / rotating / soft-drop actions
+// (a candidate position per action, accepted if it does not collide; action 0 proposes the current position) and ONE lock_piece
+// site shared by the hard drop and by gravity; only the hard drop's distance computation is a branch of its own.
+#ifndef B200_PLAY_UNIFIED
+#define B200_PLAY_UNIFIED 1
+#endif
 __device__ __forceinline__ void play(Game &g, int action) {
     if (g.end) return;
     uint32_t shape = shape_of(g.piece, g.rot);
+#if B200_PLAY_UNIFIED
+    bool lock = false;
+    if (action == 5) {   // hard drop
+        const int d = drop_distance(g.w, shape, g.px, g.py);
+        g.py += d;
+        if (g.scoring == 0) g.score += 2 * d;
+        g.dropcnt = 0;
+        lock = true;
+    } else {
+        const bool rotate = action == 3 || action == 4;
+        const int nr = rotate ? ((g.rot + (action == 3 ? 1 : 3)) & 3) : g.rot;
+        const uint32_t ns = rotate ? shape_of(g.piece, nr) : shape;
+        const int nx = g.px + (action == 2 ? 1 : 0) - (action == 1 ? 1 : 0);
+        const int ny = g.py + (action == 6 ? 1 : 0);
+        if (!collides(g.w, ns, nx, ny)) {          // action 0 (and any action code outside 1..6) proposes the current, legal position
+            g.rot = nr; shape = ns; g.px = nx;
+            if (ny != g.py) { g.py = ny; if (g.scoring == 0) g.score += 1; }
+        }
+        g.dropcnt += 1;
+        if (g.dropcnt >= g.app) {
+            g.dropcnt = 0;
+            if (!collides(g.w, shape, g.px, g.py + 1)) g.py += 1;
+            else lock = true;
+        }
+    }
+    if (lock) lock_piece(g);
+#else
     if (action == 5) {   // hard drop
         const int d = drop_distance(g.w, shape, g.px, g.py);
         g.py += d;
@@ -187,6 +221,7 @@ __device__ __forceinline__ void play(Game &g, int action) {
         if (!collides(g.w, shape, g.px, g.py + 1)) g.py += 1;
         else lock_piece(g);
     }
+#endif
 }
 
 // ---- SPEC §6 packed record <-> registers
