@@ -212,7 +212,9 @@ def run_reference(args, cfg):
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg["config"],
             "cpu_baseline": {"value": value, "unit": "sims/s", "cores": pool.P, "kind": "reference", "sample": sample},
-            "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "reference_arm": "the reference's own compiled agents/cppmodule/agent.cpp (one game per single-threaded worker process, max_nodes and "
+                             "collection as the reference does them) + torch fp32 CPU value net; `config` is the B200 arm's, for the ratio"}
     print(json.dumps(line), flush=True)
 
 
