@@ -31,11 +31,31 @@ ENV_ARGS = ((20, 10), 1, 0, 0)                   # play.py:75 defaults
 BASE_SEED = 123                                  # SURVEY §8d (echoes agent.cpp:23)
 
 
+TC_ISSUED_FLOP_PER_BOARD = 2 * 128 * 16 * (96 * 36 + 64 * 2)   # k_tc_conv: 2x18 MMAs of 128x96x16 + 2 of 128x64x16 per board
+ARENA_BYTES_PER_SLOT = 324
+
+
+def _ncu_traffic_file():
+    for name in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return p
+    return None
+
+
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
     try:
-        return json.load(open(p)).get(kernel, {}).get("dram_bytes")
+        return json.load(open(_ncu_traffic_file())).get(kernel, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
+def ncu_traffic_src():
+    """Which capture `traffic` comes from and the regime it was taken in (bench window or not)."""
+    try:
+        p = _ncu_traffic_file()
+        return {"file": os.path.relpath(p, ROOT), "regime": json.load(open(p)).get("_regime", "round-1 capture: moves 0-1 at 100-150 sims (NOT the bench window)")}
     except Exception:
         return None
 
@@ -93,6 +113,16 @@ class Clocks:
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+def ref_agent_moves(workload, sims, max_nodes):
+    """Moves a reference agent object may play before it is replaced by a fresh one (same class, same arguments, re-rooted at the
+    live game).  Why: the reference's arena cannot survive a long game — once the reachable set fills max_nodes its own
+    remove_nodes() frees nothing, agent.cpp:227-231 prints MAX_NODES EXCEEDED and calls available.back() on an empty vector
+    (undefined behaviour: the round-1 arm segfaulted there at ~60 moves), and agent.cpp:300-301 doubles `occupied` on the way.
+    A simulation creates at most 7 nodes (agent.cpp:201-208) and update_root one, so max_nodes // (7*sims + 1) moves can never
+    exhaust the free list: the unmodified reference code then never reaches its overflow path."""
+    return max(1, max_nodes // (7 * sims + 1))
+
+
 def _ref_worker(conn, wid, workload, sims):
     """One single-threaded worker = one play.py-equivalent process on the reference's compiled C++ agent."""
     try:
@@ -107,29 +137,43 @@ def _ref_worker(conn, wid, workload, sims):
         game = pt.Tetris(*ENV_ARGS)
         game.seed(BASE_SEED + wid)
         if workload == "vanilla":                        # agents/VanillaC.py:5-13
+            max_nodes = 500000
+
             def random_playout(g):
                 while not g.end:
                     g.play(randint(0, 7))
                 return g.score, 1e5
-            agent = agent_mod.MCTSAgent(sims, 500000, True, 0.99, True, random_playout, 1, False)
+
+            def make_agent():
+                return agent_mod.MCTSAgent(sims, max_nodes, True, 0.99, True, random_playout, 1, False)
         else:                                            # agents/ValueSimC.py:17-42 (LP=True, evaluator = Model_VV.inference)
             from ref_net import RefModel
+            max_nodes = 100000
             model = RefModel(O.weights_to_state_dict(O.seeded_weights(0)))
-            agent = agent_mod.OnlineMCTSAgent(sims=sims, max_nodes=100000, online=False, accumulation_policy=3, memory_size=1,
-                                              episodes_per_train=25, memory_growth_rate=5000, min_visit=25, projection=True, gamma=0.999,
-                                              benchmark=True, evaluator=model.inference, evaluation_type=0, train=(lambda *a: None), LP=True)
+
+            def make_agent():
+                return agent_mod.OnlineMCTSAgent(sims=sims, max_nodes=max_nodes, online=False, accumulation_policy=3, memory_size=1,
+                                                 episodes_per_train=25, memory_growth_rate=5000, min_visit=25, projection=True, gamma=0.999,
+                                                 benchmark=True, evaluator=model.inference, evaluation_type=0, train=(lambda *a: None), LP=True)
+        renew_after = ref_agent_moves(workload, sims, max_nodes)
+        agent = make_agent()
         agent.update_root(game)
+        age = 0
         conn.send("ready")
         while True:
             msg = conn.recv()
             if msg[0] == "stop":
                 break
-            done, t0 = 0, time.perf_counter()
+            done, renewed, t0 = 0, 0, time.perf_counter()
             if msg[0] == "moves":
                 budget_moves, budget_s = msg[1], 1e18
             else:
                 budget_moves, budget_s = 1 << 30, msg[1]
             while done < budget_moves and time.perf_counter() - t0 < budget_s:
+                if age >= renew_after:                   # inside the timed region: constructing the agent is part of the reference's cost
+                    agent = make_agent()
+                    agent.update_root(game)
+                    age, renewed = 0, renewed + 1
                 a = agent.play()
                 game.play(a)
                 agent.update_root(game)
@@ -137,35 +181,89 @@ def _ref_worker(conn, wid, workload, sims):
                     game.reset()
                     agent.update_root(game)
                 done += 1
-            conn.send((done * sims, time.perf_counter() - t0))
+                age += 1
+            conn.send((done * sims, time.perf_counter() - t0, renewed))
     except Exception as ex:   # noqa
-        conn.send(("error", repr(ex)))
+        try:
+            conn.send(("error", repr(ex)))
+        except Exception:
+            pass
 
 
 class RefPool:
+    """P single-threaded worker processes.  A worker that dies (the reference's C++ can take the whole process down) is
+    detected through its pipe / exit code, replaced by a fresh worker, and its unfinished sample counts as zero simulations."""
+
     def __init__(self, workload, sims, procs=None):
         self.P = procs or os.cpu_count() or 1
-        ctx = mp.get_context("spawn")
-        self.conns, self.procs = [], []
+        self.workload, self.sims = workload, sims
+        self.ctx = mp.get_context("spawn")
+        self.conns, self.procs = [None] * self.P, [None] * self.P
+        self.restarts, self.renewals = 0, 0
         for w in range(self.P):
-            a, b = ctx.Pipe()
-            p = ctx.Process(target=_ref_worker, args=(b, w, workload, sims), daemon=True)
-            p.start()
-            self.conns.append(a)
-            self.procs.append(p)
-        for c in self.conns:
-            r = c.recv()
-            if r != "ready":
+            self._spawn(w)
+        for w in range(self.P):
+            self._wait_ready(w)
+
+    def _spawn(self, w):
+        a, b = self.ctx.Pipe()
+        p = self.ctx.Process(target=_ref_worker, args=(b, w, self.workload, self.sims), daemon=True)
+        p.start()
+        b.close()                                        # so that a dead child gives EOF instead of a hang
+        self.conns[w], self.procs[w] = a, p
+
+    def _wait_ready(self, w, tries=3):
+        for _ in range(tries):
+            try:
+                r = self.conns[w].recv()
+                if r == "ready":
+                    return
                 raise RuntimeError("reference worker failed: %r" % (r,))
+            except (EOFError, OSError):
+                self._spawn(w)
+        raise RuntimeError("reference worker %d cannot start" % w)
+
+    def _restart(self, w):
+        self.restarts += 1
+        try:
+            self.conns[w].close()
+        except Exception:
+            pass
+        if self.procs[w].is_alive():
+            self.procs[w].kill()
+        self.procs[w].join(timeout=5)
+        self._spawn(w)
+        self._wait_ready(w)
 
     def run(self, kind, amount):
-        for c in self.conns:
-            c.send((kind, amount))
-        res = [c.recv() for c in self.conns]
-        for r in res:
-            if r[0] == "error":
-                raise RuntimeError("reference worker failed: %s" % r[1])
-        return sum(r[0] for r in res), max(r[1] for r in res)
+        """Every worker runs `amount` moves (kind == 'moves') or seconds; returns (simulations done, slowest worker's seconds)."""
+        from multiprocessing.connection import wait
+        pending = {}
+        for w in range(self.P):
+            try:
+                self.conns[w].send((kind, amount))
+                pending[self.conns[w]] = w
+            except (BrokenPipeError, OSError):
+                self._restart(w)
+        t0 = time.perf_counter()
+        n_tot, t_max = 0, 0.0
+        while pending:
+            for c in wait(list(pending), timeout=5.0):
+                w = pending.pop(c)
+                try:
+                    r = c.recv()
+                except (EOFError, OSError):
+                    r = None
+                if r is None or r[0] == "error":          # died inside the reference's code: replace it, its sample is lost
+                    if r is not None:
+                        sys.stderr.write("reference worker %d: %s\n" % (w, r[1]))
+                    self._restart(w)
+                    t_max = max(t_max, time.perf_counter() - t0)
+                    continue
+                n_tot += r[0]
+                t_max = max(t_max, r[1])
+                self.renewals += r[2]
+        return n_tot, t_max
 
     def close(self):
         for c in self.conns:
@@ -175,6 +273,15 @@ class RefPool:
                 pass
         for p in self.procs:
             p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+
+
+REF_ARM_NOTE = ("the reference's own compiled agents/cppmodule/agent.cpp (oracle/_ref, unmodified) driven as agents/ValueSimC.py:17-42 / VanillaC.py:5-13 "
+                "do: one game per single-threaded worker process, one worker per host core, torch fp32 CPU value net as the evaluator callback; "
+                "env = the oracle restatement of pyTetris (absent upstream).  The agent object is replaced by a fresh one (same arguments, "
+                "re-rooted at the live game, construction inside the timed region) every max_nodes // (7*sims+1) moves so that the reference never "
+                "reaches its arena-overflow path (agent.cpp:224-231, undefined behaviour); a worker that dies anyway is restarted and its sample lost")
 
 
 def cpu_baseline(workload, sims, seconds):
@@ -186,7 +293,8 @@ def cpu_baseline(workload, sims, seconds):
         pool.close()
     return {"value": n / t, "unit": "sims/s", "cores": pool.P, "kind": "reference",
             "sample": "%d single-threaded workers x ~%.0f s of %s at %d sims/move on the reference's compiled agent.cpp + torch fp32 CPU net "
-                      "(env = oracle restatement: pyTetris is absent upstream); %d sims total" % (pool.P, seconds, workload, sims, n)}
+                      "(env = oracle restatement: pyTetris is absent upstream); %d sims total; %d worker restarts"
+                      % (pool.P, seconds, workload, sims, n, pool.restarts)}
 
 
 def run_reference(args, cfg):
@@ -199,6 +307,7 @@ def run_reference(args, cfg):
         moves_per_step = args.ref_moves_per_step
         for _ in range(args.warmup):
             pool.run("moves", moves_per_step)
+        r0, n0 = pool.restarts, pool.renewals
         tot_n, tot_t = 0, 0.0
         for _ in range(args.steps):
             n, t = pool.run("moves", moves_per_step)
@@ -206,20 +315,28 @@ def run_reference(args, cfg):
             tot_t += t
     finally:
         pool.close()
-    value = tot_n / tot_t
-    sample = "%d workers x %d moves x %d sims per step" % (pool.P, moves_per_step, sims)
+    value = tot_n / max(tot_t, 1e-9)
+    max_nodes = 500000 if cfg["workload_key"] == "vanilla" else 100000
+    sample = ("%d workers x %d moves x %d sims per step; agent renewed every %d moves (%d renewals, %d worker restarts in the timed steps)"
+              % (pool.P, moves_per_step, sims, ref_agent_moves(cfg["workload_key"], sims, max_nodes), pool.renewals - n0, pool.restarts - r0))
     line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg["config"],
             "cpu_baseline": {"value": value, "unit": "sims/s", "cores": pool.P, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-            "reference_arm": "the reference's own compiled agents/cppmodule/agent.cpp (one game per single-threaded worker process, max_nodes and "
-                             "collection as the reference does them) + torch fp32 CPU value net; `config` is the B200 arm's, for the ratio"}
+            "reference_arm": REF_ARM_NOTE + "; `config` is the B200 arm's, for the ratio"}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args, cfg):
+    """Three passes over the SAME workload: the search is deterministic given the seeds, so every pass builds an
+    identical engine from the same seeds, plays the same W warm-up moves and then the same K moves:
+      pass 1  `value`: production path (one CUDA graph per simulation step), inputs resident in HBM, CUDA events on the engine stream
+      pass 2  per-kernel launch durations (an event pair around every kernel, direct launches) for the roofline figures
+      pass 3  `e2e`: the public API with HOST buffers — H2D of the games, D2H of actions / statistics / games every move, plus the
+              path's one exchange step (replay rows drained from the device memory k_gc fills -> all-gather over NCCL when N > 1)
+    The per-pass counters (simulations, expansions, evaluations, trace levels) must agree, and the line says so (`same_workload`)."""
     import torch
     from tetris_mcts_b200 import distributed as D
     from tetris_mcts_b200 import pyTetris as PT
@@ -236,16 +353,23 @@ def run_b200(args, cfg):
     if cfg["mode"] == "dist":
         from tetris_mcts_b200.agents.DistValueSimOnline import init_dist_weights
         dist_w = init_dist_weights(0, 50)
-    eng = BatchedEngine(G, max_nodes=M, mode=cfg["mode"], eval_kind=cfg["eval"], weights=init_weights(0) if cfg["mode"] in ("lp", "single") else None,
-                        dist_weights=dist_w, env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank, device=local_rank, rollout_variance=1e3, overflow_reset=True)
-    eng.set_games(recs)
-    eng.set_gc_headroom(cfg["gc_headroom"])
+    weights = init_weights(0) if cfg["mode"] in ("lp", "single") else None
+
+    def fresh_engine():
+        e = BatchedEngine(G, max_nodes=M, mode=cfg["mode"], eval_kind=cfg["eval"], weights=weights, dist_weights=dist_w, env_args=ENV_ARGS,
+                          seed=BASE_SEED + 7919 * rank, device=local_rank, rollout_variance=1e3, overflow_reset=True)
+        e.set_games(recs)
+        e.set_gc_headroom(cfg["gc_headroom"])
+        return e
+
+    WORK_KEYS = ("sims", "expansions", "eval_requests", "trace_levels", "new_nodes", "gcs", "tree_resets")
+    # ---- pass 1: device-timed region (inputs resident in HBM, no host buffers)
+    eng = fresh_engine()
     for _ in range(args.warmup):
         eng.play_move(sims, auto_reset=True, want_stats=False)
     eng.sync()
-    # ---- device-timed region: inputs resident in HBM, no host buffers; the production path (one captured CUDA graph per
-    # simulation step, no per-kernel events), timed with CUDA events on the engine's own stream
     c0 = eng.counters()
+    eng.set_timing(False)                      # zeroes the launch counters
     D.barrier()
     torch.cuda.synchronize()
     with Clocks(local_rank) as clk:
@@ -256,12 +380,17 @@ def run_b200(args, cfg):
     torch.cuda.synchronize()
     D.barrier()
     c1 = eng.counters()
+    launches = sum(n for _, n in eng.phase_ms().values())
     ms_max = D.max_over_ranks(ms, dev)
     delta = {k: c1[k] - c0[k] for k in c1}
     tot = D.sum_over_ranks(delta, dev)
     value = tot["sims"] / (ms_max / 1e3)
-    # ---- instrumented pass: the same K steps again with a CUDA event pair around every kernel (direct launches), for the
-    # per-kernel launch durations the roofline figures are computed from.  Not part of `value`.
+    eng.close()
+    # ---- pass 2: the same K moves with a CUDA event pair around every kernel.  Not part of `value`.
+    eng = fresh_engine()
+    for _ in range(args.warmup):
+        eng.play_move(sims, auto_reset=True, want_stats=False)
+    eng.sync()
     eng.set_timing(True)
     p0 = eng.counters()
     eng.timer_start()
@@ -272,36 +401,54 @@ def run_b200(args, cfg):
     eng.set_timing(False)
     p1 = eng.counters()
     pdelta = {k: p1[k] - p0[k] for k in p1}
-    # ---- end-to-end region: the public API with HOST buffers, H2D of the games and D2H of the results every step
+    eng.close()
+    # ---- pass 3: end to end through the public API with HOST buffers; the exchange step inside the loop
+    eng = fresh_engine()
+    cap = args.exchange_rows
+    eng.replay_enable(min_visits=25, capacity=4 * cap)            # ValueSimLP.py:11 min_visits_to_store=25; filled by k_gc (ValueSim.py:101-159)
+    block = torch.empty((cap, D.SAMPLE_BYTES), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()                                       # the buffer is handed to the engine's own stream (no cross-stream race)
     pin_recs = torch.empty((G, 20), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
-    pin_recs[:] = eng.get_games()
+    pin_recs[:] = recs
+    gather_ms, rows_seen = [], 0
+
+    def e2e_step(timed):
+        nonlocal rows_seen
+        eng.set_games(pin_recs)                                   # H2D G*80 B + update_root
+        actions, stats = eng.play_move(sims, auto_reset=True)     # D2H G*(4+84) B
+        pin_recs[:] = eng.get_games()                             # D2H G*80 B
+        n_local = eng.replay_drain_into(block.data_ptr(), cap)    # device -> device, rows stored by this move's collections
+        tg = time.perf_counter()
+        rows, counts = D.allgather_samples(block, n_local)
+        torch.cuda.synchronize()                                  # the block is rewritten by the engine's stream next move
+        if timed:
+            gather_ms.append((time.perf_counter() - tg) * 1e3)
+            rows_seen += int(rows.shape[0])
+
+    for _ in range(args.warmup):
+        e2e_step(False)
+    eng.sync()
     e0 = eng.counters()
     D.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.set_games(pin_recs)                                   # H2D G*80 B + update_root
-        actions, stats = eng.play_move(sims, auto_reset=True)     # D2H G*(4+84) B
-        pin_recs[:] = eng.get_games()                             # D2H G*80 B
+        e2e_step(True)
     eng.sync()
     torch.cuda.synchronize()
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
     D.barrier()
     e1 = eng.counters()
-    e2e_sims = D.sum_over_ranks({"sims": e1["sims"] - e0["sims"]}, dev)["sims"]
-    # ---- the one exchange step: all-gather of fixed-size replay-sample blocks (212-byte rows), outside the timed regions
-    cap = 65536
-    block = torch.zeros((cap, D.SAMPLE_BYTES), dtype=torch.uint8, device=dev)
-    n_local = eng.collect_samples_into(block.data_ptr(), cap, 25)          # ValueSimLP.py:11 min_visits_to_store=25
-    torch.cuda.synchronize()
-    D.barrier()
-    tg = time.perf_counter()
-    rows, counts = D.allgather_samples(block, n_local)
-    torch.cuda.synchronize()
-    tg = D.max_over_ranks(time.perf_counter() - tg, dev)
-    traj = {"samples_total": int(rows.shape[0]), "samples_per_rank": counts, "block_bytes_per_rank": cap * D.SAMPLE_BYTES,
-            "ms": tg * 1e3, "backend": "nccl" if world > 1 else "none"}
-    launches = sum(n for _, n in phases.values())
+    edelta = {k: e1[k] - e0[k] for k in e1}
+    e2e_sims = D.sum_over_ranks({"sims": edelta["sims"]}, dev)["sims"]
+    eng.close()
+    same = all(delta[k] == pdelta[k] == edelta[k] for k in WORK_KEYS)
+    gather_ms_max = [D.max_over_ranks(x, dev) for x in gather_ms]
+    rows_tot = D.sum_over_ranks({"r": rows_seen}, dev)["r"] / max(world, 1)       # every rank sees all rows after the gather
+    traj = {"rows_per_step": rows_tot / max(args.steps, 1), "block_bytes_per_rank": cap * D.SAMPLE_BYTES,
+            "ms_median": statistics.median(gather_ms_max) if gather_ms_max else None, "ms_max": max(gather_ms_max) if gather_ms_max else None,
+            "iterations": len(gather_ms_max), "backend": "nccl" if world > 1 else "none (1 rank: device-to-device drain only)",
+            "source": "b200_replay_drain_dev (rows k_gc stored from the observations this move's collections freed), inside the e2e loop"}
     peaks = measured_peaks()
     out = None
     if rank == 0:
@@ -316,7 +463,8 @@ def run_b200(args, cfg):
             ach = tree_bytes / tree_s / 1e9
             tr_s, tr_b = ncu_traffic("k_select_expand"), ncu_traffic("k_backup")
             roof_tree = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                         "traffic": (tr_s + tr_b) if tr_s and tr_b else None, "algorithmic_bytes_per_launch_pair": tree_bytes / max(sel_n, 1),
+                         "traffic": (tr_s + tr_b) if tr_s and tr_b else None, "traffic_src": ncu_traffic_src(),
+                         "algorithmic_bytes_per_launch_pair": tree_bytes / max(sel_n, 1),
                          "kernels": "k_select_expand + k_backup", "mean_trace_len": D_mean, "ms_per_launch_pair": (sel_ms + bk_ms) / max(sel_n, 1),
                          "peak_src": peaks["src"]}
         if cfg["mode"] == "dist":
@@ -334,16 +482,17 @@ def run_b200(args, cfg):
                 ach = boards * CONV_FLOP / (conv_ms / 1e3) / 1e12
                 kname = "k_vn_conv" if cfg["eval"] == "net" else "k_tc_conv"
                 roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
-                        "traffic": ncu_traffic(kname), "kernel": kname, "mma_flops_issued_per_launch": boards * 2 * 128 * 16 * (96 * 36 + 64 * 2) / conv_n, "ms_per_launch": conv_ms / conv_n,
+                        "traffic": ncu_traffic(kname), "traffic_src": ncu_traffic_src(), "kernel": kname,
+                        "mma_flops_issued_per_launch": boards * TC_ISSUED_FLOP_PER_BOARD / conv_n, "ms_per_launch": conv_ms / conv_n,
                         "flops_per_launch": boards * CONV_FLOP / conv_n, "boards_per_launch": boards / conv_n,
                         "fc_kernel_tflops": boards * FC_FLOP / (fc_ms / 1e3) / 1e12 if fc_ms > 0 else None,
                         "share_of_step": conv_ms / ms_instr, "peak_src": peaks["src"] + " bf16 dense, sustained",
                         "note": "achieved counts ALGORITHMIC conv FLOPs (SURVEY 8d: 2 884 608 per board).  fp32-faithful arithmetic (north_star 1e-5): "
                                 "eval=net is CUDA-core fp32 FMA; eval=net_tc is tcgen05 kind::f16 with every fp32 operand split into two scaled fp16 terms "
-                                "(3 products per algorithmic product; M=128 pixel tiles on an 8-wide grid carry 25-56% halo rows; per board 2x18 MMAs of 128x96x16 "
-                                "plus 2 of 128x64x16 for conv1), so the tensor pipe executes mma_flops_issued_per_launch.  scripts/probe/mma_probe.cu "
-                                "measures SS-mode tcgen05.mma at (A+B operand bytes)/128 B/clk with a 44.7 clk floor: these small-N MMAs are shared-memory "
-                                "operand-fetch bound, not tensor-rate bound; the bf16 peak is the driver-measured denominator, not this kernel's ceiling"}
+                                "(3 products per algorithmic product; M=128 pixel tiles carry halo rows), so the tensor pipe executes "
+                                "mma_flops_issued_per_launch.  scripts/probe/mma_probe.cu measures SS-mode tcgen05.mma at (A+B operand bytes)/128 B/clk with a "
+                                "44.7 clk floor: these small-N MMAs are shared-memory operand-fetch bound, not tensor-rate bound; the bf16 peak is the "
+                                "driver-measured denominator, not this kernel's ceiling"}
         else:
             ro_ms, ro_n = phases["rollout"]
             roof = {"bound": "hbm", "achieved": 0.0, "peak": peaks["hbm"], "unit": "GB/s", "frac": 0.0, "traffic": None, "kernel": "k_rollout",
@@ -356,19 +505,22 @@ def run_b200(args, cfg):
             except Exception as ex:   # the oracle/_ref modules are prebuilt; report rather than die
                 cpu = {"value": None, "unit": "sims/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
         config = dict(cfg["config"])
-        config.update({"parallelism": "games sharded x%d, no data-path collective" % world,
+        config.update({"parallelism": "games sharded x%d, no data-path collective in the search; one exchange step per move (replay rows, all-gather)" % world,
                        "l2": "inputs larger than L2: %.1f GB of arenas per GPU; %.2f GB of activations stream through L2 every sim-step"
-                             % (G * M * 324 / 1e9, G * 7 * 1792 * 4 / 1e9)})
+                             % (G * M * ARENA_BYTES_PER_SLOT / 1e9, G * 7 * 1792 * 4 / 1e9)})
         out = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": config, "roofline": roof, "roofline_select_backup": roof_tree, "cpu_baseline": cpu,
-               "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": G * 80 * world, "d2h_bytes_per_step": G * (4 + 84 + 80) * world},
+               "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": G * 80 * world, "d2h_bytes_per_step": G * (4 + 84 + 80) * world,
+                       "ms_per_step": 1e3 * e2e_s / steps, "includes": "set_games (H2D) + play_move (D2H actions, stats, status) + get_games (D2H) + replay drain + all-gather"},
+               "same_workload": {"value_pass_vs_instrumented_vs_e2e": bool(same), "keys": list(WORK_KEYS),
+                                 "how": "three identical engines built from the same seeds, W warm-up moves, then the same K moves (deterministic search)"},
                "gpu_launches": int(launches), "clocks": clk.summary(), "trajectory_allgather": traj,
                "phases_ms_per_step": {k: v[0] / steps for k, v in phases.items()}, "instrumented_ms_per_step": ms_instr / steps,
                "phases_note": "value / ms_per_step: K steps on the production path (each simulation step replayed as one CUDA graph).  phases_ms_per_step, "
-                              "roofline.*: a second pass of K steps with an event pair around every kernel (direct launches), instrumented_ms_per_step long",
+                              "roofline.*: the same K steps on a second identical engine with an event pair around every kernel (direct launches), "
+                              "instrumented_ms_per_step long",
                "counters_per_step": {k: v / steps for k, v in delta.items()}}
-    eng.close()
     # ---- BASELINE configs[1] alongside (Vanilla MCTS, random rollouts, no value net): short, so it rides in the same line
     if cfg["mode"] == "lp" and not args.no_secondary:
         G2, sims2 = 4096, 300
@@ -415,7 +567,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--ref-moves-per-step", type=int, default=4)
+    ap.add_argument("--ref-moves-per-step", type=int, default=2)
+    ap.add_argument("--exchange-rows", type=int, default=262144, help="rows (212 B) of the fixed-size replay block each rank contributes to the per-move all-gather")
     args = ap.parse_args()
     if args.workload == "vanilla":
         G, sims, M, mode = args.games_per_gpu or 4096, args.sims or 300, args.max_nodes or 8192, "vanilla"

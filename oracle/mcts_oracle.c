@@ -238,6 +238,9 @@ struct mo_agent {
     uint8_t *end_scratch;
     float *nstat, *ndist;          /* MO_MODE_DIST: node_stats f32[M][5], node_dist f32[M][bins] */
     uint8_t *replay_rows; int replay_n;   /* ValueSim.memory rows (212 B), filled by remove_nodes */
+    /* overflow_reset (the engine's policy beyond the reference, include/b200_tetris_mcts.h; used by bench.py): see drop_tree() */
+    int reroot_pending, reset_hit, in_expand; long resets;
+    uint32_t live[TO_RECORD_WORDS];       /* the game last handed to update_root (the object play.py owns) */
 };
 
 static uint64_t hash_words(const uint32_t *w, int n) {
@@ -322,8 +325,34 @@ void mo_agent_destroy(mo_agent *a) {
     free(a);
 }
 
-/* agent.py:206-257 remove_nodes -> get_all_childs + update_available + reset_arrays */
+/* The engine's overflow_reset policy (NOT in the reference, which dies at this point: IndexError agent.py:99 / UB agent.cpp:227-231):
+ * a collection that leaves fewer than max_nodes/8 free node slots means the reachable set itself fills the arena; the whole tree is
+ * dropped (every array zeroed except the game slots, free lists as at construction, both tables emptied) and the agent re-roots at
+ * the live game before its next simulation / inside the running update_root.  Mirrors k_gc + reset_tree (kernels.cuh, search_dev.cuh). */
+static void drop_tree(mo_agent *a) {
+    int M = a->M;
+    memset(a->child, 0, (size_t)M * MO_NA * 4);
+    memset(a->visit_n, 0, (size_t)M * 4); memset(a->value_n, 0, (size_t)M * 4); memset(a->variance_n, 0, (size_t)M * 4);
+    memset(a->episode_n, 0, (size_t)M * 4); memset(a->score, 0, (size_t)M * 4); memset(a->end_n, 0, (size_t)M);
+    memset(a->n2o, 0, (size_t)M * 4);
+    memset(a->ostate, 0, (size_t)M * TO_OBSKEY_WORDS * 4);
+    memset(a->ovisit, 0, (size_t)M * 4); memset(a->ovalue, 0, (size_t)M * 4); memset(a->ovariance, 0, (size_t)M * 4); memset(a->oend, 0, (size_t)M);
+    if (a->nstat) { memset(a->nstat, 0, (size_t)M * 5 * 4); memset(a->ndist, 0, (size_t)M * (size_t)a->cfg.dist_bins * 4); }
+    for (int i = 1; i < M; ++i) { a->available[i - 1] = i; a->oavailable[i - 1] = i; }
+    a->n_avail = M - 1; a->n_oavail = M - 1;
+    memset(a->ntab.slot, 0, sizeof(int32_t) * (size_t)a->ntab.cap);
+    memset(a->otab.slot, 0, sizeof(int32_t) * (size_t)a->otab.cap);
+    a->reroot_pending = 1; a->reset_hit = 1; a->resets += 1;
+}
+
+static void remove_nodes_ref(mo_agent *a);
 static void remove_nodes(mo_agent *a) {
+    remove_nodes_ref(a);
+    if (a->cfg.overflow_reset && a->n_avail < a->M / 8) drop_tree(a);
+}
+
+/* agent.py:206-257 remove_nodes -> get_all_childs + update_available + reset_arrays */
+static void remove_nodes_ref(mo_agent *a) {
     int M = a->M;
     a->counters[3] += 1;
     uint8_t *occ = (uint8_t *)malloc((size_t)M), *oocc = (uint8_t *)calloc((size_t)M, 1);
@@ -392,7 +421,10 @@ static int new_node(mo_agent *a, const to_game *g) {
     to_pack(g, rec);
     int idx = tab_find(&a->ntab, a->game, rec);
     if (idx) return idx;
-    if (a->n_avail == 0) remove_nodes(a);                 /* agent.py:96-97 */
+    if (a->n_avail == 0) {
+        remove_nodes(a);                                  /* agent.py:96-97 */
+        if (a->reset_hit && a->in_expand) return -1;      /* overflow_reset: the tree was dropped under a running expansion */
+    }
     if (a->n_avail == 0) { a->overflow = 1; return 0; }   /* reference: IndexError / UB (agent.cpp:227-231) */
     idx = a->available[--a->n_avail];                     /* agent.py:99 pop() from the right */
     memcpy(a->game + (size_t)idx * TO_RECORD_WORDS, rec, sizeof(rec));
@@ -414,22 +446,29 @@ static int new_node(mo_agent *a, const to_game *g) {
 }
 
 /* agent.py:136-145 expand */
-static void expand(mo_agent *a, int leaf) {
+static int expand(mo_agent *a, int leaf) {                /* returns -1 when overflow_reset dropped the tree under it */
     to_game g, t;
     to_unpack(&g, a->game + (size_t)leaf * TO_RECORD_WORDS);
     a->counters[1] += 1;
+    a->in_expand = 1; a->reset_hit = 0;
     for (int i = 0; i < MO_NA; ++i) {
         t = g;
         to_play(&t, i);
         int c = new_node(a, &t);
+        if (c < 0) { a->in_expand = 0; a->counters[1] -= 1; return -1; }   /* the engine counts an expansion when it completes */
         a->child[(size_t)leaf * MO_NA + i] = c;
     }
+    a->in_expand = 0;
+    return 0;
 }
 
 void mo_agent_update_root(mo_agent *a, const uint32_t *rec20) {
     to_game g;
     to_unpack(&g, rec20);
-    a->root = new_node(a, &g);
+    memcpy(a->live, rec20, sizeof(a->live));
+    a->reset_hit = 0;
+    a->root = new_node(a, &g);      /* a tree dropped earlier (or inside this call) is simply re-rooted here */
+    a->reroot_pending = 0;
     if (g.end) a->episode += 1;
 }
 
@@ -453,6 +492,13 @@ static void evaluate(mo_agent *a, const int32_t *obs, int k, float *v, float *va
 int mo_agent_mcts(mo_agent *a, int sims) {
     const mo_config *cf = &a->cfg;
     for (int s = 0; s < sims; ++s) {
+        if (a->reroot_pending) {        /* overflow_reset: the tree was dropped; re-root at the live game (reset_tree, search_dev.cuh) */
+            to_game lv;
+            to_unpack(&lv, a->live);
+            a->reset_hit = 0;
+            a->root = new_node(a, &lv);
+            a->reroot_pending = 0;
+        }
         if (cf->mode == MO_MODE_DIST) {
             /* The loop agents/DistValueSimOnline.py:36-75 sketches (not runnable upstream), on the numba cores:
              * select_trace_distributional -> r = leaf score; leaf not ended: dist = net(leaf state), expand;
@@ -475,7 +521,7 @@ int mo_agent_mcts(mo_agent *a, int sims) {
                     for (int j = 0; j < 4; ++j) st[(key[10] >> (8 * j)) & 0xff] = -1;
                     dn_forward(cf->weights, st, 1, cf->dist_bins, dist);
                 }
-                expand(a, leaf);
+                if (expand(a, leaf) < 0) continue;       /* tree dropped: this simulation is abandoned */
                 if (a->overflow) return -1;
             } else {
                 memset(dist, 0, sizeof(float) * (size_t)cf->dist_bins);
@@ -495,7 +541,7 @@ int mo_agent_mcts(mo_agent *a, int sims) {
         if (cf->mode == MO_MODE_LP) {                     /* ValueSimLP.py:44-70 */
             int32_t c_nodes[MO_NA], c_obs[MO_NA]; float v[MO_NA], var[MO_NA]; int k = 0;
             if (!lg.end) {
-                expand(a, leaf);
+                if (expand(a, leaf) < 0) continue;       /* tree dropped: this simulation is abandoned (no evaluation, no backup) */
                 if (a->overflow) return -1;
                 k = mo_unique_child_obs(leaf, a->child, a->score, a->n2o, c_nodes, c_obs);
                 evaluate(a, c_obs, k, v, var);
@@ -540,7 +586,7 @@ int mo_agent_mcts(mo_agent *a, int sims) {
                 /* ValueSim.py:86: int + np.float32 -> float32 under numpy>=2 (NEP 50), the version in this image */
                 float sum = (float)lg.score + v;
                 _value = (double)sum; _variance = (double)var;
-                expand(a, leaf);
+                if (expand(a, leaf) < 0) continue;
                 if (a->overflow) return -1;
             }
             mo_backup_trace_obs(a->last_trace, D, a->ovisit, a->ovalue, a->ovariance, a->n2o, a->score, _value, _variance, cf->gamma);
@@ -550,7 +596,7 @@ int mo_agent_mcts(mo_agent *a, int sims) {
                 to_game r = lg;
                 while (!r.end) { to_play(&r, (int)(agent_rand(a) % MO_NA)); a->counters[5] += 1; }
                 _value = (double)r.score; _variance = cf->rollout_variance;
-                expand(a, leaf);
+                if (expand(a, leaf) < 0) continue;
                 if (a->overflow) return -1;
             } else { _value = (double)lg.score; _variance = 0; }
             mo_backup_trace_obs(a->last_trace, D, a->ovisit, a->ovalue, a->ovariance, a->n2o, a->score, _value, _variance, cf->gamma);
@@ -592,7 +638,7 @@ int mo_agent_root(const mo_agent *a) { return a->root; }
 void mo_agent_remove_nodes(mo_agent *a) { remove_nodes(a); }
 int mo_agent_n_free(const mo_agent *a) { return a->n_avail; }   /* len(self.available), agents/agent.py:72 */
 int mo_agent_episode(const mo_agent *a) { return a->episode; }
-long mo_agent_counter(const mo_agent *a, int w) { return (w >= 0 && w < 6) ? a->counters[w] : -1; }
+long mo_agent_counter(const mo_agent *a, int w) { return (w >= 0 && w < 6) ? a->counters[w] : (w == 7 ? a->resets : -1); }
 
 void mo_agent_export(const mo_agent *a, int32_t *child, float *score, int32_t *episode, int32_t *n2o, int32_t *visit,
                      float *value, float *variance, uint8_t *obs_end, uint32_t *game_recs, uint32_t *obs_keys) {

@@ -59,6 +59,8 @@ typedef struct {
     int dist_bins;         /* MO_MODE_DIST: atoms (DistValueSimOnline.py:13: 50) */
     double dist_vmin, dist_vmax;   /* value range (DistValueSimOnline.py:13: 0, 5000) */
     int replay_min_visits, replay_cap;   /* ValueSim.py:14 min_visits_to_store / memory_size; 0 = no replay memory */
+    int overflow_reset;    /* NOT the reference: the engine's bench policy (b200_config.overflow_reset) — a collection that leaves fewer than
+                              max_nodes/8 free slots drops the tree and re-roots at the live game; 0 = reference behaviour (overflow is an error) */
 } mo_config;
 
 typedef struct mo_agent mo_agent;
@@ -72,7 +74,7 @@ void mo_agent_remove_nodes(mo_agent *a);                                 /* agen
 int mo_agent_n_free(const mo_agent *a);                                   /* len(self.available) */
 int mo_agent_replay(mo_agent *a, uint8_t *rows212, int max_rows);   /* ValueSim.memory rows stored by remove_nodes; empties the memory */
 int mo_agent_episode(const mo_agent *a);
-long mo_agent_counter(const mo_agent *a, int which); /* 0 sims, 1 expansions, 2 evals, 3 gcs, 4 trace levels, 5 rollout steps */
+long mo_agent_counter(const mo_agent *a, int which); /* 0 sims, 1 expansions, 2 evals, 3 gcs, 4 trace levels, 5 rollout steps, 7 trees dropped (overflow_reset) */
 /* export in the reference's array layout (agent.py:58-88); any pointer may be NULL */
 void mo_agent_export(const mo_agent *a, int32_t *child, float *score, int32_t *episode, int32_t *n2o,
                      int32_t *visit, float *value, float *variance, uint8_t *obs_end, uint32_t *game_recs,

@@ -44,7 +44,7 @@ class MoConfig(C.Structure):
         ("lp_end_from_obs", C.c_int), ("lp_var_gamma2", C.c_int), ("rollout_variance", C.c_double),
         ("eval_mode", C.c_int), ("weights", C.c_void_p), ("eval_cb", C.c_void_p), ("eval_ctx", C.c_void_p),
         ("search_seed", C.c_uint32), ("stale_pop", C.c_int), ("dist_bins", C.c_int), ("dist_vmin", C.c_double), ("dist_vmax", C.c_double),
-        ("replay_min_visits", C.c_int), ("replay_cap", C.c_int),
+        ("replay_min_visits", C.c_int), ("replay_cap", C.c_int), ("overflow_reset", C.c_int),
     ]
 
 
@@ -234,8 +234,10 @@ class Agent:
 
     def __init__(self, max_nodes=100000, mode=0, gamma=0.999, low=1, eval_mode=0, weights=None, eval_cb=None,
                  lp_end_from_obs=0, lp_var_gamma2=1, rollout_variance=1e3, search_seed=0, stale_pop=1,
-                 app=1, scoring=0, randomizer=0, dist_bins=50, dist_vmin=0.0, dist_vmax=5000.0, replay_min_visits=0, replay_cap=0):
+                 app=1, scoring=0, randomizer=0, dist_bins=50, dist_vmin=0.0, dist_vmax=5000.0, replay_min_visits=0, replay_cap=0,
+                 overflow_reset=0):
         cfg = MoConfig()
+        cfg.overflow_reset = int(overflow_reset)
         cfg.replay_min_visits, cfg.replay_cap = replay_min_visits, replay_cap
         cfg.dist_bins, cfg.dist_vmin, cfg.dist_vmax = dist_bins, dist_vmin, dist_vmax
         self.dist_bins = dist_bins

@@ -36,8 +36,12 @@ names = ['S0_arrive', 'wait_c1', 'E1', 'wait_c2', 'E2', 'wait_c3', 'E3', 'S0_wai
 tot = pr[:8].sum() + pr[14:16].sum()
 print({n: round(float(pr[i]) / max(float(tot), 1), 3) for i, n in enumerate(names)}, 'worker cycles total', int(tot), 'boards', c['eval_requests'] // 148)
 
-pt = np.zeros(8, np.uint64)
+pt = np.zeros(16, np.uint64)
 L.lib().b200_debug_prof_tree.argtypes = [L.P, L.P]
 L.check(L.lib().b200_debug_prof_tree(eng.h, L.ptr(pt)))
 tt = float(pt[:4].sum() + pt[5])
 print('k_select_expand sampled groups', int(pt[4]), {n: round(float(pt[i]) / max(tt, 1), 3) for i, n in enumerate(['select', 'leaf_load', 'expand', 'finish+evalreq', '-', 'fused_backup']) if n != '-'}, 'mean clk/group', int(tt / max(float(pt[4]), 1)))
+if pt[11]:
+    lv = float(pt[11])
+    print('per level (B200_SELECT_PROF build, sampled groups): levels %d  row line %.0f clk | statistics %.0f clk | pick %.0f clk | total %.0f clk' % (
+        int(lv), float(pt[8]) / lv, float(pt[9]) / lv, float(pt[10]) / lv, float(pt[8] + pt[9] + pt[10]) / lv))

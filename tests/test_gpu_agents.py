@@ -97,3 +97,37 @@ def test_dist_agent_class_like_play_py(gpu_lib, oracle):
     m, v = agent.get_value()
     assert 0 <= m <= 5000 and v >= 0
     agent.close()
+
+
+def test_valuesim_loads_the_checkpoint_like_the_reference(gpu_lib, tmp_path, monkeypatch):
+    """agents/ValueSim.py:42-44: Model().load() reads ./pytorch_model/model_checkpoint (model/model.py:163-174) when it exists.  A checkpoint
+    on disk must change what the agent's network computes; without one the default-initialised weights are used."""
+    import torch
+    from tetris_mcts_b200.agents.ValueSimLP import ValueSimLP
+    from tetris_mcts_b200.engine import BatchedEngine
+    from tetris_mcts_b200.model.model_vv import WEIGHT_KEYS, init_weights
+    from tetris_mcts_b200.pyTetris import Tetris
+    env_args = ((20, 10), 1, 0, 0)
+    monkeypatch.chdir(tmp_path)
+    state = np.zeros((20, 10), np.int8)
+    state[15:, :7] = 1
+    state[2, 4:6] = -1; state[3, 4:6] = -1
+    a0 = ValueSimLP(sims=10, env=Tetris, env_args=env_args, benchmark=True, online=False, min_visit=40)       # no checkpoint: default model
+    v0 = a0.evaluate_state(state)
+    a0.close()
+    w = init_weights(5)
+    sd, off = {}, 0
+    for name, shape in WEIGHT_KEYS:
+        n = int(np.prod(shape))
+        sd[name] = torch.from_numpy(w[off:off + n].reshape(shape).copy())
+        off += n
+    (tmp_path / "pytorch_model").mkdir()
+    torch.save({"model_state_dict": sd, "optimizer_state_dict": {}}, str(tmp_path / "pytorch_model" / "model_checkpoint"))   # model/model.py:143-160
+    a1 = ValueSimLP(sims=10, env=Tetris, env_args=env_args, benchmark=True, online=False, min_visit=40)
+    v1 = a1.evaluate_state(state)
+    a1.close()
+    ref = BatchedEngine(1, max_nodes=64, eval_kind="net_tc", weights=w)
+    want = ref.valuenet(state[None])
+    ref.close()
+    assert (v1[0], v1[1]) == (want[0][0], want[1][0])
+    assert (v0[0], v0[1]) != (v1[0], v1[1])

@@ -4,7 +4,7 @@ from sys import stderr
 import numpy as np
 
 from .agent import TreeAgent
-from ..model.model_vv import init_weights
+from ..model.model_vv import init_weights, load_checkpoint_weights
 
 perr = dict(file=stderr, flush=True)
 
@@ -14,7 +14,13 @@ class ValueSim(TreeAgent):
 
     def __init__(self, online=True, memory_size=500000, min_visits_to_store=10, gamma=0.999, memory_growth_rate=5000, weights=None, **kwargs):
         kwargs.pop("max_nodes", None)
-        super().__init__(max_nodes=100000, gamma=gamma, low=1, weights=init_weights(0) if weights is None else weights, **kwargs)   # ValueSim.py:16
+        if weights is None:
+            # ValueSim.py:42-44: self.model = Model(); self.model.load(); self.model.training(False).  Model.load (model/model.py:163-174)
+            # reads ./pytorch_model/model_checkpoint when it exists and otherwise keeps the default-initialised network.
+            weights = load_checkpoint_weights()
+            if weights is None:
+                weights = init_weights(0)
+        super().__init__(max_nodes=100000, gamma=gamma, low=1, weights=weights, **kwargs)   # ValueSim.py:16
         self.online, self.min_visits_to_store = online, min_visits_to_store
         if online and not self.benchmark:                         # ValueSim.py:21-37: the replay memory lives on the device (k_gc fills it)
             self._eng.replay_enable(min_visits=min_visits_to_store, capacity=memory_size)
@@ -29,7 +35,9 @@ class ValueSim(TreeAgent):
         if not (self.online and not self.benchmark):
             return replay.rows_to_memory(np.zeros((0, replay.SAMPLE_BYTES), np.uint8))
         cap = 500000
-        buf = torch.zeros((cap, replay.SAMPLE_BYTES), dtype=torch.uint8, device="cuda")
+        dev = torch.device("cuda", int(self._eng.cfg.device))      # the engine's device, not torch's current one
+        buf = torch.empty((cap, replay.SAMPLE_BYTES), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)                                # the engine copies on its own stream: nothing of torch's may be pending on buf
         n = self._eng.replay_drain_into(buf.data_ptr(), cap)
         rows = buf[:n].cpu().numpy()
         if dump_data and n:

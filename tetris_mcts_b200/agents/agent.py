@@ -143,6 +143,7 @@ class TreeAgent(Agent):                                          # agents/agent.
         return s["value"][o], s["variance"][o]
 
     def remove_nodes(self):                                       # agents/agent.py:246-257 (also run on the device where new_node needs it, :96-97)
+        self._snap = None                                         # the collection frees and zeroes slots: snapshots are stale
         self._eng.remove_nodes()
 
     def counters(self):

@@ -74,6 +74,25 @@ static void drop_step_graph(b200_engine *e) {
     e->step_graph_failed = false;
 }
 
+// temporary device buffers of the standalone entry points: freed on every return path
+struct Scratch {
+    std::vector<void *> bufs;
+    ~Scratch() { for (void *q : bufs) cudaFree(q); }
+    template <typename T> cudaError_t get(T **out, size_t bytes) {
+        void *q = nullptr;
+        cudaError_t err = cudaMalloc(&q, bytes ? bytes : 1);
+        if (err == cudaSuccess) { bufs.push_back(q); *out = (T *)q; }
+        return err;
+    }
+};
+
+static void dfree(b200_engine *e, void *p) {   // release one engine-owned allocation early (a buffer that is being replaced)
+    if (!p) return;
+    for (size_t i = 0; i < e->allocs.size(); ++i)
+        if (e->allocs[i] == p) { e->allocs.erase(e->allocs.begin() + i); break; }
+    cudaFree(p);
+}
+
 template <typename T>
 static int dalloc(b200_engine *e, T **p, size_t n, bool zero = true) {
     void *q = nullptr;
@@ -151,6 +170,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
     CK(cudaSetDevice(cfg->device));
     b200_engine *e = new b200_engine();
+    struct Guard { b200_engine *e; ~Guard() { if (e) b200_engine_destroy(e); } } guard{e};   // every failing return below destroys the half-built engine
     e->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
@@ -190,7 +210,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     e->d_game_stats = A.counters + 8;
     float *zt = nullptr;
     rc |= dalloc(e, &zt, ZTABLE_N);
-    if (rc) { b200_engine_destroy(e); return B200_ERR_CUDA; }
+    if (rc) return B200_ERR_CUDA;
     {   // z(n) = norm_quantile(n) narrowed to float: special.h:26-33 + core.h:93, evaluated with the host libm
         std::vector<float> h(ZTABLE_N);
         const double l2 = log(2.0), l22 = log(22.0), l41 = log(41.0);
@@ -206,6 +226,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     k_init_arena<<<e->n_sm * 8, 256, 0, e->stream>>>(A, e->d_default_rec, cfg->seed);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
+    guard.e = nullptr;
     *out = e;
     return B200_OK;
 }
@@ -279,6 +300,7 @@ extern "C" int b200_load_weights(b200_engine *e, const float *w) {
 
 static int ensure_act3(b200_engine *e, size_t rows) {
     if (e->act3_rows >= rows) return 0;
+    if (e->d_act3) { cudaStreamSynchronize(e->stream); dfree(e, e->d_act3); e->d_act3 = nullptr; e->act3_rows = 0; }
     if (dalloc(e, &e->d_act3, rows * 1792, false)) return B200_ERR_CUDA;
     e->act3_rows = rows;
     return 0;
@@ -348,6 +370,7 @@ static int launch_distnet_on(b200_engine *e, const uint2 *req, const int32_t *n_
     if (!e->have_dist_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_dist_weights was not called");
     if (e->dn_rows < max_rows) {
         const bool had = e->d_dn_act != nullptr;
+        if (had) { cudaStreamSynchronize(e->stream); dfree(e, e->d_dn_act); e->d_dn_act = nullptr; e->dn_rows = 0; }
         if (dalloc(e, &e->d_dn_act, max_rows * 2048, false)) return B200_ERR_CUDA;
         e->dn_rows = max_rows;
         if (had) drop_step_graph(e);
@@ -372,8 +395,9 @@ extern "C" int b200_distnet_forward(b200_engine *e, const int8_t *states, int k,
     if (!e || !states || !dist || k < 1 || atoms != e->DW.atoms) return fail(B200_ERR_BAD_ARG, "bad argument (atoms must match the loaded weights)");
     CK(cudaSetDevice(e->cfg.device));
     int8_t *d_states = nullptr; uint32_t *d_keys = nullptr; uint2 *d_req = nullptr; int32_t *d_n = nullptr; float *d_out = nullptr;
-    CK(cudaMalloc(&d_states, (size_t)k * 200)); CK(cudaMalloc(&d_keys, (size_t)k * KEY_WORDS * 4)); CK(cudaMalloc(&d_req, (size_t)k * 8));
-    CK(cudaMalloc(&d_n, 4)); CK(cudaMalloc(&d_out, (size_t)k * atoms * 4));
+    Scratch tmp;
+    CK(tmp.get(&d_states, (size_t)k * 200)); CK(tmp.get(&d_keys, (size_t)k * KEY_WORDS * 4)); CK(tmp.get(&d_req, (size_t)k * 8));
+    CK(tmp.get(&d_n, 4)); CK(tmp.get(&d_out, (size_t)k * atoms * 4));
     CK(cudaMemcpyAsync(d_states, states, (size_t)k * 200, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(d_n, &k, 4, cudaMemcpyHostToDevice, e->stream));
     k_states_to_keys<<<(k + 127) / 128, 128, 0, e->stream>>>(d_states, k, d_keys, d_req);
@@ -385,7 +409,6 @@ extern "C" int b200_distnet_forward(b200_engine *e, const int8_t *states, int k,
         if (ce != cudaSuccess) rc = fail(B200_ERR_CUDA, cudaGetErrorString(ce));
     }
     cudaStreamSynchronize(e->stream);
-    cudaFree(d_states); cudaFree(d_keys); cudaFree(d_req); cudaFree(d_n); cudaFree(d_out);
     return rc;
 }
 
@@ -470,7 +493,7 @@ static int enqueue_step(b200_engine *e) {
         PhaseTimer t(e, PH_SELECT);
         Arena Ap = A;
         Ap.prof = e->timing ? A.counters + 32 : nullptr;
-        k_select_expand<<<blocks_groups(G), TPB, 0, e->stream>>>(Ap);
+        k_select_expand<<<(G + SE_GAMES_PER_BLOCK - 1) / SE_GAMES_PER_BLOCK, TPB, 0, e->stream>>>(Ap);
     }
     {   // remove_nodes for the games that ran out of free slots in this step, then the rest of their expansion
         PhaseTimer t(e, PH_GC);
@@ -610,10 +633,10 @@ extern "C" int b200_debug_prof(b200_engine *e, uint64_t *out16) {   // clock64 p
     return B200_OK;
 }
 
-extern "C" int b200_debug_prof_tree(b200_engine *e, uint64_t *out8) {   // clock64 sums of sampled groups of k_select_expand (timing mode)
-    if (!e || !out8) return fail(B200_ERR_BAD_ARG, "null argument");
+extern "C" int b200_debug_prof_tree(b200_engine *e, uint64_t *out16) {   // clock64 sums of sampled groups of k_select_expand (timing mode); 8..11: per-level split (B200_SELECT_PROF builds)
+    if (!e || !out16) return fail(B200_ERR_BAD_ARG, "null argument");
     CK(cudaSetDevice(e->cfg.device));
-    CK(cudaMemcpyAsync(out8, e->A.counters + 32, 8 * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(out16, e->A.counters + 32, 16 * 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return B200_OK;
 }
@@ -733,8 +756,9 @@ extern "C" int b200_valuenet_forward(b200_engine *e, const int8_t *states, int k
     CK(cudaSetDevice(e->cfg.device));
     int8_t *d_states = nullptr; uint32_t *d_keys = nullptr; uint2 *d_req = nullptr; int32_t *d_n = nullptr; float2 *d_out = nullptr;
     size_t kp = ((size_t)k + 7) & ~(size_t)7;
-    CK(cudaMalloc(&d_states, (size_t)k * 200)); CK(cudaMalloc(&d_keys, kp * KEY_WORDS * 4)); CK(cudaMalloc(&d_req, kp * 8));
-    CK(cudaMalloc(&d_n, 4)); CK(cudaMalloc(&d_out, kp * 8));
+    Scratch tmp;
+    CK(tmp.get(&d_states, (size_t)k * 200)); CK(tmp.get(&d_keys, kp * KEY_WORDS * 4)); CK(tmp.get(&d_req, kp * 8));
+    CK(tmp.get(&d_n, 4)); CK(tmp.get(&d_out, kp * 8));
     CK(cudaMemcpyAsync(d_states, states, (size_t)k * 200, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(d_n, &k, 4, cudaMemcpyHostToDevice, e->stream));
     k_states_to_keys<<<(k + 127) / 128, 128, 0, e->stream>>>(d_states, k, d_keys, d_req);
@@ -748,7 +772,6 @@ extern "C" int b200_valuenet_forward(b200_engine *e, const int8_t *states, int k
         else for (int i = 0; i < k; ++i) { v[i] = h[i].x; var[i] = h[i].y; }
     }
     cudaStreamSynchronize(e->stream);
-    cudaFree(d_states); cudaFree(d_keys); cudaFree(d_req); cudaFree(d_n); cudaFree(d_out);
     return rc;
 }
 
@@ -792,22 +815,22 @@ static int env_stream_op(uint32_t *recs, const int32_t *actions, int8_t *state_o
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
     uint32_t *d = nullptr; int32_t *da = nullptr; int8_t *ds = nullptr;
-    CK(cudaMalloc(&d, (size_t)n * REC_WORDS * 4));
+    Scratch tmp;
+    CK(tmp.get(&d, (size_t)n * REC_WORDS * 4));
     CK(cudaMemcpy(d, recs, (size_t)n * REC_WORDS * 4, cudaMemcpyHostToDevice));
     if (actions) {
-        CK(cudaMalloc(&da, (size_t)n * 4));
+        CK(tmp.get(&da, (size_t)n * 4));
         CK(cudaMemcpy(da, actions, (size_t)n * 4, cudaMemcpyHostToDevice));
         k_env_step<<<(n + 127) / 128, 128>>>(d, da, n);
         CK(cudaGetLastError());
         CK(cudaMemcpy(recs, d, (size_t)n * REC_WORDS * 4, cudaMemcpyDeviceToHost));
     }
     if (state_out) {
-        CK(cudaMalloc(&ds, (size_t)n * 200));
+        CK(tmp.get(&ds, (size_t)n * 200));
         k_env_state<<<(n + 127) / 128, 128>>>(d, ds, n);
         CK(cudaGetLastError());
         CK(cudaMemcpy(state_out, ds, (size_t)n * 200, cudaMemcpyDeviceToHost));
     }
-    cudaFree(d); cudaFree(da); cudaFree(ds);
     return B200_OK;
 }
 
@@ -816,13 +839,13 @@ extern "C" int b200_tetris_new(uint32_t *recs, int n, int app, int scoring, int 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ERR_CUDA, "no CUDA device: this library has no CPU path");
     uint32_t *d = nullptr, *ds = nullptr;
-    CK(cudaMalloc(&d, (size_t)n * REC_WORDS * 4));
+    Scratch tmp;
+    CK(tmp.get(&d, (size_t)n * REC_WORDS * 4));
     if (reset) CK(cudaMemcpy(d, recs, (size_t)n * REC_WORDS * 4, cudaMemcpyHostToDevice));
-    if (seeds && !reset) { CK(cudaMalloc(&ds, (size_t)n * 4)); CK(cudaMemcpy(ds, seeds, (size_t)n * 4, cudaMemcpyHostToDevice)); }
+    if (seeds && !reset) { CK(tmp.get(&ds, (size_t)n * 4)); CK(cudaMemcpy(ds, seeds, (size_t)n * 4, cudaMemcpyHostToDevice)); }
     k_new_games<<<(n + 127) / 128, 128>>>(d, n, app, scoring, randomizer, ds, reset);
     CK(cudaGetLastError());
     CK(cudaMemcpy(recs, d, (size_t)n * REC_WORDS * 4, cudaMemcpyDeviceToHost));
-    cudaFree(d); cudaFree(ds);
     return B200_OK;
 }
 

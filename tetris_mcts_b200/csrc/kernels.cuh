@@ -6,8 +6,13 @@
 
 namespace b200 {
 
+#ifndef B200_ONE_GAME_PER_WARP
+#define B200_ONE_GAME_PER_WARP 0   // development aid (A/B): k_select_expand with one game per warp (lanes 8-31 idle) to measure what four
+                                   // independent walks per warp cost each other
+#endif
 constexpr int GROUPS_PER_BLOCK = 16;
 constexpr int TPB = GROUPS_PER_BLOCK * 8;
+constexpr int SE_GAMES_PER_BLOCK = B200_ONE_GAME_PER_WARP ? TPB / 32 : GROUPS_PER_BLOCK;
 
 __device__ __forceinline__ void load_rec(const uint32_t *src, uint32_t (&w)[REC_WORDS]) {
 #pragma unroll
@@ -112,9 +117,10 @@ __global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, un
         if (A.pending[g] != PEND_ROOT) return;
         gp.sync();
         if (gp.lane == 0) A.pending[g] = PEND_NONE;
-    } else if ((status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) {
-        reset_tree(A, gp, g, status);   // re-roots at the live game
     }
+    // overflow_reset: a tree dropped by k_gc (in the last simulation step, or by the collection this very update_root asked for
+    // in its first pass) is re-rooted at the live game, then the update proceeds as usual (episode count, auto reset)
+    if ((status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) reset_tree(A, gp, g, status);
     if (status != ST_OK) return;
     const bool may_suspend = !only_pending;
     uint32_t w[REC_WORDS];
@@ -231,7 +237,11 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
     Grp gp;
+#if B200_ONE_GAME_PER_WARP
+    const int g = (threadIdx.x & 31) < 8 ? blockIdx.x * SE_GAMES_PER_BLOCK + (threadIdx.x >> 5) : A.G;
+#else
     const int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
+#endif
     GroupOut out{false, 0, 0, 0, 0, 0};
     if (g < A.G) select_expand_group(A, gp, g, s_z, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS, out);
     __syncwarp();

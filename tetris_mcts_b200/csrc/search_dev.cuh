@@ -280,6 +280,7 @@ struct ArenaAcc {
     __device__ __forceinline__ int get_trace(int d) const { return traceg[d]; }
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return (zs && n >= 0 && n < ZS_N) ? zs[n] : ztab(A, n); }
+    __device__ __forceinline__ unsigned long long *level_prof() const { return (A.prof && (g & 63) == 0) ? A.prof + 8 : nullptr; }
 };
 
 struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
@@ -302,13 +303,24 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
     __device__ __forceinline__ int get_trace(int d) const { return trace[d]; }
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = *rng; uint32_t r = rng_next(sr); *rng = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return ztab(*A, n); }
+    __device__ __forceinline__ unsigned long long *level_prof() const { return nullptr; }
 };
 
 // ------------------------------------------------------------------ select (core.h:167-224)
 // Returns the leaf; writes the trace.  All 8 lanes return the same values.
+#ifndef B200_SELECT_PROF
+#define B200_SELECT_PROF 0   // development aid: clock64 split of one walk level (row line landed | statistics landed | child picked), sampled groups
+#endif
 template <typename Acc>
 __device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int root, int low, int trace_max, int &D_out, int &status) {
     int idx = root, D = 0;
+#if B200_SELECT_PROF
+    unsigned long long *lp = gp.lane == 0 ? acc.level_prof() : nullptr;
+    long long lt = lp ? clock64() : 0;
+#define LEVEL_PROF(i) do { if (lp) { const long long _n = clock64(); atomicAdd(&lp[i], (unsigned long long)(_n - lt)); lt = _n; } } while (0)
+#else
+#define LEVEL_PROF(i) do { } while (0)
+#endif
     for (;;) {
         if (D >= trace_max) { status = ST_TRACE_FULL; break; }
         if (gp.lane == 0) acc.put_trace(D, idx);
@@ -316,10 +328,12 @@ __device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int r
         int o; float s_idx;
         Uniq u;
         acc.level(gp, idx, D - 1, o, s_idx, u);
+        LEVEL_PROF(0);
         if (u.first_mask == 0) break;                                   // core.h:200 no children: leaf
         int4 st = make_int4(0, 0, 0, 0);
         if (u.is_first) st = acc.stat(o, D);                            // the children live one level below
         unsigned lowmask = gp.ballot(u.is_first && st.x < low);          // core.h:65-77
+        LEVEL_PROF(1);
         int pick;
         if (lowmask) {
             uint32_t r = 0;
@@ -349,7 +363,12 @@ __device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int r
             pick = ((gp.ballot(q != q) >> first) & 1u) ? first : ql;
         }
         idx = gp.bcast(u.rep_c, pick);
+        LEVEL_PROF(2);
+#if B200_SELECT_PROF
+        if (lp) atomicAdd(&lp[3], 1ull);
+#endif
     }
+#undef LEVEL_PROF
     D_out = D;
     return idx;
 }

@@ -42,6 +42,18 @@ def state_dict_to_weights(sd):
     return np.concatenate(parts)
 
 
+def load_checkpoint_weights(filename=EXP_PATH + "model_checkpoint"):
+    """Model.load (model/model.py:163-174): the checkpoint's model_state_dict as the C-ABI weight vector, or None (after the
+    reference's own message) when the file does not exist — the agent then keeps its default-initialised network."""
+    if os.path.isfile(filename):
+        import torch
+        print("Loading model...", flush=True)
+        ck = torch.load(filename, map_location="cpu")
+        return state_dict_to_weights(ck["model_state_dict"])
+    print("Checkpoint not found, using default model", flush=True)
+    return None
+
+
 class Model_VV:
     def __init__(self, device=0, seed=0, **kwargs):
         from ..engine import BatchedEngine
@@ -50,14 +62,10 @@ class Model_VV:
         self._eng.load_weights(self.weights)
 
     def load(self, filename=EXP_PATH + "model_checkpoint"):       # model/model.py:163-174
-        if os.path.isfile(filename):
-            import torch
-            print("Loading model...", flush=True)
-            ck = torch.load(filename, map_location="cpu")
-            self.weights = state_dict_to_weights(ck["model_state_dict"])
+        w = load_checkpoint_weights(filename)
+        if w is not None:
+            self.weights = w
             self._eng.load_weights(self.weights)
-        else:
-            print("Checkpoint not found, using default model", flush=True)
 
     def training(self, flag):                                     # inference only on this path
         if flag:
