@@ -94,6 +94,11 @@ int b200_env_step(b200_engine *e, const int32_t *actions);
 /* --- one whole move of play.py:118-177 for every game: mcts -> get_action -> play -> update_root (-> reset) */
 int b200_play_move(b200_engine *e, int sims, int auto_reset, int32_t *actions_out, float *stats_out);
 
+/* --- the episodes that ended inside b200_update_root(auto_reset) / b200_play_move since the last call (play.py:161-177 prints
+ *     `Episode: .. Score: .. Lines Cleared: ..` from these numbers before game.reset()): out4[i] = {game, score, line_clears, episode};
+ *     at most cap rows are copied, *count_out = episodes ended (the device log holds 4 * n_games rows between drains) */
+int b200_finished_games(b200_engine *e, int32_t *out4, int cap, int32_t *count_out);
+
 int b200_status(b200_engine *e, int32_t *status);            /* per-game 0 ok / B200_ERR_ARENA_FULL / B200_ERR_TRACE_FULL */
 int b200_counters(b200_engine *e, uint64_t *out16);          /* 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels
                                                                 5 rollout steps 6 new nodes 7 tree resets 8 games finished 9 score sum 10 lines sum */

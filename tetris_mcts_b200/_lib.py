@@ -56,6 +56,7 @@ def lib():
         L.b200_env_step.argtypes = [P, P]
         L.b200_play_move.argtypes = [P, C.c_int, C.c_int, P, P]
         L.b200_status.argtypes = [P, P]
+        L.b200_finished_games.argtypes = [P, P, C.c_int, P]
         L.b200_remove_nodes.argtypes = [P, C.c_int]
         L.b200_set_gc_headroom.argtypes = [P, C.c_int]
         L.b200_counters.argtypes = [P, P]

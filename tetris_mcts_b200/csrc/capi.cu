@@ -201,6 +201,8 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     rc |= dalloc(e, &A.gc_list, G); rc |= dalloc(e, &A.pending, G); rc |= dalloc(e, &A.resume_a, G);
     rc |= dalloc(e, &A.eval_out, G * 8); rc |= dalloc(e, &A.rollout_val, G);
     rc |= dalloc(e, &A.counters, 48);
+    A.fin_cap = 4 * A.G;
+    rc |= dalloc(e, &A.fin_log, (size_t)A.fin_cap * 4); rc |= dalloc(e, &A.fin_count, 1);
     if (cfg->mode == MODE_DIST) {
         A.dist_bins = cfg->dist_bins; A.dist_vmin = cfg->dist_vmin; A.dist_vmax = cfg->dist_vmax;
         rc |= dalloc(e, &A.nstat, GM * NSTAT_WORDS); rc |= dalloc(e, &A.ndist, GM * (size_t)A.dist_bins); rc |= dalloc(e, &A.dist_eval, G * (size_t)A.dist_bins);
@@ -603,6 +605,23 @@ extern "C" int b200_play_move(b200_engine *e, int sims, int auto_reset, int32_t 
     if (rc) return rc;
     rc = b200_update_root(e, auto_reset);
     if (rc) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+// The episodes that ended (and were reset) in the update_root calls since the last drain: out4[i] = {game, score, line_clears, episode},
+// at most `cap` rows, count_out = how many ended (may exceed cap: the log holds 4 * n_games rows between drains).  play.py:161-177.
+extern "C" int b200_finished_games(b200_engine *e, int32_t *out4, int cap, int32_t *count_out) {
+    if (!e || !out4 || cap < 0 || !count_out) return fail(B200_ERR_BAD_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    int32_t n = 0;
+    CK(cudaMemcpyAsync(&n, e->A.fin_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *count_out = n;
+    int m = n < e->A.fin_cap ? n : e->A.fin_cap;
+    if (m > cap) m = cap;
+    if (m > 0) CK(cudaMemcpyAsync(out4, e->A.fin_log, (size_t)m * 16, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemsetAsync(e->A.fin_count, 0, 4, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return B200_OK;
 }

@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, un
             atomicAdd(&game_stats[1], (unsigned long long)gm.score);
             atomicAdd(&game_stats[2], (unsigned long long)gm.lines);
         }
+        if (gp.lane == 0 && A.fin_log) {                       // play.py:164: the line is printed from these numbers before game.reset()
+            const int slot = atomicAdd(A.fin_count, 1);
+            if (slot < A.fin_cap) reinterpret_cast<int4 *>(A.fin_log)[slot] = make_int4(g, (int)gm.score, (int)gm.lines, A.episode[g]);
+        }
         reset_game(gm);
         pack(gm, w);
         if (gp.lane == 0) store_rec(A.cur + (size_t)g * REC_WORDS, w);

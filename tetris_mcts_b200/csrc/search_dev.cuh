@@ -63,6 +63,9 @@ struct Arena {
     // replay memory (ValueSim.memory, agents/ValueSim.py:25-30; agent.cpp:610-613): 212-byte rows {int8 state[200], f32 value,
     // f32 variance, f32 visit}, filled by k_gc from the observations a collection frees (ValueSim.py:101-159)
     uint8_t *replay; int32_t *replay_count; int replay_cap, replay_min_visits;
+    // finished episodes of the last update_root(auto_reset) calls: {game, score, line_clears, episode} per finished game, what play.py:161-177
+    // prints as its `Episode: .. Score: .. Lines Cleared: ..` line before it resets the game; drained by b200_finished_games
+    int32_t *fin_log; int32_t *fin_count; int fin_cap;
     float2 *eval_out;              // [G][8] (value, variance) per child slot; slot 7 = the leaf itself
     float *rollout_val;            // [G]
     // distributional mode (agents/core_distributional.py; BASELINE config 5): node-indexed statistics and value histograms

@@ -119,6 +119,16 @@ class BatchedEngine:
         L.check(L.lib().b200_play_move(self.h, int(sims), int(auto_reset), L.ptr(actions), L.ptr(stats)))
         return actions, stats
 
+    def finished_games(self):
+        """Episodes that ended (and were reset) since the last call: int32[k,4] rows {game, score, line_clears, episode}, sorted by game
+        (play.py:161-177: the numbers of its `Episode:` line)."""
+        cap = 4 * self.n_games
+        out = np.zeros((cap, 4), np.int32)
+        cnt = np.zeros(1, np.int32)
+        L.check(L.lib().b200_finished_games(self.h, L.ptr(out), cap, L.ptr(cnt)))
+        rows = out[:min(int(cnt[0]), cap)]
+        return rows[np.lexsort((rows[:, 3], rows[:, 0]))]
+
     def sync(self):
         L.check(L.lib().b200_sync(self.h))
 
