@@ -166,6 +166,33 @@ int b200_collect_samples_dev(b200_engine *e, int min_visits, void *out_dev, int 
 int b200_replay_enable(b200_engine *e, int min_visits, int capacity);
 int b200_replay_drain_dev(b200_engine *e, void *out_dev, int capacity, int32_t *count_out);
 
+/* --- value-network training step: Model_VV._loss / Model.train / Yogi.step / Model_VV.train_data of the reference
+ *     (model/model_vv.py:94-153,227-231, model/model.py:52-119, model/yogi.py:39-90) on the device.  weights = the state_dict vector of
+ *     b200_load_weights (PyTorch layouts); a batch is {states int8[n][200], value f32[n], variance f32[n], weight f32[n]} (the four arrays
+ *     of ValueSim.memory, agents/ValueSim.py:25-30).  Host logic that stays on the host (validation split, batch sampling, early stopping,
+ *     checkpoint files): tetris_mcts_b200/model/model_vv.py Model_VV.train_data. */
+typedef struct b200_trainer b200_trainer;
+const char *b200_trainer_last_error(void);
+int b200_trainer_create(int device, const float *weights, int max_batch, b200_trainer **out);     /* Model_VV._init_model (model_vv.py:125-134) */
+int b200_trainer_destroy(b200_trainer *t);
+int b200_trainer_set_hyper(b200_trainer *t, double lr, double beta1, double beta2, double eps, double weight_decay);   /* Yogi(...) model_vv.py:132 */
+int b200_trainer_set_out_ubound(b200_trainer *t, float ub_value, float ub_variance);             /* model_vv.py:227-231 */
+int b200_trainer_get_weights(b200_trainer *t, float *weights_out);                               /* model.state_dict() */
+int b200_trainer_set_weights(b200_trainer *t, const float *weights);                             /* model.load_state_dict() */
+int b200_trainer_get_state(b200_trainer *t, float *exp_avg, float *exp_avg_sq, int64_t *step);   /* optimizer.state_dict(); step -1 = no state yet */
+int b200_trainer_set_state(b200_trainer *t, const float *exp_avg, const float *exp_avg_sq, int64_t step);   /* load_state_dict; step < 0 = reset_optimizer */
+int b200_trainer_get_grads(b200_trainer *t, float *grads_out);                                   /* p.grad of the last step, state_dict order (478338 floats) */
+/* Model_VV._loss under no_grad on one chunk (Model.compute_loss, model/model.py:52-83): mean and population std of (weight *) logl; pred_out NULL or [n][2] */
+int b200_trainer_loss(b200_trainer *t, const int8_t *states, const float *value, const float *variance, const float *weight, int n,
+                      int weighted, double *loss, double *loss_std, float *pred_out);
+/* Model.train (model/model.py:95-119): forward, loss, backward, gradient norm, clip when grad_clip > 0, Yogi step */
+int b200_trainer_step(b200_trainer *t, const int8_t *states, const float *value, const float *variance, const float *weight, int n,
+                      int weighted, double grad_clip, double *loss, double *loss_std, double *grad_norm);
+/* the same step on a batch gathered ON THE DEVICE from 212-byte replay rows (b200_replay_drain_dev / the all-gather block): idx[n] (host) are row
+ * indices (np.random.choice, model/model.py:207), weight = visit * weight_scale (weights / weights.mean(), model/model.py:186-187) */
+int b200_trainer_step_rows_dev(b200_trainer *t, const void *rows_dev, int n_rows, const int32_t *idx, int n, float weight_scale,
+                               int weighted, double grad_clip, double *loss, double *loss_std, double *grad_norm);
+
 #ifdef __cplusplus
 }
 #endif

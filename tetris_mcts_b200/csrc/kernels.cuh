@@ -6,13 +6,13 @@
 
 namespace b200 {
 
-#ifndef B200_ONE_GAME_PER_WARP
-#define B200_ONE_GAME_PER_WARP 0   // development aid (A/B): k_select_expand with one game per warp (lanes 8-31 idle) to measure what four
-                                   // independent walks per warp cost each other
+#ifndef B200_GAMES_PER_WARP
+#define B200_GAMES_PER_WARP 4      // development aid (A/B): k_select_expand with 1 or 2 games per warp (the other 8-lane groups idle) to measure
+                                   // what independent walks sharing a warp cost each other (every load waits for the slowest group's miss)
 #endif
 constexpr int GROUPS_PER_BLOCK = 16;
 constexpr int TPB = GROUPS_PER_BLOCK * 8;
-constexpr int SE_GAMES_PER_BLOCK = B200_ONE_GAME_PER_WARP ? TPB / 32 : GROUPS_PER_BLOCK;
+constexpr int SE_GAMES_PER_BLOCK = (TPB / 32) * B200_GAMES_PER_WARP;
 
 __device__ __forceinline__ void load_rec(const uint32_t *src, uint32_t (&w)[REC_WORDS]) {
 #pragma unroll
@@ -175,22 +175,31 @@ template <int NL> __device__ __forceinline__ void backup_game(const Arena &A, in
 // What one group hands to the CTA-level epilogue of k_select_expand: its evaluation request (per lane) and its counters.
 struct GroupOut { bool ask; int my_o; int sims, D, expanded, new_nodes; };
 
+// The whole warp calls this together (four games per warp): the walk runs in lockstep over the four groups (select_trace, GrpW);
+// everything around it is per group.  `g` >= A.G marks a group without a game.
 __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &gp, int g, const float *s_z, uint32_t *stage, GroupOut &out) {
-    int status = A.status[g];
-    const bool do_prof = A.prof && (g & 63) == 0 && gp.lane == 0;
+    const bool valid = g < A.G;
+    int status = valid ? A.status[g] : ST_ARENA_FULL;
+    const bool do_prof = valid && A.prof && (g & 63) == 0 && gp.lane == 0;
     long long ptick = do_prof ? clock64() : 0;
 #if B200_FUSED_BACKUP
     // the previous simulation of this game is folded into the statistics first (k_backup's work, see backup_game)
-    if (status == ST_OK && A.mode != MODE_DIST) backup_game<8>(A, g, gp.mask, gp.lane);
+    if (valid && status == ST_OK && A.mode != MODE_DIST) backup_game<8>(A, g, gp.mask, gp.lane);
     if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[5], (unsigned long long)(_n - ptick)); ptick = _n; }
 #endif
-    if ((status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) reset_tree(A, gp, g, status);
-    if (status != ST_OK) return;
-    ArenaAcc acc(A, g, s_z);
+    if (valid && (status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) reset_tree(A, gp, g, status);
+    const bool active = valid && status == ST_OK;
+    ArenaAcc acc(A, valid ? g : 0, s_z);
     int D = 0;
 #define TREE_PROF(i) do { if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[i], (unsigned long long)(_n - ptick)); ptick = _n; } } while (0)
-    int leaf = A.mode == MODE_DIST ? dist_select_group(A, gp, g, A.root[g], D, status)
-                                   : select_trace(acc, gp, A.root[g], A.low, A.trace_max, D, status);
+    int leaf = 0;
+    if (A.mode == MODE_DIST) {               // grid-uniform branch; the distributional walk keeps its per-group form
+        if (active) leaf = dist_select_group(A, gp, g, A.root[g], D, status);
+    } else {
+        __syncwarp();
+        leaf = select_trace(acc, active, active ? A.root[g] : 0, A.low, A.trace_max, D, status);
+    }
+    if (!active) return;
     if (status != ST_OK) { if (gp.lane == 0) A.status[g] = status; return; }
     TREE_PROF(0);
     uint32_t w[REC_WORDS];
@@ -241,13 +250,14 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
     Grp gp;
-#if B200_ONE_GAME_PER_WARP
-    const int g = (threadIdx.x & 31) < 8 ? blockIdx.x * SE_GAMES_PER_BLOCK + (threadIdx.x >> 5) : A.G;
+#if B200_GAMES_PER_WARP < 4
+    const int g = (threadIdx.x & 31) < 8 * B200_GAMES_PER_WARP
+                      ? blockIdx.x * SE_GAMES_PER_BLOCK + (threadIdx.x >> 5) * B200_GAMES_PER_WARP + ((threadIdx.x & 31) >> 3) : A.G;
 #else
     const int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
 #endif
     GroupOut out{false, 0, 0, 0, 0, 0};
-    if (g < A.G) select_expand_group(A, gp, g, s_z, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS, out);
+    select_expand_group(A, gp, g, s_z, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS, out);
     __syncwarp();
     const unsigned askmask = __ballot_sync(0xffffffffu, out.ask);
     if ((threadIdx.x & 31) == 0) s_wreq[threadIdx.x >> 5] = __popc(askmask);
@@ -807,13 +817,11 @@ struct TwinArgs {
     int32_t *trace; uint32_t *rng; int32_t *out;
 };
 
-__global__ void k_twin_select(Arena A, TwinArgs t, int index, int low, int max_trace) {
-    Grp gp;
-    if (threadIdx.x >= 8) return;
+__global__ void k_twin_select(Arena A, TwinArgs t, int index, int low, int max_trace) {   // one warp; the first 8-lane group owns the tree
     RefAcc acc{t.child, t.visit, t.value, t.variance, t.score, t.n2o, t.trace, t.rng, &A};
     int D = 0, status = ST_OK;
-    select_trace(acc, gp, index, low, max_trace, D, status);
-    if (gp.lane == 0) { t.out[0] = D; t.out[1] = status; }
+    select_trace(acc, threadIdx.x < 8, index, low, max_trace, D, status);
+    if (threadIdx.x == 0) { t.out[0] = D; t.out[1] = status; }
 }
 
 __global__ void k_twin_unique(Arena A, TwinArgs t, int index) {

@@ -87,6 +87,22 @@ struct Grp {
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 
+// The same interface with the CONSTANT full mask: legal only where all 32 lanes of the warp are converged (the four groups of a warp
+// in lockstep).  A sub-warp mask held in a register makes nvcc guard every shuffle / vote with MATCH.ANY + REDUX + VOTEU + a divergence
+// branch (~70 clk on the dependent chain, ~16 of them per level of the walk); with the literal 0xffffffff the guard disappears.
+struct GrpW {
+    static constexpr unsigned mask = 0xffffffffu;
+    int lane; unsigned shift;
+    __device__ __forceinline__ GrpW() {
+        int l = threadIdx.x & 31;
+        lane = l & 7;
+        shift = (unsigned)(l & 24);
+    }
+    template <typename T> __device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(0xffffffffu, v, src, 8); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(0xffffffffu, p) >> shift) & 0xffu; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
 __device__ __forceinline__ size_t node_at(const Arena &A, int g, int i) { return (size_t)g * A.M + i; }
 
 // ------------------------------------------------------------------ exact arithmetic (see header comment)
@@ -130,7 +146,8 @@ __device__ __forceinline__ void welford_level(int4 &st, double &v, double var, f
 // strictly largest score, earliest on ties).
 struct Uniq { bool is_first; int rep_c; float rep_s; unsigned first_mask; int rep_lane; };
 
-__device__ __forceinline__ Uniq unique_children(const Grp &gp, int c, int o, float s) {
+template <typename G>
+__device__ __forceinline__ Uniq unique_children(const G &gp, int c, int o, float s) {
     bool valid = gp.lane < 7 && c != 0;
     unsigned vmask = gp.ballot(valid);
     int first = -1, rep_c = 0, rep_lane = 0;
@@ -165,7 +182,7 @@ __device__ __forceinline__ uint32_t link_word(const Uniq &u) {
 #define B200_WARM_EXPAND 1
 #endif
 #ifndef B200_WARM_SELECT
-#define B200_WARM_SELECT 1   // measured -1 % on k_select_expand (B200, 16384 games)
+#define B200_WARM_SELECT 0   // round 1 (moves 0-3, shallow trees): -1 % on k_select_expand; round 2 (moves 0-5, mean depth 36-62): +13 % -> off
 #endif
 // L2 residency hints (performance only).  One simulation step streams ~200 MB of activations (conv -> fc) and ~20 MB of new
 // nodes through the 126 MB L2, so without hints nothing of the trees survives from one step to the next although every step
@@ -229,25 +246,31 @@ struct ArenaAcc {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
         o = row[15]; s = __int_as_float(row[23]);
     }
-    // one level of select: observation of this lane's child, the node's own score, the cached de-duplication
-    __device__ __forceinline__ void level(const Grp &gp, int idx, int depth, int &o, float &s_idx, Uniq &u) const {
+    // one level of select: observation of this lane's child, the node's own score, the cached de-duplication.  `on` = this lane's group
+    // is still walking (the loads are predicated, the shuffles are executed by every lane: see GrpW)
+    template <typename G>
+    __device__ __forceinline__ void level(const G &gp, bool on, int idx, int depth, int &o, float &s_idx, Uniq &u) const {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS + gp.lane;
+        float s = 0.f; uint32_t lw = 0u;
+        o = 0;
+        if (on) {
 #if B200_L2_HOT_LEVELS > 0
-        const uint64_t pol = l2_policy(depth < B200_L2_HOT_LEVELS);
-        o = ldg_hint(row + 8, pol);
-        const float s = __int_as_float(ldg_hint(row + 16, pol));
-        const uint32_t lw = (uint32_t)ldg_hint(row + 24, pol);
+            const uint64_t pol = l2_policy(depth < B200_L2_HOT_LEVELS);
+            o = ldg_hint(row + 8, pol);
+            s = __int_as_float(ldg_hint(row + 16, pol));
+            lw = (uint32_t)ldg_hint(row + 24, pol);
 #else
-        o = row[8];
-        const float s = __int_as_float(row[16]);
-        const uint32_t lw = (uint32_t)row[24];
+            o = row[8];
+            s = __int_as_float(row[16]);
+            lw = (uint32_t)row[24];
 #endif
+        }
         s_idx = gp.bcast(s, 7);
         u.is_first = lw >> 31; u.rep_lane = (int)((lw >> 28) & 7u); u.rep_c = (int)(lw & LINK_NODE_MASK);
         u.rep_s = gp.bcast(s, u.rep_lane);
         u.first_mask = gp.ballot(u.is_first);
 #if B200_WARM_SELECT
-        if (u.is_first) {   // start fetching every candidate child's row while the statistics are loaded and compared
+        if (on && u.is_first) {   // start fetching every candidate child's row while the statistics are loaded and compared
             const int32_t *cr = rowg + (size_t)u.rep_c * ROW_WORDS;
             touch32(cr + 8); touch32(cr + 16); touch32(cr + 24);
         }
@@ -294,9 +317,11 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
         else { c = 0; o = n2o[idx]; s = score[idx]; }
     }
     __device__ __forceinline__ void meta(int idx, int &o, float &s) const { o = n2o[idx]; s = score[idx]; }
-    __device__ __forceinline__ void level(const Grp &gp, int idx, int, int &o, float &s_idx, Uniq &u) const {
-        int c; float s;
-        children(idx, gp.lane, c, o, s);
+    template <typename G>
+    __device__ __forceinline__ void level(const G &gp, bool on, int idx, int, int &o, float &s_idx, Uniq &u) const {
+        int c = 0; float s = 0.f;
+        o = 0;
+        if (on) children(idx, gp.lane, c, o, s);
         s_idx = gp.bcast(s, 7);
         u = unique_children(gp, c, o, s);
     }
@@ -314,64 +339,77 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
 #ifndef B200_SELECT_PROF
 #define B200_SELECT_PROF 0   // development aid: clock64 split of one walk level (row line landed | statistics landed | child picked), sampled groups
 #endif
+// Warp-lockstep walk: the four 8-lane groups of a warp descend their four trees level by level TOGETHER, all 32 lanes converged, so
+// that every shuffle and vote carries the literal full mask (GrpW).  `active` = this lane's group has a tree to walk; a group that
+// has reached its leaf idles (predicated) until the deepest of the four is done.  Returns the leaf; writes the trace; all 8 lanes of
+// a group return the same values.  The whole warp must call this together.
 template <typename Acc>
-__device__ __forceinline__ int select_trace(const Acc &acc, const Grp &gp, int root, int low, int trace_max, int &D_out, int &status) {
+__device__ __forceinline__ int select_trace(const Acc &acc, bool active, int root, int low, int trace_max, int &D_out, int &status) {
+    const GrpW gp;
     int idx = root, D = 0;
+    bool walking = active;
 #if B200_SELECT_PROF
-    unsigned long long *lp = gp.lane == 0 ? acc.level_prof() : nullptr;
+    unsigned long long *lp = (active && gp.lane == 0) ? acc.level_prof() : nullptr;
     long long lt = lp ? clock64() : 0;
-#define LEVEL_PROF(i) do { if (lp) { const long long _n = clock64(); atomicAdd(&lp[i], (unsigned long long)(_n - lt)); lt = _n; } } while (0)
+#define LEVEL_PROF(i) do { if (lp && walking) { const long long _n = clock64(); atomicAdd(&lp[i], (unsigned long long)(_n - lt)); lt = _n; } } while (0)
 #else
 #define LEVEL_PROF(i) do { } while (0)
 #endif
-    for (;;) {
-        if (D >= trace_max) { status = ST_TRACE_FULL; break; }
-        if (gp.lane == 0) acc.put_trace(D, idx);
-        ++D;
+    while (__any_sync(0xffffffffu, walking)) {
+        if (walking && D >= trace_max) { status = ST_TRACE_FULL; walking = false; }
+        if (walking) {
+            if (gp.lane == 0) acc.put_trace(D, idx);
+            ++D;
+        }
         int o; float s_idx;
         Uniq u;
-        acc.level(gp, idx, D - 1, o, s_idx, u);
+        acc.level(gp, walking, idx, D - 1, o, s_idx, u);
         LEVEL_PROF(0);
-        if (u.first_mask == 0) break;                                   // core.h:200 no children: leaf
+        if (u.first_mask == 0) walking = false;                         // core.h:200 no children: leaf (group-uniform)
         int4 st = make_int4(0, 0, 0, 0);
-        if (u.is_first) st = acc.stat(o, D);                            // the children live one level below
-        unsigned lowmask = gp.ballot(u.is_first && st.x < low);          // core.h:65-77
+        if (walking && u.is_first) st = acc.stat(o, D);                 // the children live one level below
+        const unsigned lowmask = gp.ballot(walking && u.is_first && st.x < low);   // core.h:65-77
         LEVEL_PROF(1);
-        int pick;
-        if (lowmask) {
+        int pick = 0;
+        if (__any_sync(0xffffffffu, lowmask != 0u)) {                   // warp-uniform branch: the draw of every group that needs one
             uint32_t r = 0;
-            if (gp.lane == 0) r = acc.rand();
+            if (lowmask != 0u && gp.lane == 0) r = acc.rand();
             r = gp.bcast(r, 0);
-            pick = (int)__fns(lowmask, 0, (int)(r % (uint32_t)__popc(lowmask)) + 1);
-        } else {
-            int n = u.is_first ? st.x : 0;                               // core.h:88 accumulate(visit)
-            n += __shfl_xor_sync(gp.mask, n, 1, 8);
-            n += __shfl_xor_sync(gp.mask, n, 2, 8);
-            n += __shfl_xor_sync(gp.mask, n, 4, 8);
-            float z = acc.z(n);
-            float q = u.is_first ? clt_q(__int_as_float(st.y), u.rep_s, s_idx, z, __int_as_float(st.z), st.x) : 0.f;
+            if (lowmask != 0u) pick = (int)__fns(lowmask, 0, (int)(r % (uint32_t)__popc(lowmask)) + 1);
+        }
+        {
+            int n = (walking && u.is_first) ? st.x : 0;                  // core.h:88 accumulate(visit)
+            n += __shfl_xor_sync(0xffffffffu, n, 1, 8);
+            n += __shfl_xor_sync(0xffffffffu, n, 2, 8);
+            n += __shfl_xor_sync(0xffffffffu, n, 4, 8);
+            const float z = acc.z(n);
+            const bool cmp = walking && u.is_first;
+            const float q = cmp ? clt_q(__int_as_float(st.y), u.rep_s, s_idx, z, __int_as_float(st.z), st.x) : 0.f;
             // core.h:94-101: the first strict maximum in list order = the largest q, the lowest lane on ties, as a 3-step
             // butterfly.  A NaN never wins a `>`; it is the answer only when it is the first entry of the list.
-            const bool cand = u.is_first && q == q;
+            const bool cand = cmp && q == q;
             float qv = cand ? q : -INFINITY;
             int ql = cand ? gp.lane : 8 + gp.lane;                       // non-candidates lose every tie
 #pragma unroll
             for (int d = 1; d < 8; d <<= 1) {
-                const float oq = __shfl_xor_sync(gp.mask, qv, d, 8);
-                const int ol = __shfl_xor_sync(gp.mask, ql, d, 8);
+                const float oq = __shfl_xor_sync(0xffffffffu, qv, d, 8);
+                const int ol = __shfl_xor_sync(0xffffffffu, ql, d, 8);
                 const bool take = oq > qv || (oq == qv && ol < ql);
                 qv = take ? oq : qv; ql = take ? ol : ql;
             }
             const int first = __ffs(u.first_mask) - 1;
-            pick = ((gp.ballot(q != q) >> first) & 1u) ? first : ql;
+            const unsigned nanmask = gp.ballot(cmp && q != q);
+            if (lowmask == 0u) pick = (first >= 0 && ((nanmask >> first) & 1u)) ? first : ql;
         }
-        idx = gp.bcast(u.rep_c, pick);
+        const int next = gp.bcast(u.rep_c, pick);
+        if (walking) idx = next;
         LEVEL_PROF(2);
 #if B200_SELECT_PROF
-        if (lp) atomicAdd(&lp[3], 1ull);
+        if (lp && walking) atomicAdd(&lp[3], 1ull);
 #endif
     }
 #undef LEVEL_PROF
+    __syncwarp();
     D_out = D;
     return idx;
 }

@@ -48,7 +48,23 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity);
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef B200_MBAR_FASTPATH
+#define B200_MBAR_FASTPATH 1   // most waits of the conv pipeline find their phase already complete: one warp-wide test_wait (a broadcast read)
+#endif                         // answers that without the lane-0 poll + __syncwarp round trip
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+#if B200_MBAR_FASTPATH
+    if (__all_sync(0xffffffffu, mbar_test(bar, parity))) return;
+#endif
     if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
     __syncwarp();
 }
