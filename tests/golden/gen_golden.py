@@ -9,6 +9,8 @@
   agent_cpp_golden.npz  actions / game records of the reference's own C++ agent twin (agents/cppmodule/agent.cpp compiled unchanged)
   agent_modes_golden.npz  the reference's own agents/ValueSim.py and agents/Vanilla.py (the other two mcts loops); their
                       rand() / randint draw from the oracle's xorshift stream (oracle/rand_shim.c, LD_PRELOAD)
+  train_golden.npz    optimiser steps of the reference's own Model_VV.train (model/model.py:95-119, GaussianLL model_vv.py:94-101,
+                      Yogi model/yogi.py) on torch CPU; the torch-1.x overloads those files call are re-created at run time
 Run:  python tests/golden/gen_golden.py      (needs /root/reference and `make -C oracle`)"""
 import os
 import sys
@@ -275,6 +277,119 @@ def gen_agent_cpp(pt):
     print("agent_cpp_golden: %d cases, %s moves" % (len(cases), [c["moves"] for c in cases]))
 
 
+
+def legacy_torch_overloads():
+    """The reference's training code calls torch-1.x overloads that torch 2.x removed: Tensor.add_(Number alpha, Tensor other) and
+    Tensor.add(Number, Tensor) (model/model_vv.py:100, model/yogi.py:71,74), addcmul_(Number, Tensor, Tensor) (yogi.py:78-82),
+    addcdiv_(Number, Tensor, Tensor) (yogi.py:88).  To RUN THE REFERENCE FILES UNMODIFIED this generator re-creates exactly those
+    signatures on torch.Tensor for the duration of the run (alpha-first forms forwarded to the modern keyword forms; same arithmetic)."""
+    import numbers
+    import torch
+    T = torch.Tensor
+    orig = dict(add_=T.add_, add=T.add, addcmul_=T.addcmul_, addcdiv_=T.addcdiv_)
+
+    def add_(self, *a, **k):
+        if len(a) == 2 and isinstance(a[0], numbers.Number) and isinstance(a[1], torch.Tensor):
+            return orig["add_"](self, a[1], alpha=a[0])
+        return orig["add_"](self, *a, **k)
+
+    def add(self, *a, **k):
+        if len(a) == 2 and isinstance(a[0], numbers.Number) and isinstance(a[1], torch.Tensor):
+            return orig["add"](self, a[1], alpha=a[0])
+        return orig["add"](self, *a, **k)
+
+    def addcmul_(self, *a, **k):
+        if len(a) == 3 and isinstance(a[0], numbers.Number):
+            return orig["addcmul_"](self, a[1], a[2], value=a[0])
+        return orig["addcmul_"](self, *a, **k)
+
+    def addcdiv_(self, *a, **k):
+        if len(a) == 3 and isinstance(a[0], numbers.Number):
+            return orig["addcdiv_"](self, a[1], a[2], value=a[0])
+        return orig["addcdiv_"](self, *a, **k)
+
+    T.add_, T.add, T.addcmul_, T.addcdiv_ = add_, add, addcmul_, addcdiv_
+    return orig
+
+
+def gen_train():
+    """train_golden.npz: the reference's own Model_VV (model/model_vv.py:104-231, torch CPU, Yogi model/yogi.py) taking optimiser steps on a
+    seeded batch — Model.train(batch, weighted=...) (model/model.py:95-119) called exactly as Model.train_data does (:207-209).
+    Recorded: loss / loss_std / gradient norm of every step, the gradients of the first step, the weights and the optimiser state after
+    the last step (large tensors strided), Model.compute_loss on a validation chunk, and a clipped-gradient step."""
+    import torch
+    from model.model_vv import Model_VV
+    torch.set_num_threads(1)
+    legacy_torch_overloads()
+    rng = np.random.default_rng(11)
+    n = 96
+    g = O.Game(seed=9)
+    states = []
+    while len(states) < n:                                    # positions of real (random-play) games: {0, 1, -1} as agents/agent.py:122 stores them
+        if g.end:
+            g.reset()
+        g.play(int(rng.integers(0, 7)))
+        states.append(g.state())
+    states = np.stack(states).astype(np.int8)
+    value = rng.uniform(0, 60, (n, 1)).astype(np.float32)
+    variance = rng.uniform(0.0, 400, (n, 1)).astype(np.float32)
+    variance[:6] = 0.01                                       # below variance_bound: clamped to 0.1 (model_vv.py:140)
+    visit = rng.integers(25, 400, (n, 1)).astype(np.float32)
+    weight = (visit / visit.mean()).astype(np.float32)        # model/model.py:186-187
+    out = dict(states=states, value=value, variance=variance, weight=weight, seed=0)
+    names = ["head.conv1.weight", "head.conv1.bias", "head.conv2.weight", "head.conv2.bias", "head.conv3.weight", "head.conv3.bias",
+             "head.fc1.weight", "head.fc1.bias", "head.fc_out.weight", "head.fc_out.bias"]
+
+    def fresh():
+        m = Model_VV(use_cuda=False)
+        sd = {k: torch.from_numpy(v.copy()) for k, v in O.weights_to_state_dict(O.seeded_weights(0)).items()}
+        m.model.load_state_dict(sd)
+        m.model.out_ubound = torch.tensor([float(value.max()), float(variance.max())])     # Model_VV.train_data, model_vv.py:227-231
+        m.training(True)
+        return m
+
+    def flat(m, what):
+        params = dict(m.model.named_parameters())
+        if what == "w":
+            return np.concatenate([params[k].detach().numpy().ravel() for k in names]).astype(np.float32)
+        if what == "g":
+            return np.concatenate([params[k].grad.detach().numpy().ravel() for k in names]).astype(np.float32)
+        st = m.optimizer.state
+        return np.concatenate([st[params[k]][what].detach().numpy().ravel() for k in names]).astype(np.float32)
+
+    batch = lambda: [states[:, None, :, :].astype(np.float32), value.copy(), variance.copy(), weight.copy()]   # noqa: E731
+    out["ubound"] = np.array([value.max(), variance.max()], np.float32)
+    for tag, weighted, clip, steps in (("w", True, 0.0, 3), ("u", False, 0.0, 1), ("c", True, 0.5, 1)):
+        m = fresh()
+        rec = []
+        for it in range(steps):
+            r = m.train(batch(), grad_clip=clip, weighted=weighted)
+            rec.append([r["loss"], r["loss_std"], r["grad_norm"]])
+            if it == 0:
+                out[tag + "_grad0"] = flat(m, "g")            # p.grad after the first backward (after clipping when clip > 0)
+        out[tag + "_steps"] = np.array(rec, np.float64)
+        out[tag + "_weights"] = flat(m, "w")
+        if tag == "w":
+            out[tag + "_exp_avg"] = flat(m, "exp_avg")
+            out[tag + "_exp_avg_sq"] = flat(m, "exp_avg_sq")
+            m.training(False)
+            val = m.compute_loss([b[:40] for b in batch()], weighted=True, chunksize=16)     # model/model.py:52-83
+            out["w_val"] = np.array([val["loss"], val["loss_std"]], np.float64)
+            v, var = m.inference(states[:8, None, :, :])
+            out["w_pred"] = np.concatenate([v, var], axis=1).astype(np.float32)
+    # keep the fixture small: fc1.weight (458752 values) strided, everything else in full
+    lo, hi = 18816, 18816 + 458752
+    keep = np.ones(478338, bool)
+    keep[lo:hi] = False
+    keep[lo:hi:97] = True
+    out["keep_index"] = np.nonzero(keep)[0].astype(np.int32)
+    for k in list(out):
+        if isinstance(out[k], np.ndarray) and out[k].shape == (478338,):
+            out[k] = out[k][keep]
+    np.savez_compressed(os.path.join(HERE, "train_golden.npz"), **out)
+    print("train_golden: %d samples; steps (loss, std, gnorm):\n%s" % (n, out["w_steps"]))
+
+
 def gen_dist():
     """Outputs of the reference's own numba cores (agents/core_distributional.py) on seeded inputs."""
     import agents.core_distributional as R
@@ -326,6 +441,8 @@ if __name__ == "__main__":
     pt, core = O.mount_reference()
     if "--dist" in sys.argv:
         gen_dist()
+    elif "--train" in sys.argv:
+        gen_train()
     elif "--agent-gc" in sys.argv:
         gen_agent_explicit_gc(pt)
     elif "--agent-modes" in sys.argv:
@@ -339,5 +456,6 @@ if __name__ == "__main__":
         gen_agent_explicit_gc(pt)
         gen_agent_cpp(pt)
         gen_dist()
+        gen_train()
         import subprocess
         subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-modes"], check=True)

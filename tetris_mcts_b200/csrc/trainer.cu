@@ -196,9 +196,6 @@ __global__ void k_flat_to_nhwc_relu(const float *__restrict__ dflat, const float
         d[((size_t)b * 56 + p) * 32 + c] = flat[i] > 0.f ? dflat[i] : 0.f;
     }
 }
-__global__ void k_relu_mask(const float *__restrict__ act, size_t n, float *__restrict__ d) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) if (!(act[i] > 0.f)) d[i] = 0.f;
-}
 
 // ------------------------------------------------------------------------------------------------ head: fc_out, sigmoid, bounds, loss
 // One thread per sample: z = h . Wo^T + bo (fp64 accumulate), s = sigmoid(z), pred = s * ub + lb (model_vv.py:48-52), GaussianLL

@@ -201,8 +201,8 @@ constexpr int TCC_OFF_W1 = TCC_OFF_W3 + TCC_WBYTES;
 constexpr int TCC_OFF_A1 = TCC_OFF_W1 + TCC_W1BYTES;
 constexpr int TCC_OFF_IM = TCC_OFF_A1 + TCC_SLOTS * TCC_ASLOT;
 constexpr int TCC_OFF_BIAS = TCC_OFF_IM + TCC_SLOTS * TCC_IMSLOT;   // 96 floats
-constexpr int TCC_OFF_KEY = TCC_OFF_BIAS + 96 * 4;                  // TCC_SLOTS x 16 key words (ring)
-constexpr int TCC_OFF_BAR = TCC_OFF_KEY + TCC_SLOTS * 16 * 4;       // 7 x TCC_SLOTS mbarriers + tmem pointer
+constexpr int TCC_OFF_KEY = TCC_OFF_BIAS + 96 * 4;                  // TCC_SLOTS x 32 words: the front-end warp's row table (20 rows: settled | piece << 16)
+constexpr int TCC_OFF_BAR = TCC_OFF_KEY + TCC_SLOTS * 32 * 4;       // 7 x TCC_SLOTS mbarriers + tmem pointer
 constexpr int TCC_SMEM = TCC_OFF_BAR + 7 * TCC_SLOTS * 8 + 16;
 constexpr int TCC_TMEM_COLS = 512;          // 4 slots x 128 columns; a slot's three accumulators reuse the same columns in turn
 constexpr int ACT3_KCHUNKS = 224;           // 1792 / 8
@@ -289,7 +289,6 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     constexpr int NS = TCC_SLOTS;
     uint64_t *bar_c1 = bars, *bar_c2 = bars + NS, *bar_c3 = bars + 2 * NS;             // tensor core -> workers: layer of slot done
     uint64_t *bar_a0 = bars + 3 * NS, *bar_a1 = bars + 4 * NS, *bar_a2 = bars + 5 * NS; // workers -> issuer: operand of slot written
-    uint64_t *bar_k = bars + 6 * NS;                                                    // loader -> workers: key of slot landed
     uint32_t *sKey = reinterpret_cast<uint32_t *>(smem + TCC_OFF_KEY);
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + TCC_OFF_BAR + 7 * NS * 8);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -303,7 +302,8 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     if (t < 32) { sB[t] = W.b1[t]; sB[32 + t] = W.b2[t]; sB[64 + t] = W.b3[t]; }
     if (t == 0) {
         for (int i = 0; i < 3 * NS; ++i) mbar_init(&bars[i], 1);
-        for (int i = 3 * NS; i < 6 * NS; ++i) mbar_init(&bars[i], TCC_WORKERS / 32);      // one arrival per worker warp
+        for (int i = 3 * NS; i < 4 * NS; ++i) mbar_init(&bars[i], 1);                      // a0: the front-end warp alone builds the conv1 operand
+        for (int i = 4 * NS; i < 6 * NS; ++i) mbar_init(&bars[i], TCC_WORKERS / 32);      // a1, a2: one arrival per worker warp
         for (int i = 6 * NS; i < 7 * NS; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
@@ -375,9 +375,11 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
             if (prof && do_prof) for (int i = 12; i < 14; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
         }
     } else if (warp == TCC_LOADER) {
-        // ===================================================== key loader: global loads stay out of the workers' way (their
-        // proxy fences would otherwise wait for every outstanding load).  A key is a random 48-byte read from an arena of tens
-        // of GB (~2.4 k clk); TCC_KEYS_AHEAD of them are kept in flight so that the loader never paces the workers.
+        // ===================================================== front end (one warp): observation key -> conv1 operand.
+        // A key is a random 48-byte read from an arena of tens of GB (~2.4 k clk); TCC_KEYS_AHEAD of them are kept in flight.  The same
+        // warp then builds the im2col operand of conv1 (fp16, exact {-1,0,1}): row p = y*8 + x of the 18x8 output grid, k = tap = dy*3 + dx,
+        // taps 0..7 as ONE 16-byte store, tap 8 in the second k chunk.  (Round 1 had all 16 worker warps build it, 27 % of their cycle;
+        // one warp running up to TCC_SLOTS boards ahead of the epilogues does it off the workers' critical path.)
         uint2 rqs = make_uint2(0, 0);
         uint32_t kq[TCC_KEYS_AHEAD];
         auto fetch = [&](int i) -> uint32_t {                       // whole warp; board i of this CTA (i < n_local)
@@ -393,11 +395,41 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                 const int i = i0 + j;
                 if (i >= n_local) break;
                 const int slot = i % NS;
-                if (i >= NS) mbar_wait_warp(&bar_c1[slot], (uint32_t)((i - NS) / NS) & 1u);     // conv1 of the slot's previous board done => its key was consumed
-                if (lane < 12) sKey[slot * 16 + lane] = kq[j];
+                // row table: lane r < 20 holds board row r: settled cells in bits 0..9, the falling piece's cells in bits 16..25
+                const uint32_t kw = kq[j];
+                const uint32_t rowpair = __shfl_sync(0xffffffffu, kw, (lane >> 1) & 15), pcs = __shfl_sync(0xffffffffu, kw, 10);
+                uint32_t tab = (rowpair >> ((lane & 1) * 16)) & 0x3ffu;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                    // the falling piece's cells (sorted bytes of key word 10)
+                    const uint32_t cell = (pcs >> (8 * k)) & 0xffu, pr = (cell * 205u) >> 11, pcol = cell - pr * 10u;
+                    tab |= (pr == (uint32_t)lane ? 1u : 0u) << (16 + pcol);
+                }
+                if (i + TCC_KEYS_AHEAD < n_local) kq[j] = fetch(i + TCC_KEYS_AHEAD);            // next key of this register, in flight while the operand is built
+                if (i >= NS) mbar_wait_warp(&bar_c1[slot], (uint32_t)((i - NS) / NS) & 1u);     // conv1 of the slot's previous board has read its operand
+                if (lane < 20) sKey[slot * 32 + lane] = tab;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_k[slot]);
-                if (i + TCC_KEYS_AHEAD < n_local) kq[j] = fetch(i + TCC_KEYS_AHEAD);
+                uint8_t *im = smem + TCC_OFF_IM + slot * TCC_IMSLOT;
+#pragma unroll
+                for (int pp = 0; pp < 5; ++pp) {                 // 144 pixels over 32 lanes
+                    const int p = pp * 32 + lane;
+                    if (p < 144) {
+                        const int y = p >> 3, x = p & 7;
+                        uint32_t hv[9];
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t rw = sKey[slot * 32 + y + dy] >> x;
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)       // 1 settled, -1 falling piece, 0 empty (model_vv.py:212)
+                                hv[dy * 3 + dx] = ((rw >> dx) & 1u) * 0x3C00u | ((rw >> (16 + dx)) & 1u) * 0xBC00u;
+                        }
+                        *reinterpret_cast<uint4 *>(im + p * 16) =
+                            make_uint4(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16), hv[4] | (hv[5] << 16), hv[6] | (hv[7] << 16));   // taps 0..7
+                        *reinterpret_cast<uint32_t *>(im + TCC_IMROWS * 16 + p * 16) = hv[8];                                        // tap 8
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a0[slot]);
             }
         }
     } else {
@@ -410,46 +442,6 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
 #pragma unroll
         for (int e = 0; e < 8; ++e) { bias1[e] = sB[cq * 8 + e]; bias2[e] = sB[32 + cq * 8 + e]; bias3[e] = sB[64 + cq * 8 + e]; }
         for (int i = 0; i < n_local + 3; ++i) {
-            // ---- S0(i): observation key -> im2col operand of conv1 (fp16, exact): row p = y*8 + x, k = tap = dy*3 + dx.
-            // Lanes 3k, 3k+1, 3k+2 of a warp hold the three filter rows of pixel p = 10*warp + k; lane 3k gathers them with two
-            // shuffles and writes the row's taps 0..7 as ONE 16-byte store (2-byte scatter stores were 4-way bank conflicted).
-            if (i < n_local) {
-                const int slot = i % NS;
-                const int pk = lane / 3, dy = lane - pk * 3, p = warp * 10 + pk, y = p >> 3, x = p & 7, r = y + dy;
-                const bool valid = lane < 30 && p < 144;                 // 15 warps x 10 pixels
-                mbar_wait_warp(&bar_k[slot], (uint32_t)(i / NS) & 1u);
-                PROF_T(7);
-                uint32_t lo = 0, hi = 0;
-                if (valid) {
-                    const uint32_t rowword = sKey[slot * 16 + (r >> 1)], pcs = sKey[slot * 16 + 10];
-                    const uint32_t settled = (rowword >> ((r & 1) * 16)) >> x;
-                    uint32_t piece = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {                // the falling piece's cells (sorted bytes of key word 10)
-                        const uint32_t cell = (pcs >> (8 * k)) & 0xffu, pr = (cell * 205u) >> 11, pcol = cell - pr * 10u;
-                        piece |= (pr == (uint32_t)r ? 1u : 0u) << pcol;
-                    }
-                    piece >>= x;
-                    uint32_t hv[3];
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx)               // 1 settled, -1 falling piece, 0 empty (model_vv.py:212)
-                        hv[dx] = ((settled >> dx) & 1u) * 0x3C00u | ((piece >> dx) & 1u) * 0xBC00u;
-                    lo = hv[0] | (hv[1] << 16); hi = hv[2];
-                }
-                const uint32_t a_lo = __shfl_down_sync(0xffffffffu, lo, 1), a_hi = __shfl_down_sync(0xffffffffu, hi, 1);
-                const uint32_t b_lo = __shfl_down_sync(0xffffffffu, lo, 2), b_hi = __shfl_down_sync(0xffffffffu, hi, 2);
-                if (valid && dy == 0) {
-                    uint8_t *row0 = smem + TCC_OFF_IM + slot * TCC_IMSLOT + p * 16;
-                    *reinterpret_cast<uint4 *>(row0) = make_uint4(lo, hi | (a_lo << 16), (a_lo >> 16) | (a_hi << 16), b_lo);   // taps 0..7
-                    *reinterpret_cast<uint32_t *>(row0 + TCC_IMROWS * 16) = b_hi;                                              // tap 8
-                }
-                PROF_T(14);
-                fence_async_smem();
-                PROF_T(15);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_a0[slot]);     // 32 same-address arrivals would serialise in the shared-memory pipe the MMAs read through
-                PROF_T(0);
-            }
             // ---- E2(i-2): conv2 epilogue: dx sum + bias + ReLU + split -> act2 (16x8 grid), in place of the slot's act1
             if (i >= 2 && i - 2 < n_local) {
                 const int j = i - 2, slot = j % NS;
