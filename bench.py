@@ -380,6 +380,8 @@ def run_b200(args, cfg):
     torch.cuda.synchronize()
     D.barrier()
     c1 = eng.counters()
+    longest_trace = c1.pop("max_trace_len", None)             # not cumulative: the longest trace of the last move
+    c0.pop("max_trace_len", None)
     launches = sum(n for _, n in eng.phase_ms().values())
     ms_max = D.max_over_ranks(ms, dev)
     delta = {k: c1[k] - c0[k] for k in c1}
@@ -400,6 +402,7 @@ def run_b200(args, cfg):
     phases = eng.phase_ms()
     eng.set_timing(False)
     p1 = eng.counters()
+    p0.pop("max_trace_len", None); p1.pop("max_trace_len", None)
     pdelta = {k: p1[k] - p0[k] for k in p1}
     eng.close()
     # ---- pass 3: end to end through the public API with HOST buffers; the exchange step inside the loop
@@ -439,6 +442,7 @@ def run_b200(args, cfg):
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
     D.barrier()
     e1 = eng.counters()
+    e0.pop("max_trace_len", None); e1.pop("max_trace_len", None)
     edelta = {k: e1[k] - e0[k] for k in e1}
     e2e_sims = D.sum_over_ranks({"sims": edelta["sims"]}, dev)["sims"]
     eng.close()
@@ -514,13 +518,14 @@ def run_b200(args, cfg):
                "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": G * 80 * world, "d2h_bytes_per_step": G * (4 + 84 + 80) * world,
                        "ms_per_step": 1e3 * e2e_s / steps, "includes": "set_games (H2D) + play_move (D2H actions, stats, status) + get_games (D2H) + replay drain + all-gather"},
                "same_workload": {"value_pass_vs_instrumented_vs_e2e": bool(same), "keys": list(WORK_KEYS),
+                                 "differing": {k: [delta[k], pdelta[k], edelta[k]] for k in WORK_KEYS if not (delta[k] == pdelta[k] == edelta[k])},
                                  "how": "three identical engines built from the same seeds, W warm-up moves, then the same K moves (deterministic search)"},
                "gpu_launches": int(launches), "clocks": clk.summary(), "trajectory_allgather": traj,
                "phases_ms_per_step": {k: v[0] / steps for k, v in phases.items()}, "instrumented_ms_per_step": ms_instr / steps,
                "phases_note": "value / ms_per_step: K steps on the production path (each simulation step replayed as one CUDA graph).  phases_ms_per_step, "
                               "roofline.*: the same K steps on a second identical engine with an event pair around every kernel (direct launches), "
                               "instrumented_ms_per_step long",
-               "counters_per_step": {k: v / steps for k, v in delta.items()}}
+               "counters_per_step": {k: v / steps for k, v in delta.items()}, "longest_trace_last_step": longest_trace}
     # ---- BASELINE configs[1] alongside (Vanilla MCTS, random rollouts, no value net): short, so it rides in the same line
     if cfg["mode"] == "lp" and not args.no_secondary:
         G2, sims2 = 4096, 300
@@ -538,7 +543,7 @@ def run_b200(args, cfg):
             e2.play_move(sims2, auto_reset=True, want_stats=False)
         ms2 = D.max_over_ranks(e2.timer_stop(), dev)
         k1 = e2.counters()
-        d2 = D.sum_over_ranks({k: k1[k] - k0[k] for k in k1}, dev)
+        d2 = D.sum_over_ranks({k: k1[k] - k0[k] for k in k1 if k != "max_trace_len"}, dev)
         e2.close()
         if out is not None:
             out["also_configs1_vanilla"] = {"workload": "BASELINE configs[1]: Vanilla MCTS, %d games/GPU, %d sims/move" % (G2, sims2), "value": d2["sims"] / (ms2 / 1e3),

@@ -77,8 +77,8 @@ int b200_update_root(b200_engine *e, int auto_reset);
 
 /* --- TreeAgent.remove_nodes (agents/agent.py:246-257; a public method, also reached from new_node :96-97 when the free list is
  * empty): collect every game that has fewer than min_free free node slots (INT_MAX: every game), as one batched launch.
- * b200_set_gc_headroom(n > 0) makes b200_update_root do that after re-rooting (the driver calling remove_nodes() between moves
- * whenever len(agent.available) < n); 0 (default) = only the reference's own call site, inside new_node. */
+ * b200_set_gc_headroom(n > 0) makes b200_update_root / b200_play_move do that after re-rooting (the driver calling remove_nodes() between
+ * moves whenever len(agent.available) < n; b200_set_games only re-roots); 0 (default) = only the reference's own call site, inside new_node. */
 int b200_remove_nodes(b200_engine *e, int min_free);
 int b200_set_gc_headroom(b200_engine *e, int min_free);
 
@@ -101,7 +101,8 @@ int b200_finished_games(b200_engine *e, int32_t *out4, int cap, int32_t *count_o
 
 int b200_status(b200_engine *e, int32_t *status);            /* per-game 0 ok / B200_ERR_ARENA_FULL / B200_ERR_TRACE_FULL */
 int b200_counters(b200_engine *e, uint64_t *out16);          /* 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels
-                                                                5 rollout steps 6 new nodes 7 tree resets 8 games finished 9 score sum 10 lines sum */
+                                                                5 rollout steps 6 new nodes 7 tree resets 8 games finished 9 score sum 10 lines sum
+                                                                12 longest trace of the last b200_run_sims (not cumulative) */
 int b200_sync(b200_engine *e);
 int b200_timer_start(b200_engine *e);                        /* CUDA-event stopwatch on the engine's stream (sync, then record) */
 int b200_timer_stop(b200_engine *e, float *ms);              /* record, wait, elapsed milliseconds since b200_timer_start */

@@ -14,6 +14,7 @@ import os
 TIMING = os.environ.get('NO_TIMING') != '1'
 eng.set_timing(TIMING)
 prev = eng.counters()
+pprev = {k: v[0] for k, v in eng.phase_ms().items()} if TIMING else None
 for mv in range(moves):
     t = time.time()
     try:
@@ -23,8 +24,14 @@ for mv in range(moves):
     dt = time.time() - t
     c = eng.counters()
     d = {k: c[k] - prev[k] for k in c}; prev = c
-    print('move %2d %.3fs sims/s %.3g new_nodes/game %.0f evals/sim %.2f D %.2f gcs %d resets %d finished %d' % (
-        mv, dt, G * sims / dt, d['new_nodes'] / G, d['eval_requests'] / max(d['sims'], 1), d['trace_levels'] / max(d['sims'], 1), d['gcs'], d['tree_resets'], c['games_finished']), flush=True)
+    ph = ''
+    if TIMING:
+        pm = {k: v[0] for k, v in eng.phase_ms().items()}
+        ph = ' | ms: ' + ' '.join('%s %.1f' % (k[:6], pm[k] - pprev[k]) for k in ('select_expand', 'conv', 'fc', 'backup', 'gc'))
+        pprev = pm
+    print('move %2d %.3fs sims/s %.3g new_nodes/game %.0f evals/sim %.2f D %.2f Dmax %d gcs %d resets %d finished %d%s' % (
+        mv, dt, G * sims / dt, d['new_nodes'] / G, d['eval_requests'] / max(d['sims'], 1), d['trace_levels'] / max(d['sims'], 1), c['max_trace_len'],
+        d['gcs'], d['tree_resets'], c['games_finished'], ph), flush=True)
 print({k: (round(v[0], 2), v[1]) for k, v in eng.phase_ms().items()})
 
 import ctypes

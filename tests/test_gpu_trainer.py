@@ -90,13 +90,17 @@ def test_validation_loss_inference_and_device_rows(gpu_lib, tmp_path):
     t1.close(); t2.close()
 
 
-def test_train_data_loop_lowers_the_loss_and_hot_swaps(gpu_lib, tmp_path, monkeypatch, capfd):
+def test_train_data_loop_lowers_the_loss_and_hot_swaps(gpu_lib, tmp_path, monkeypatch):
     """Model.train_data (model/model.py:176-249): split, batches, validation lines in the reference's log format (web/parseLog.py:61-66),
     early stopping with the best checkpoint re-loaded; the inference kernels then use the trained weights."""
+    import io
     import re
     from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.model import model_vv as MV
     from tetris_mcts_b200.model.model_vv import Model_VV
     monkeypatch.chdir(tmp_path)
+    log = io.StringIO()
+    monkeypatch.setattr(MV, "perr", dict(file=log, flush=True))                  # the reference prints these lines to stderr (model/model.py:13)
     rng = np.random.default_rng(3)
     recs = PT.new_games(64, (1, 0, 0), np.arange(5, 69, dtype=np.uint32))
     states = []
@@ -111,7 +115,7 @@ def test_train_data_loop_lowers_the_loss_and_hot_swaps(gpu_lib, tmp_path, monkey
     before = m.compute_loss([d[-76:] for d in [data[0], data[1], data[2], data[3] / data[3].mean()]], weighted=True)["loss"]
     np.random.seed(0)
     m.train_data([d.copy() for d in data], batch_size=64, iters_per_val=25, max_iters=200)
-    err = capfd.readouterr().err
+    err = log.getvalue()
     train_re = r'Iteration:\s*(?P<iter>\d*)\s*training loss:\s*(?P<t_loss>\d*\.\d*)\s*validation loss:\s*(?P<v_loss>\d*\.\d*)±\s*(?P<v_loss_err>\d*\.\d*|nan)\s*gradient norm:\s*(?P<g_norm>\d*\.\d*)'
     assert re.search(r'Training data size:\s*(\d*)\s*Validation data size:\s*(\d*)', err) and len(re.findall(train_re, err)) >= 4
     after = m.compute_loss([d[-76:] for d in [data[0], data[1], data[2], data[3] / data[3].mean()]], weighted=True)["loss"]

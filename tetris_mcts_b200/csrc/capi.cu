@@ -195,6 +195,7 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     rc |= dalloc(e, &A.n_nfree, G); rc |= dalloc(e, &A.n_ofree, G);
     rc |= dalloc(e, &A.root, G); rc |= dalloc(e, &A.episode, G); rc |= dalloc(e, &A.status, G); rc |= dalloc(e, &A.srng, G);
     rc |= dalloc(e, &A.trace, G * A.trace_max); rc |= dalloc(e, &A.trace_len, G); rc |= dalloc(e, &A.leaf_kind, G);
+    rc |= dalloc(e, &A.trace_meta, G * A.trace_max);
     rc |= dalloc(e, &A.nmark, GM); rc |= dalloc(e, &A.omark, GM); rc |= dalloc(e, &A.gc_queue, GM * 2);
     rc |= dalloc(e, &A.cur, G * REC_WORDS);
     rc |= dalloc(e, &A.req, G * 8); rc |= dalloc(e, &A.n_req, 2);
@@ -450,7 +451,7 @@ extern "C" int b200_set_gc_headroom(b200_engine *e, int min_free) {
     return B200_OK;
 }
 
-extern "C" int b200_update_root(b200_engine *e, int auto_reset) {
+static int update_root_impl(b200_engine *e, int auto_reset, bool headroom_collection) {
     if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
     CK(cudaSetDevice(e->cfg.device));
     {
@@ -460,7 +461,7 @@ extern "C" int b200_update_root(b200_engine *e, int auto_reset) {
         k_gc<<<gc_blocks(e), GC_THREADS, 0, e->stream>>>(e->A);                 // games whose free list ran dry (usually none)
         k_update_root<<<blocks_groups(e->A.G), TPB, 0, e->stream>>>(e->A, auto_reset, e->d_game_stats, 1);
     }
-    if (e->gc_headroom > 0) {
+    if (headroom_collection && e->gc_headroom > 0) {
         int rc = b200_remove_nodes(e, e->gc_headroom);
         if (rc) return rc;
     }
@@ -468,11 +469,13 @@ extern "C" int b200_update_root(b200_engine *e, int auto_reset) {
     return B200_OK;
 }
 
+extern "C" int b200_update_root(b200_engine *e, int auto_reset) { return update_root_impl(e, auto_reset, true); }
+
 extern "C" int b200_set_games(b200_engine *e, const uint32_t *recs) {
     if (!e || !recs) return fail(B200_ERR_BAD_ARG, "null argument");
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaMemcpyAsync(e->A.cur, recs, (size_t)e->A.G * REC_WORDS * 4, cudaMemcpyHostToDevice, e->stream));
-    int rc = b200_update_root(e, 0);
+    int rc = update_root_impl(e, 0, false);   // handing the games over is not a move: the driver's between-moves collection (b200_set_gc_headroom) is not due here
     if (rc) return rc;
     return check_status(e);
 }
@@ -553,6 +556,7 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
     const Arena &A = e->A;
     const bool need_net = A.mode != MODE_VANILLA && e->cfg.eval_kind != B200_EVAL_SYNTHETIC;
     if (need_net && !(A.mode == MODE_DIST ? e->have_dist_weights : e->have_weights)) return fail(B200_ERR_NO_WEIGHTS, "b200_load_weights was not called");
+    CK(cudaMemsetAsync(A.counters + 12, 0, sizeof(unsigned long long), e->stream));   // counter 12: the longest trace of this call
     for (int s = 0; s < sims; ++s) {
         if (!e->timing && e->step_exec) {
             CK(cudaGraphLaunch(e->step_exec, e->stream));

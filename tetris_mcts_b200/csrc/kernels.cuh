@@ -244,10 +244,10 @@ __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &g
 __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     __shared__ float s_z[ZS_N];
     __shared__ __align__(16) uint32_t s_stage[GROUPS_PER_BLOCK * STAGE_GROUP_WORDS];
-    __shared__ unsigned s_cnt[4];          // sims, trace levels, expansions, new nodes of this CTA
+    __shared__ unsigned s_cnt[5];          // sims, trace levels, expansions, new nodes, longest trace of this CTA
     __shared__ int s_wreq[TPB / 32 + 1];   // requests per warp, then the CTA's base in the request list
     for (int i = threadIdx.x; i < ZS_N; i += TPB) s_z[i] = A.ztable[i];
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
     Grp gp;
 #if B200_GAMES_PER_WARP < 4
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     const unsigned askmask = __ballot_sync(0xffffffffu, out.ask);
     if ((threadIdx.x & 31) == 0) s_wreq[threadIdx.x >> 5] = __popc(askmask);
     if (gp.lane == 0 && out.sims) {
-        atomicAdd(&s_cnt[0], 1u); atomicAdd(&s_cnt[1], (unsigned)out.D);
+        atomicAdd(&s_cnt[0], 1u); atomicAdd(&s_cnt[1], (unsigned)out.D); atomicMax(&s_cnt[4], (unsigned)out.D);
         if (out.expanded) atomicAdd(&s_cnt[2], 1u);
         if (out.new_nodes) atomicAdd(&s_cnt[3], (unsigned)out.new_nodes);
     }
@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
         if (s_cnt[0]) { atomicAdd(&A.counters[0], (unsigned long long)s_cnt[0]); atomicAdd(&A.counters[4], (unsigned long long)s_cnt[1]); }
         if (s_cnt[2]) atomicAdd(&A.counters[1], (unsigned long long)s_cnt[2]);
         if (s_cnt[3]) atomicAdd(&A.counters[6], (unsigned long long)s_cnt[3]);
+        if (s_cnt[4] > (unsigned)A.counters[12]) atomicMax(&A.counters[12], (unsigned long long)s_cnt[4]);   // longest trace since b200_run_sims began
     }
     __syncthreads();
     if (out.ask) {
@@ -586,11 +587,11 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
     // ---- early loads: trace entries of the first window, then their node fields + the leaf's child row + evaluator outputs
     const int n0 = D < NL ? D : NL;
     int tidx = 0;
-    if (lane < n0) tidx = acc.get_trace(D - 1 - lane);
-    const int leaf = __shfl_sync(mask, tidx, 0, NL);
+    if (lane == 0) tidx = acc.get_trace(D - 1);
     const bool lp_children = A.mode == MODE_LP && kind == LEAF_EXPANDED;
     int wo = -1 - lane; float wsc = 0.f;                      // this lane's level of the current window: observation, score
-    if (lane < n0) acc.meta(tidx, D - 1 - lane, wo, wsc);
+    if (lane < n0) acc.get_trace_meta(D - 1 - lane, wo, wsc); // recorded by the walk: one coalesced read instead of a gather per level
+    const int leaf = __shfl_sync(mask, tidx, 0, NL);
     int c = 0, o = 0; float s = 0.f;
     float2 ev = make_float2(0.f, 0.f);
     if (lp_children && lane < 8) { acc.children(leaf, lane, c, o, s); ev = A.eval_out[(size_t)g * 8 + lane]; }
@@ -651,13 +652,13 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
         {   // the next window's node fields, in flight while this window is folded
             const int ntop = top - NL;
             wo = -1 - lane; wsc = 0.f;
-            if (ntop >= 0 && lane <= ntop) acc.meta(acc.get_trace(ntop - lane), ntop - lane, wo, wsc);
+            if (ntop >= 0 && lane <= ntop) acc.get_trace_meta(ntop - lane, wo, wsc);
         }
         if (any_dup) {                                  // shared observation inside the window: scalar walk for this window
             if (lane == 0) {
                 for (int i = top; i > top - n; --i) {
                     int oo; float ss;
-                    acc.meta(acc.get_trace(i), oo, ss);
+                    acc.get_trace_meta(i, oo, ss);
                     int4 s2 = acc.stat(oo);
                     welford_level(s2, v, var, ss, A.gamma);
                     acc.set_stat(oo, s2);

@@ -55,6 +55,8 @@ struct Arena {
     int32_t *nfree, *ofree; int32_t *n_nfree, *n_ofree;
     int32_t *root, *episode, *status; uint32_t *srng;
     int32_t *trace, *trace_len, *leaf_kind;
+    int2 *trace_meta;              // [G][trace_max] {own observation, own score bits} of every node on the trace, written by the walk (it has
+                                   // both in lane 7 of the level it just loaded) so that the backup needs no second gather per level
     uint8_t *nmark, *omark; int32_t *gc_queue;
     uint32_t *cur;                 // [G][20] the live game of each tree (the object play.py owns)
     const float *ztable;
@@ -234,10 +236,10 @@ constexpr int ZS_N = 2048;   // z(n) entries staged in shared memory by k_select
 
 struct ArenaAcc {
     const Arena &A; int g; const float *zs;
-    const int32_t *rowg; int4 *statg; int32_t *traceg;      // this game's slices of the arena (address arithmetic hoisted out of the loops)
+    const int32_t *rowg; int4 *statg; int32_t *traceg; int2 *tmetag;   // this game's slices of the arena (address arithmetic hoisted out of the loops)
     __device__ __forceinline__ ArenaAcc(const Arena &A_, int g_, const float *zs_ = nullptr)
         : A(A_), g(g_), zs(zs_), rowg(A_.row + (size_t)g_ * A_.M * ROW_WORDS), statg(A_.stat + (size_t)g_ * A_.M),
-          traceg(A_.trace + (size_t)g_ * A_.trace_max) {}
+          traceg(A_.trace + (size_t)g_ * A_.trace_max), tmetag(A_.trace_meta + (size_t)g_ * A_.trace_max) {}
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
         c = row[lane]; o = row[8 + lane]; s = __int_as_float(row[16 + lane]);   // lane 7: own episode / obs / score
@@ -304,6 +306,8 @@ struct ArenaAcc {
     }
     __device__ __forceinline__ void put_trace(int d, int idx) const { traceg[d] = idx; }
     __device__ __forceinline__ int get_trace(int d) const { return traceg[d]; }
+    __device__ __forceinline__ void put_trace_meta(int d, int o, float s) const { tmetag[d] = make_int2(o, __float_as_int(s)); }
+    __device__ __forceinline__ void get_trace_meta(int d, int &o, float &s) const { const int2 m = tmetag[d]; o = m.x; s = __int_as_float(m.y); }
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return (zs && n >= 0 && n < ZS_N) ? zs[n] : ztab(A, n); }
     __device__ __forceinline__ unsigned long long *level_prof() const { return (A.prof && (g & 63) == 0) ? A.prof + 8 : nullptr; }
@@ -329,6 +333,7 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
     __device__ __forceinline__ void set_stat(int o, int4 st) const { visit[o] = st.x; value[o] = __int_as_float(st.y); variance[o] = __int_as_float(st.z); }
     __device__ __forceinline__ void put_trace(int d, int idx) const { trace[d] = idx; }
     __device__ __forceinline__ int get_trace(int d) const { return trace[d]; }
+    __device__ __forceinline__ void put_trace_meta(int, int, float) const {}
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = *rng; uint32_t r = rng_next(sr); *rng = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return ztab(*A, n); }
     __device__ __forceinline__ unsigned long long *level_prof() const { return nullptr; }
@@ -364,6 +369,7 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
         int o; float s_idx;
         Uniq u;
         acc.level(gp, walking, idx, D - 1, o, s_idx, u);
+        if (walking && gp.lane == 7) acc.put_trace_meta(D - 1, o, s_idx);   // lane 7 holds the node's own observation and score
         LEVEL_PROF(0);
         if (u.first_mask == 0) walking = false;                         // core.h:200 no children: leaf (group-uniform)
         int4 st = make_int4(0, 0, 0, 0);

@@ -334,14 +334,14 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
             const bool do_prof = blockIdx.x == 0;
             long long pacc[16] = {0}, ptick = clock64();
             for (int i = 0; i < n_local + 1; ++i) {
-                if (i >= 1) {                                    // conv2 (model_vv.py:34): act1 on the 18x8 grid
+                // conv1(i) goes FIRST: its operand comes from the front-end warp (boards ahead), its accumulator columns were last read by
+                // E3(i-4), and E1(i-1) — the last phase of the workers' previous iteration, a1(i-1) — implies that E3(i-4) is done.  With
+                // conv1 queued behind the 18 MMAs of conv2 (round 1: the workers built the operand, so it could not be ready earlier) the
+                // workers stood at E1(i) for ~1 k clk per board waiting for it.
+                if (i >= 1) {
                     const int j = i - 1, slot = j % NS;
                     mbar_wait(&bar_a1[slot], (uint32_t)(j / NS) & 1u);
                     PROF_T(10);
-                    tc_fence_after();
-                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
-                    umma_commit(&bar_c2[slot]);
-                    PROF_T(11);
                 }
                 if (i < n_local) {                               // conv1 (model_vv.py:32): im2col [256 x 16] x W1 [16 x 64], two M tiles
                     const int slot = i % NS;
@@ -353,6 +353,13 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     umma_f16(tmem_base + slot * 128 + 64, a0 + 128, b0, umma_idesc_f16(128, 64), 0u);
                     umma_commit(&bar_c1[slot]);
                     PROF_T(9);
+                }
+                if (i >= 1) {                                    // conv2 (model_vv.py:34): act1 on the 18x8 grid
+                    const int j = i - 1, slot = j % NS;
+                    tc_fence_after();
+                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
+                    umma_commit(&bar_c2[slot]);
+                    PROF_T(11);
                 }
             }
             if (prof && do_prof) for (int i = 8; i < 12; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);

@@ -138,7 +138,7 @@ class BatchedEngine:
         return st
 
     COUNTER_NAMES = ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "rollout_steps", "new_nodes", "tree_resets",
-                     "games_finished", "score_sum", "lines_sum")
+                     "games_finished", "score_sum", "lines_sum", "_11", "max_trace_len")
 
     def counters(self):
         c = np.zeros(16, np.uint64)
