@@ -6,6 +6,9 @@
 
 namespace b200 {
 
+#ifndef B200_PV_PREFETCH
+#define B200_PV_PREFETCH 2         // 0 off; 1 one request per row / statistics line; 2 every sector of the row the walk reads + the neighbouring
+#endif                             // statistics lines; 3 denser statistics coverage
 #ifndef B200_GAMES_PER_WARP
 #define B200_GAMES_PER_WARP 4      // development aid (A/B): k_select_expand with 1 or 2 games per warp (the other 8-lane groups idle) to measure
                                    // what independent walks sharing a warp cost each other (every load waits for the slowest group's miss)
@@ -192,6 +195,38 @@ __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &g
     ArenaAcc acc(A, valid ? g : 0, s_z);
     int D = 0;
 #define TREE_PROF(i) do { if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[i], (unsigned long long)(_n - ptick)); ptick = _n; } } while (0)
+#if B200_PV_PREFETCH
+    // Principal-variation prefetch (performance hint only): a game's walk mostly retraces its previous simulation's path — deep, narrow
+    // trees grow at the end of one line — and every level of the walk is two DEPENDENT misses (row line, then the children's statistics;
+    // ~3.5 k clk of the ~4.5 k clk per level).  The previous trace is known (A.trace, A.trace_meta), so its row lines and the statistics
+    // lines around each chosen child's observation are requested from L2 all at once, before the walk: where the new walk follows the
+    // old path it finds them in L2 instead of paying DRAM + TLB latency level after level.  Siblings' observation ids are consecutive
+    // (allocated by consecutive pops of the free list), so the line of the chosen child's statistics and its neighbours cover them.
+    if (active && A.mode != MODE_DIST) {
+        const int pd = A.trace_len[g];
+        const int32_t *tr = A.trace + (size_t)g * A.trace_max;
+        const int2 *tm = A.trace_meta + (size_t)g * A.trace_max;
+        const char *stat_lo = reinterpret_cast<const char *>(acc.statg), *stat_hi = stat_lo + (size_t)A.M * sizeof(int4) - 1;
+        for (int d = gp.lane; d < pd; d += 8) {
+            const int idx = tr[d], o = tm[d].x;
+            const char *r = reinterpret_cast<const char *>(acc.rowg + (size_t)idx * ROW_WORDS);
+            prefetch_l2(r + 32);
+#if B200_PV_PREFETCH >= 2
+            prefetch_l2(r + 64); prefetch_l2(r + 96);
+#endif
+            const char *st = reinterpret_cast<const char *>(acc.statg + o);
+            prefetch_l2(st);
+#if B200_PV_PREFETCH >= 2
+            const char *a = st - 96, *b = st + 96;
+            prefetch_l2(a < stat_lo ? stat_lo : a); prefetch_l2(b > stat_hi ? stat_hi : b);
+#endif
+#if B200_PV_PREFETCH >= 3
+            const char *c = st - 48, *e2 = st + 48;
+            prefetch_l2(c < stat_lo ? stat_lo : c); prefetch_l2(e2 > stat_hi ? stat_hi : e2);
+#endif
+        }
+    }
+#endif
     int leaf = 0;
     if (A.mode == MODE_DIST) {               // grid-uniform branch; the distributional walk keeps its per-group form
         if (active) leaf = dist_select_group(A, gp, g, A.root[g], D, status);

@@ -218,6 +218,9 @@ __device__ __forceinline__ void stg_hint(int4 *p, int4 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
+// non-blocking L2 prefetch: no destination register, so nothing ever waits for it (unlike the touch loads below)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 __device__ __forceinline__ uint32_t touch32(const void *p) {
     uint32_t v;
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
