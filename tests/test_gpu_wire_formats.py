@@ -55,3 +55,22 @@ def test_play_batched_emits_the_reference_wire_formats(gpu_lib, tmp_path):
     line_stats = np.memmap(str(tmp_path / "tmp" / "line_stats"), mode='r', dtype=np.int32, shape=(4,))
     assert set(np.unique(board)) <= {-1, 0, 1} and (board == -1).sum() == 4
     assert combo[0] >= 0 and score[0] >= 0 and lines_mm[0] == line_stats[0] + 2 * line_stats[1] + 3 * line_stats[2] + 4 * line_stats[3]
+
+
+def test_play_batched_saves_state_rows(gpu_lib, tmp_path):
+    """--save: one util/Data.py `State` row per game and move (play.py:131-132), written by tetris_mcts_b200.data.DataSaver."""
+    from tetris_mcts_b200 import data as D
+    from tetris_mcts_b200 import play_batched as PB
+    out = io.StringIO()
+    PB.main(["--agent_type", "Vanilla", "--mcts_sims", "8", "--ngames", "1000", "--n_parallel", "16", "--max_nodes", "1024", "--endless", "--max_moves", "6",
+             "--save", "--save_dir", str(tmp_path) + "/", "--save_file", "data", "--cycle", "2"], out=out)
+    if D.have_pytables():
+        import tables
+        with tables.open_file(str(tmp_path / "data2")) as f:
+            rows = f.root.State.read()
+    else:
+        rows = np.concatenate([np.load(str(p)) for p in sorted(tmp_path.glob("data2.*.npy"))])
+    assert len(rows) == 16 * 6 and rows.dtype == D.STATE_DTYPE
+    assert set(np.unique(rows["board"])) <= {-1, 0, 1} and ((rows["board"] == -1).sum(axis=(1, 2)) == 4).all()
+    assert np.allclose(rows["policy"].sum(axis=1), 1.0, atol=1e-5) and (rows["cycle"] == 2).all()
+    assert ((rows["action"] >= 0) & (rows["action"] < 7)).all() and (rows["child_stats"][:, 0].sum(axis=1) > 0).all()

@@ -7,8 +7,9 @@
 namespace b200 {
 
 #ifndef B200_PV_PREFETCH
-#define B200_PV_PREFETCH 2         // 0 off; 1 one request per row / statistics line; 2 every sector of the row the walk reads + the neighbouring
-#endif                             // statistics lines; 3 denser statistics coverage
+#define B200_PV_PREFETCH 0         // 0 off; 1 one request per row / statistics line; 2 every sector of the row the walk reads + the neighbouring
+#endif                             // statistics lines; 3 denser statistics coverage.  Measured on B200 (profiles/exp_variants_r2e.txt): the walk's
+                                   // per-level time does not move (4.81 -> 4.65 k clk) and k_select_expand gets 10-18 % SLOWER: off
 #ifndef B200_GAMES_PER_WARP
 #define B200_GAMES_PER_WARP 4      // development aid (A/B): k_select_expand with 1 or 2 games per warp (the other 8-lane groups idle) to measure
                                    // what independent walks sharing a warp cost each other (every load waits for the slowest group's miss)

@@ -84,17 +84,27 @@ def run(args, out=sys.stdout):
         replay_buf = torch.empty((cap, 212), dtype=torch.uint8, device=torch.device("cuda", args.device))
         torch.cuda.synchronize()
     status = RealtimeStatus(args.status_dir) if args.realtime_status else None
+    saver = None
+    if args.save:                                                                          # play.py:93-94, 131-132
+        from .data import DataSaver, rows_from_move
+        saver = DataSaver(args.save_dir, args.save_file, args.cycle)
+        episode_of = np.zeros(args.n_parallel, np.int32)                                    # play.py passes ngames: the episode a row belongs to
     tracker = ScoreTracker()
     ngames, moves, stored = 0, 0, 0
     try:
         while True:
             if status:
                 status.update(eng.get_games()[args.watch])
-            eng.play_move(args.mcts_sims, auto_reset=True, want_stats=False)               # agent.play(); game.play(action); agent.update_root(game); reset
+            before = eng.get_games() if saver else None
+            actions, stats = eng.play_move(args.mcts_sims, auto_reset=True, want_stats=saver is not None)   # agent.play(); game.play(action); agent.update_root(game); reset
+            if saver:
+                saver.add_rows(rows_from_move(before, actions, stats, args.cycle, episode_of))
             moves += 1
             done = False
             for g, score, lines, _ep in eng.finished_games():
                 ngames += 1
+                if saver:
+                    episode_of[g] = ngames
                 if args.endless:
                     print(EPISODE_FMT.format(ngames, int(score), int(lines)), flush=True, file=out)
                 else:
@@ -112,6 +122,8 @@ def run(args, out=sys.stdout):
     finally:
         print(flush=True, file=out)                                                         # play.py:179
         eng.close()                                                                         # play.py:181
+        if saver:
+            saver.close()                                                                   # play.py:183-184
     return ngames, moves, tracker
 
 
@@ -125,6 +137,10 @@ def main(argv=None, out=sys.stdout):
     p.add_argument('--ngames', default=50, type=int)
     p.add_argument('--online', default=False, action='store_true')
     p.add_argument('--realtime_status', default=False, action='store_true')
+    p.add_argument('--save', default=False, action='store_true')
+    p.add_argument('--save_dir', default='./data/', type=str)
+    p.add_argument('--save_file', default='data', type=str)
+    p.add_argument('--cycle', default=0, type=int)
     p.add_argument('--tetris_randomizer', default=0, type=int)
     p.add_argument('--tetris_scoring', default=0, type=int)
     p.add_argument('--n_parallel', default=4096, type=int, help='concurrent games on the device')
