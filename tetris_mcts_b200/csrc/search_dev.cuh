@@ -193,6 +193,9 @@ __device__ __forceinline__ uint32_t link_word(const Uniq &u) {
 #ifndef B200_L2_HOT_LEVELS
 #define B200_L2_HOT_LEVELS 16
 #endif
+#ifndef B200_ROW_HINT
+#define B200_ROW_HINT 1        // 0: the walk loads its row words without an L2 policy (the statistics keep theirs)
+#endif
 __device__ __forceinline__ uint64_t l2_policy(bool keep) {
     uint64_t last, normal;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(last));
@@ -259,7 +262,7 @@ struct ArenaAcc {
         float s = 0.f; uint32_t lw = 0u;
         o = 0;
         if (on) {
-#if B200_L2_HOT_LEVELS > 0
+#if B200_L2_HOT_LEVELS > 0 && B200_ROW_HINT
             const uint64_t pol = l2_policy(depth < B200_L2_HOT_LEVELS);
             o = ldg_hint(row + 8, pol);
             s = __int_as_float(ldg_hint(row + 16, pol));

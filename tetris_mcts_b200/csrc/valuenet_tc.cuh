@@ -177,7 +177,10 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2
 // All three layers live on an 8-wide pixel grid (p = y*8 + x), so p+dx never leaves the 32-lane warp that owns the row.
 // 18 MMAs (3 dy x 2 channel halves x 3 split products, N = 96) replace the 36 narrow ones of the tap-by-tap form, and
 // conv1 (K = 9 taps, exact {-1,0,1} inputs) runs on the tensor core too from an im2col operand the workers build.
-constexpr int TCC_WORKERS = 512;            // warps 0-15: decode / im2col and the three epilogues
+#ifndef B200_CONV_SETS
+#define B200_CONV_SETS 2                    // 2: two independent worker sets (8 warps x 16 channels) on alternating boards; 1: the round-1 form (16 warps x 8 channels, one phase at a time)
+#endif
+constexpr int TCC_WORKERS = 512;            // warps 0-15: the three epilogues
 constexpr int TCC_ISSUER = TCC_WORKERS / 32; // warp 16: MMA issuer of conv1 + conv2 (one elected lane)
 constexpr int TCC_ISSUER3 = TCC_ISSUER + 1; // warp 17: MMA issuer of conv3.  A 56-clk MMA costs its issuing thread ~8 dependent instructions
                                             // (uniform-register moves + the elect loop) and that thread shares its scheduler with four busy
@@ -303,7 +306,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     if (t == 0) {
         for (int i = 0; i < 3 * NS; ++i) mbar_init(&bars[i], 1);
         for (int i = 3 * NS; i < 4 * NS; ++i) mbar_init(&bars[i], 1);                      // a0: the front-end warp alone builds the conv1 operand
-        for (int i = 4 * NS; i < 6 * NS; ++i) mbar_init(&bars[i], TCC_WORKERS / 32);      // a1, a2: one arrival per worker warp
+        for (int i = 4 * NS; i < 6 * NS; ++i) mbar_init(&bars[i], TCC_WORKERS / 32 / B200_CONV_SETS);   // a1, a2: one arrival per worker warp (of the board's set)
         for (int i = 6 * NS; i < 7 * NS; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
@@ -326,6 +329,50 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     int n_local = 0;
     for (int run = blockIdx.x; run < n_runs; run += gridDim.x) n_local += min(TCC_RUN, n_req - run * TCC_RUN);
     auto board_of = [&](int i) -> int { return ((i / TCC_RUN) * (int)gridDim.x + (int)blockIdx.x) * TCC_RUN + (i % TCC_RUN); };
+#if B200_CONV_SETS == 2
+    if (warp == TCC_ISSUER || warp == TCC_ISSUER3) {
+        // ===================================================== MMA issuers, one per worker set (set s owns the boards i = s, s+2, s+4, ... of this CTA).
+        // Order per board of the set: conv1(i) and conv3(i-2) as soon as the set's previous board has left its conv2 epilogue (a2(i-2): that
+        // epilogue is the last phase of the set's iteration, so E3(i-4) — the last reader of slot i's accumulator columns — is done as
+        // well), conv1 FIRST so that the set's next phase, E1(i), never waits behind 18 MMAs; conv2(i) when E1(i) has written its operand.
+        if (lane == 0) {
+            const int set = warp - TCC_ISSUER;
+            const uint32_t s_w1 = smem_u32(smem + TCC_OFF_W1), s_w2 = smem_u32(smem + TCC_OFF_W2), s_w3 = smem_u32(smem + TCC_OFF_W3);
+            const uint32_t s_act = smem_u32(smem + TCC_OFF_A1), s_im = smem_u32(smem + TCC_OFF_IM);
+            const bool do_prof = blockIdx.x == 0 && set == 0;
+            long long pacc[16] = {0}, ptick = clock64();
+            for (int i = set; i - 2 < n_local; i += 2) {
+                const int slot = i % NS, pslot = (i - 2) & (NS - 1);
+                const bool has = i < n_local, hasp = i >= 2;             // (i - 2 < n_local by the loop condition)
+                if (hasp) { mbar_wait(&bar_a2[pslot], (uint32_t)((i - 2) / NS) & 1u); PROF_T(12); }
+                if (has) {                                       // conv1 (model_vv.py:32): im2col [256 x 16] x W1 [16 x 64], two M tiles
+                    mbar_wait(&bar_a0[slot], (uint32_t)(i / NS) & 1u);
+                    PROF_T(8);
+                    tc_fence_after();
+                    const uint64_t a0 = umma_desc(s_im + slot * TCC_IMSLOT, TCC_IMROWS * 16, 128), b0 = umma_desc(s_w1, 64 * 16, 128);
+                    umma_f16(tmem_base + slot * 128, a0, b0, umma_idesc_f16(128, 64), 0u);
+                    umma_f16(tmem_base + slot * 128 + 64, a0 + 128, b0, umma_idesc_f16(128, 64), 0u);
+                    umma_commit(&bar_c1[slot]);
+                    PROF_T(9);
+                }
+                if (hasp) {                                      // conv3 (model_vv.py:36): act2 on the 16x8 grid
+                    tc_fence_after();
+                    issue_conv_layer(tmem_base + pslot * 128, s_act + pslot * TCC_ASLOT, s_w3);
+                    umma_commit(&bar_c3[pslot]);
+                    PROF_T(13);
+                }
+                if (has) {                                       // conv2 (model_vv.py:34): act1 on the 18x8 grid
+                    mbar_wait(&bar_a1[slot], (uint32_t)(i / NS) & 1u);
+                    PROF_T(10);
+                    tc_fence_after();
+                    issue_conv_layer(tmem_base + slot * 128, s_act + slot * TCC_ASLOT, s_w2);
+                    umma_commit(&bar_c2[slot]);
+                    PROF_T(11);
+                }
+            }
+            if (prof && do_prof) for (int i = 8; i < 14; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+        }
+#else
     if (warp == TCC_ISSUER) {
         // ===================================================== MMA issuer
         if (lane == 0) {
@@ -381,6 +428,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
             }
             if (prof && do_prof) for (int i = 12; i < 14; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
         }
+#endif
     } else if (warp == TCC_LOADER) {
         // ===================================================== front end (one warp): observation key -> conv1 operand.
         // A key is a random 48-byte read from an arena of tens of GB (~2.4 k clk); TCC_KEYS_AHEAD of them are kept in flight.  The same
@@ -440,6 +488,117 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
             }
         }
     } else {
+#if B200_CONV_SETS == 2
+        // ===================================================== workers: two sets of 8 warps, each with its own boards (set s: i = s, s+2, ...).
+        // The three epilogues of a board are latency chains (barrier, TMEM load, shuffles, conversions, shared-memory fence, arrive); with all 16
+        // warps in one phase every scheduler's four warps stalled together.  Two independent sets in different phases fill each other's gaps;
+        // a thread now owns 16 output channels of its pixel row (two 8-channel chunks, one barrier wait / fence / arrive for both).
+        // Per set, iteration j (board i = 2j + s):  E1(i) | E3(i-2) | E2(i)   — conv2(i) runs under E3(i-2), conv3(i-2) under E1(i).
+        const int set = warp >> 3, w8 = warp & 7;
+        const bool do_prof = blockIdx.x == 0 && t == 0;
+        long long pacc[16] = {0}, ptick = clock64();
+        const int q = w8 & 3, ch = w8 >> 2, m = q * 32 + lane;          // TMEM lane quadrant, 16-channel half, pixel row
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int y = m >> 3, x = m & 7;
+        for (int i = set; i - 2 < n_local; i += 2) {
+            const bool has = i < n_local, hasp = i >= 2;
+            // ---- E1(i): conv1 epilogue: bias + ReLU + split -> act1 (18x8 grid)
+            if (has) {
+                const int slot = i % NS;
+                mbar_wait_warp(&bar_c1[slot], (uint32_t)(i / NS) & 1u);
+                PROF_T(1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cq = 2 * ch + c;
+                    uint8_t *abase = smem + TCC_OFF_A1 + slot * TCC_ASLOT + cq * TCC_R * 16;
+                    const uint32_t t_lane = t_row + slot * 128 + cq * 8;
+                    {
+                        float w1[8], w2[8], o[8];
+                        tmem_ld8x2(t_lane, w1, w2);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + sB[cq * 8 + e], 0.f) * TC_SCALE_A;
+                        uint4 c1, c2;
+                        split8(o, c1, c2);
+                        *reinterpret_cast<uint4 *>(abase + m * 16) = c1;
+                        *reinterpret_cast<uint4 *>(abase + 4 * TCC_R * 16 + m * 16) = c2;
+                    }
+                    if (q == 0) {                                // rows 128..143 sit in lanes 0..15 of the second M tile
+                        float w1[8], w2[8], o[8];
+                        tmem_ld8x2(t_lane + 64, w1, w2);
+                        if (lane < 16) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + sB[cq * 8 + e], 0.f) * TC_SCALE_A;
+                            uint4 c1, c2;
+                            split8(o, c1, c2);
+                            *reinterpret_cast<uint4 *>(abase + (128 + lane) * 16) = c1;
+                            *reinterpret_cast<uint4 *>(abase + 4 * TCC_R * 16 + (128 + lane) * 16) = c2;
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a1[slot]);
+                PROF_T(2);
+            }
+            // ---- E3(i-2): conv3 epilogue: dx sum + bias + ReLU + split -> act3 in HBM (FC tile layout)
+            if (hasp) {
+                const int j = i - 2, slot = j % NS, ridx = board_of(j);
+                mbar_wait_warp(&bar_c3[slot], (uint32_t)(j / NS) & 1u);
+                PROF_T(5);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cq = 2 * ch + c;
+                    float v[8];
+                    tmem_ld_conv_sum(t_row + slot * 128 + cq * 8, v);
+                    if (y < 14 && x < 4) {
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[64 + cq * 8 + e], 0.f) * TC_SCALE_A;
+                        uint4 c1, c2;
+                        split8(o, c1, c2);
+                        const int kc = (y * 4 + x) * 4 + cq;
+                        *reinterpret_cast<uint4 *>(act3 + act3_off(0, n_tiles, ridx, kc)) = c1;
+                        *reinterpret_cast<uint4 *>(act3 + act3_off(1, n_tiles, ridx, kc)) = c2;
+                    }
+                }
+                tc_fence_before();
+                PROF_T(6);
+            }
+            // ---- E2(i): conv2 epilogue: dx sum + bias + ReLU + split -> act2 (16x8 grid), in place of the slot's act1
+            if (has) {
+                const int slot = i % NS;
+                mbar_wait_warp(&bar_c2[slot], (uint32_t)(i / NS) & 1u);
+                PROF_T(3);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cq = 2 * ch + c;
+                    float v[8];
+                    tmem_ld_conv_sum(t_row + slot * 128 + cq * 8, v);
+                    if ((m & 7) < 6) {
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + sB[32 + cq * 8 + e], 0.f) * TC_SCALE_A;
+                        uint4 c1, c2;
+                        split8(o, c1, c2);
+                        uint8_t *base = smem + TCC_OFF_A1 + slot * TCC_ASLOT + (cq * TCC_R + m) * 16;
+                        *reinterpret_cast<uint4 *>(base) = c1;
+                        *reinterpret_cast<uint4 *>(base + 4 * TCC_R * 16) = c2;
+                    }
+                }
+                tc_fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a2[slot]);
+                PROF_T(4);
+            }
+        }
+        if (prof && do_prof) for (int i = 0; i < 8; ++i) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
+    }
+#else
         // ===================================================== workers (512 threads)
         const bool do_prof = blockIdx.x == 0 && t == 0;
         long long pacc[16] = {0}, ptick = clock64();
@@ -539,6 +698,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
         }
         if (prof && do_prof) for (int i = 0; i < 16; ++i) if (i < 8 || i > 13) atomicAdd(&prof[i], (unsigned long long)pacc[i]);
     }
+#endif
 #undef PROF_T
     tc_fence_before();
     __syncthreads();
