@@ -178,7 +178,9 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &c1, uint4 &c2
 // 18 MMAs (3 dy x 2 channel halves x 3 split products, N = 96) replace the 36 narrow ones of the tap-by-tap form, and
 // conv1 (K = 9 taps, exact {-1,0,1} inputs) runs on the tensor core too from an im2col operand the workers build.
 #ifndef B200_CONV_SETS
-#define B200_CONV_SETS 2                    // 2: two independent worker sets (8 warps x 16 channels) on alternating boards; 1: the round-1 form (16 warps x 8 channels, one phase at a time)
+#define B200_CONV_SETS 1                    // 1: 16 worker warps x 8 channels, one phase at a time; 2: two independent worker sets (8 warps x 16 channels) on alternating
+                                            // boards, one MMA issuer each.  Measured on B200 (profiles/exp_variants_r2f.txt): 2 751 clk per board with one set, 3 204 with
+                                            // two (a thread's two 8-channel chunks run back to back and every phase gets 2.4 x longer, more than the overlap wins): 1
 #endif
 constexpr int TCC_WORKERS = 512;            // warps 0-15: the three epilogues
 constexpr int TCC_ISSUER = TCC_WORKERS / 32; // warp 16: MMA issuer of conv1 + conv2 (one elected lane)
