@@ -167,6 +167,17 @@ int b200_collect_samples_dev(b200_engine *e, int min_visits, void *out_dev, int 
 int b200_replay_enable(b200_engine *e, int min_visits, int capacity);
 int b200_replay_drain_dev(b200_engine *e, void *out_dev, int capacity, int32_t *count_out);
 
+/* --- the online agent's accumulation policies and memory trimming (OnlineMCTSAgent::remove_nodes agent.cpp:619-708: policies 0-3;
+ *     weighted_trimming :710-749; random_trimming :751-775; store_nodes' random drop :800-801), on the memory b200_replay_enable created
+ *     (memory_size = capacity, min_visit = min_visits).  b200_replay_policy_step = the decision the reference takes inside remove_nodes() after
+ *     storing: call it after collections (single game: after every step / update_root in which counter 3 moved — then memory contents, trimming
+ *     and the moments of training equal the compiled agent.cpp's; batched: once per move) with current_episode = games finished so far
+ *     (agent.cpp:279-280).  *train_now != 0: train on the first *memory_index rows (b200_replay_peek_dev), then b200_replay_policy_trained. */
+int b200_replay_policy(b200_engine *e, int accumulation_policy, int episodes_per_train, int memory_growth_rate);
+int b200_replay_policy_step(b200_engine *e, int64_t current_episode, int32_t *train_now, int32_t *memory_index);
+int b200_replay_policy_trained(b200_engine *e, int64_t current_episode);
+int b200_replay_peek_dev(b200_engine *e, void *out_dev, int n_rows);
+
 /* --- value-network training step: Model_VV._loss / Model.train / Yogi.step / Model_VV.train_data of the reference
  *     (model/model_vv.py:94-153,227-231, model/model.py:52-119, model/yogi.py:39-90) on the device.  weights = the state_dict vector of
  *     b200_load_weights (PyTorch layouts); a batch is {states int8[n][200], value f32[n], variance f32[n], weight f32[n]} (the four arrays

@@ -9,6 +9,8 @@
   agent_cpp_golden.npz  actions / game records of the reference's own C++ agent twin (agents/cppmodule/agent.cpp compiled unchanged)
   agent_modes_golden.npz  the reference's own agents/ValueSim.py and agents/Vanilla.py (the other two mcts loops); their
                       rand() / randint draw from the oracle's xorshift stream (oracle/rand_shim.c, LD_PRELOAD)
+  agent_online_golden.npz  the replay memory the reference's own OnlineMCTSAgent (agent.cpp, online) hands to its train callback under each of
+                      its four accumulation policies (weighted / random trimming included), one process per policy
   train_golden.npz    optimiser steps of the reference's own Model_VV.train (model/model.py:95-119, GaussianLL model_vv.py:94-101,
                       Yogi model/yogi.py) on torch CPU; the torch-1.x overloads those files call are re-created at run time
 Run:  python tests/golden/gen_golden.py      (needs /root/reference and `make -C oracle`)"""
@@ -278,6 +280,70 @@ def gen_agent_cpp(pt):
 
 
 
+
+ONLINE_CASES = {0: dict(memory_size=400, ept=2, growth=150, sims=12, M=2500, moves=420, seed=31, min_visit=3),
+                1: dict(memory_size=300, ept=3, growth=150, sims=12, M=2500, moves=420, seed=32, min_visit=3),
+                2: dict(memory_size=300, ept=3, growth=150, sims=12, M=2500, moves=420, seed=33, min_visit=3),
+                3: dict(memory_size=400, ept=2, growth=90, sims=12, M=2500, moves=420, seed=34, min_visit=3)}
+
+
+def gen_agent_cpp_online(pt, policy):
+    """One accumulation policy of the reference's own OnlineMCTSAgent (agents/cppmodule/agent.cpp:571-820 compiled unchanged, online=True,
+    benchmark=False): every train(m_state, m_value, m_variance, m_visit, memory_index) call (agent.cpp:698) is recorded — when it happens
+    (move index) and the memory it is handed — together with the actions played.  A fresh process per policy: the reference's random source
+    (std::mt19937 mt(123), agent.cpp:29) and random_trimming's IntSampler (a function-static, agent.cpp:752) are process-global."""
+    agent_mod = O.load_ref_module("agent")
+    cs = ONLINE_CASES[policy]
+
+    def evaluator(obs):                                   # agent.cpp:430-434
+        v, var = synthetic_inference(np.asarray(obs).astype(np.int8))
+        return [v[:, 0].tolist(), var[:, 0].tolist()]
+
+    calls, move_now = [], [0]
+
+    def train(state, value, variance, visit, n):          # agent.cpp:698
+        calls.append((move_now[0], np.array(state[:n, 0], np.int8), np.array(value[:n, 0], np.float32), np.array(variance[:n, 0], np.float32),
+                      np.array(visit[:n, 0], np.float32)))
+
+    game = pt.Tetris((20, 10), 1, 0, 0)
+    game.seed(cs["seed"])
+    ag = agent_mod.OnlineMCTSAgent(sims=cs["sims"], max_nodes=cs["M"], online=True, accumulation_policy=policy, memory_size=cs["memory_size"],
+                                   episodes_per_train=cs["ept"], memory_growth_rate=cs["growth"], min_visit=cs["min_visit"], projection=True,
+                                   gamma=0.999, benchmark=False, evaluator=evaluator, evaluation_type=0, train=train, LP=True)
+    out = {"start": np.array(game.get_record(), np.uint32)}
+    ag.update_root(game)
+    acts = []
+    for mv in range(cs["moves"]):
+        move_now[0] = mv
+        a = ag.play()
+        acts.append(int(a))
+        game.play(a)
+        ag.update_root(game)
+        if game.end:
+            game.reset()
+            ag.update_root(game)
+    out["actions"] = np.array(acts, np.int32)
+    out["n_calls"] = len(calls)
+    out["call_moves"] = np.array([c[0] for c in calls], np.int32)
+    for i, c in enumerate(calls):
+        out["t%d_state" % i], out["t%d_value" % i], out["t%d_variance" % i], out["t%d_visit" % i] = c[1], c[2], c[3], c[4]
+    for k, v in cs.items():
+        out["cfg_" + k] = v
+    np.savez_compressed(os.path.join(HERE, "_online_p%d.npz" % policy), **out)
+    print("agent_online policy %d: %d train calls at moves %s, rows %s" % (policy, len(calls), [c[0] for c in calls][:12], [len(c[2]) for c in calls][:12]))
+
+
+def merge_online():
+    out = {}
+    for p in range(4):
+        f = os.path.join(HERE, "_online_p%d.npz" % p)
+        z = np.load(f)
+        for k in z.files:
+            out["p%d_%s" % (p, k)] = z[k]
+        os.remove(f)
+    np.savez_compressed(os.path.join(HERE, "agent_online_golden.npz"), **out)
+
+
 def legacy_torch_overloads():
     """The reference's training code calls torch-1.x overloads that torch 2.x removed: Tensor.add_(Number alpha, Tensor other) and
     Tensor.add(Number, Tensor) (model/model_vv.py:100, model/yogi.py:71,74), addcmul_(Number, Tensor, Tensor) (yogi.py:78-82),
@@ -443,6 +509,13 @@ if __name__ == "__main__":
         gen_dist()
     elif "--train" in sys.argv:
         gen_train()
+    elif "--agent-online" in sys.argv:
+        gen_agent_cpp_online(pt, int(sys.argv[sys.argv.index("--agent-online") + 1]))
+    elif "--agent-online-all" in sys.argv:
+        import subprocess
+        for pol in range(4):
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-online", str(pol)], check=True, stderr=subprocess.DEVNULL)
+        merge_online()
     elif "--agent-gc" in sys.argv:
         gen_agent_explicit_gc(pt)
     elif "--agent-modes" in sys.argv:
@@ -458,4 +531,5 @@ if __name__ == "__main__":
         gen_dist()
         gen_train()
         import subprocess
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-online-all"], check=True)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-modes"], check=True)

@@ -80,6 +80,10 @@ def lib():
         L.b200_collect_samples_dev.argtypes = [P, C.c_int, P, C.c_int, P]
         L.b200_replay_enable.argtypes = [P, C.c_int, C.c_int]
         L.b200_replay_drain_dev.argtypes = [P, P, C.c_int, P]
+        L.b200_replay_policy.argtypes = [P, C.c_int, C.c_int, C.c_int]
+        L.b200_replay_policy_step.argtypes = [P, C.c_int64, P, P]
+        L.b200_replay_policy_trained.argtypes = [P, C.c_int64]
+        L.b200_replay_peek_dev.argtypes = [P, P, C.c_int]
         L.b200_load_dist_weights.argtypes = [P, P, C.c_int]
         L.b200_distnet_forward.argtypes = [P, P, C.c_int, C.c_int, P]
         L.b200_export_dist.argtypes = [P, C.c_int, P, P]

@@ -14,6 +14,7 @@
 #include "valuenet_simt.cuh"
 #include "dist_dev.cuh"
 #include "distnet_simt.cuh"
+#include "replay_policy.cuh"
 #ifdef B200_WITH_TC
 #include "valuenet_tc.cuh"
 #endif
@@ -62,6 +63,8 @@ struct b200_engine {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // sampling
     uint8_t *d_samples = nullptr; int sample_cap = 0; int32_t *d_sample_count = nullptr;
+    // replay-memory policy (agent.cpp:619-775)
+    ReplayPolicy rp; uint8_t *d_rp_tmp = nullptr, *d_rp_keep = nullptr; float *d_rp_vis = nullptr; int32_t *d_rp_kept = nullptr; int replay_alloc = 0;
     // one simulation step captured as a CUDA graph (replayed when phase timing is off: ~7 launches + 1 memset per step, 500 steps/move)
     int gc_headroom = 0;           // b200_set_gc_headroom: collect between moves every game with fewer free slots than this
     cudaGraphExec_t step_exec = nullptr; bool step_graph_failed = false;
@@ -1094,8 +1097,12 @@ extern "C" int b200_replay_enable(b200_engine *e, int min_visits, int capacity) 
     if (!e || capacity < 1 || min_visits < 0) return fail(B200_ERR_BAD_ARG, "bad argument");
     CK(cudaSetDevice(e->cfg.device));
     if (e->A.replay) return fail(B200_ERR_BAD_ARG, "replay memory already enabled");
-    if (dalloc(e, &e->A.replay, (size_t)capacity * 212) || dalloc(e, &e->A.replay_count, 1)) return B200_ERR_CUDA;
+    // twice the capacity is allocated: accumulation policy 0 (b200_replay_policy) stages the rows of a collection past memory_size before its
+    // random drop decides which of them stay (agent.cpp:800-801); k_gc itself never stores past A.replay_cap
+    if (dalloc(e, &e->A.replay, (size_t)2 * capacity * 212) || dalloc(e, &e->A.replay_count, 1)) return B200_ERR_CUDA;
+    e->replay_alloc = 2 * capacity;
     e->A.replay_cap = capacity; e->A.replay_min_visits = min_visits;
+    e->rp.memory_size = capacity;
     drop_step_graph(e);
     CK(cudaStreamSynchronize(e->stream));
     return B200_OK;
@@ -1128,5 +1135,171 @@ extern "C" int b200_collect_samples_dev(b200_engine *e, int min_visits, void *ou
     CK(cudaMemcpyAsync(count_out, e->d_sample_count, 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (*count_out > capacity) *count_out = capacity;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- replay-memory policies
+static int rp_count(b200_engine *e, int32_t *n) {
+    CK(cudaMemcpyAsync(n, e->A.replay_count, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (*n > e->A.replay_cap) *n = e->A.replay_cap;
+    return B200_OK;
+}
+static int rp_set_count(b200_engine *e, int32_t n) {
+    CK(cudaMemcpyAsync(e->A.replay_count, &n, 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+static int rp_scratch(b200_engine *e) {
+    if (e->d_rp_tmp) return B200_OK;
+    if (dalloc(e, &e->d_rp_tmp, (size_t)e->replay_alloc * 212, false) || dalloc(e, &e->d_rp_keep, (size_t)e->replay_alloc, false) ||
+        dalloc(e, &e->d_rp_vis, (size_t)e->replay_alloc, false) || dalloc(e, &e->d_rp_kept, 1)) return B200_ERR_CUDA;
+    return B200_OK;
+}
+// rows [lo, hi) with keep[i] != 0 are packed, in order, at lo, lo+1, ...; everything else in the memory stays as it is (the reference compacts
+// in place by copying downwards, so positions past the packed rows keep their old content).  Returns the number of packed rows.
+static int rp_compact(b200_engine *e, const std::vector<uint8_t> &keep, int lo, int hi, int *kept) {
+    int rc = rp_scratch(e);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->d_rp_keep, keep.data(), (size_t)hi, cudaMemcpyHostToDevice, e->stream));
+    k_replay_compact<<<1, 1024, 0, e->stream>>>(e->A.replay, e->d_rp_keep, lo, hi, e->d_rp_tmp, e->d_rp_kept);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(kept, e->d_rp_kept, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (*kept > 0) CK(cudaMemcpyAsync(e->A.replay + (size_t)lo * 212, e->d_rp_tmp + (size_t)lo * 212, (size_t)*kept * 212, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
+// OnlineMCTSAgent(accumulation_policy, episodes_per_train, memory_growth_rate) agent.cpp:588-617; memory_size / min_visit = b200_replay_enable's
+extern "C" int b200_replay_policy(b200_engine *e, int policy, int episodes_per_train, int memory_growth_rate) {
+    if (!e || !e->A.replay || policy < 0 || policy > 3 || episodes_per_train < 1 || memory_growth_rate < 0) return fail(B200_ERR_BAD_ARG, "replay memory not enabled / bad policy");
+    CK(cudaSetDevice(e->cfg.device));
+    ReplayPolicy fresh;
+    fresh.policy = policy; fresh.memory_size = e->rp.memory_size; fresh.episodes_per_train = episodes_per_train; fresh.memory_growth_rate = memory_growth_rate;
+    e->rp = fresh;
+    e->A.replay_cap = policy == 0 ? e->replay_alloc : e->rp.memory_size;      // policy 0: rows are staged past memory_size until the drop has decided
+    drop_step_graph(e);
+    return rp_set_count(e, 0);
+}
+
+// weighted_trimming(percentile) agent.cpp:710-749 (literally, including that the first removed row is not subtracted from memory_index)
+static int rp_weighted_trimming(b200_engine *e, double percentile) {
+    ReplayPolicy &P = e->rp;
+    const int N = P.memory_size;
+    int rc = rp_scratch(e);
+    if (rc) return rc;
+    k_replay_visits<<<(N + 255) / 256, 256, 0, e->stream>>>(e->A.replay, N, e->d_rp_vis);
+    std::vector<float> vis(N);
+    CK(cudaMemcpyAsync(vis.data(), e->d_rp_vis, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    std::vector<int> weights(N);
+    for (int i = 0; i < N; ++i) weights[i] = (int)vis[i];
+    std::sort(weights.begin(), weights.end());
+    const int threshold = weights[(int)(N * percentile)];
+    int idx_fill = -1;
+    for (int i = 0; i < N; ++i) if (vis[i] <= (float)threshold) { idx_fill = i; break; }
+    std::vector<uint8_t> keep(N, 1);
+    for (int i = idx_fill; i < N; ++i) if (vis[i] <= (float)threshold) keep[i] = 0;
+    for (int i = idx_fill + 1; i < N; ++i) if (vis[i] <= (float)threshold) --P.memory_index;
+    int kept = 0;
+    return rp_compact(e, keep, idx_fill, N, &kept);
+}
+
+// random_trimming(fraction) agent.cpp:751-775: IntSampler(memory_size).sample(n) = std::shuffle of the persistent index vector, first n, sorted
+static int rp_random_trimming(b200_engine *e, double fraction) {
+    ReplayPolicy &P = e->rp;
+    const int N = P.memory_size;
+    if (P.sampler.empty()) { P.sampler.resize(N); std::iota(P.sampler.begin(), P.sampler.end(), 0); }
+    std::shuffle(P.sampler.begin(), P.sampler.end(), P.mt);
+    std::vector<int> indices(P.sampler.begin(), P.sampler.begin() + (int)(N * fraction));
+    if (indices.empty()) return B200_OK;                          // (the reference reads indices.front() of an empty vector here: UB)
+    std::sort(indices.begin(), indices.end());
+    std::vector<uint8_t> keep(N, 1);
+    for (int i : indices) keep[i] = 0;
+    P.memory_index -= (int)indices.size();
+    int kept = 0;
+    return rp_compact(e, keep, indices.front(), N, &kept);
+}
+
+// The policy half of OnlineMCTSAgent::remove_nodes (agent.cpp:632-702), to be called after the collection(s) that stored rows — the reference
+// runs it inside every remove_nodes(); a single-game engine calls it after every simulation step / update_root in which counter 3 (collections)
+// moved and then reproduces the reference exactly; a batched run calls it once per move.  current_episode = Agent::current_episode
+// (agent.cpp:69,279-280: games finished so far).  *train_now = the reference would call train(m_state, m_value, m_variance, m_visit, memory_index)
+// now: drain the first *memory_index rows (b200_replay_peek_dev), train, then b200_replay_policy_trained().
+extern "C" int b200_replay_policy_step(b200_engine *e, int64_t current_episode, int32_t *train_now, int32_t *memory_index) {
+    if (!e || !train_now || !memory_index || e->rp.policy < 0) return fail(B200_ERR_BAD_ARG, "no replay policy configured");
+    CK(cudaSetDevice(e->cfg.device));
+    ReplayPolicy &P = e->rp;
+    int32_t count = 0;
+    int rc = rp_count(e, &count);
+    if (rc) return rc;
+    const int cur = (int)current_episode;
+    if (P.policy == 0) {
+        // store_nodes' drop (agent.cpp:798-801), applied to the rows this collection staged, in their order: ++accumulated_nodes; a row is dropped
+        // with probability memory_drop_prob; storing stops when the memory is full (:817)
+        std::vector<uint8_t> keep((size_t)std::max(count, 1), 1);
+        int kept_total = P.memory_index;
+        bool full = kept_total >= P.memory_size;
+        for (int i = P.memory_index; i < count; ++i) {
+            if (full) { keep[i] = 0; continue; }
+            ++P.accumulated_nodes;
+            if (P.unif(P.mt) < P.memory_drop_prob) { keep[i] = 0; continue; }
+            if (++kept_total == P.memory_size) full = true;
+        }
+        if (count > P.memory_index) {
+            int kept = 0;
+            rc = rp_compact(e, keep, P.memory_index, count, &kept);
+            if (rc) return rc;
+        }
+        P.memory_index = kept_total;
+        rc = rp_set_count(e, P.memory_index);
+        if (rc) return rc;
+    } else {
+        P.memory_index = count < P.memory_size ? count : P.memory_size;
+    }
+    bool pass = false;
+    const int diff = cur - P.last_training_episode;
+    if (P.policy == 0) {
+        if (P.last_accumulation_episode != cur) {
+            P.nodes_per_episode.push_back(P.accumulated_nodes);
+            if ((int)P.nodes_per_episode.size() > P.episodes_per_train) P.nodes_per_episode.pop_front();
+            const int sum = std::accumulate(P.nodes_per_episode.begin(), P.nodes_per_episode.end(), 0);
+            P.memory_drop_prob = std::max(0., 1. - double(P.memory_size) / sum);
+            P.accumulated_nodes = 0;
+            P.last_accumulation_episode = cur;
+        }
+        pass = diff >= P.episodes_per_train;
+        if (!pass && P.memory_index >= P.memory_size) { rc = rp_random_trimming(e, 0.01); if (rc) return rc; rc = rp_set_count(e, P.memory_index); if (rc) return rc; }
+    } else if (P.policy == 1) {
+        pass = diff >= P.episodes_per_train;
+        if (!pass && P.memory_index >= P.memory_size) { rc = rp_weighted_trimming(e, 0.01); if (rc) return rc; rc = rp_set_count(e, P.memory_index); if (rc) return rc; }
+    } else if (P.policy == 2) {
+        pass = diff >= P.episodes_per_train || P.memory_index >= P.memory_size;
+    } else {
+        const int m_size = std::min(P.n_trains * P.memory_growth_rate, P.memory_size);
+        pass = P.memory_index >= m_size;
+    }
+    *train_now = pass ? 1 : 0;
+    *memory_index = P.memory_index;
+    return B200_OK;
+}
+
+// after train(...): ++n_trains; memory_index = 0; last_training_episode = current_episode (agent.cpp:697-701)
+extern "C" int b200_replay_policy_trained(b200_engine *e, int64_t current_episode) {
+    if (!e || e->rp.policy < 0) return fail(B200_ERR_BAD_ARG, "no replay policy configured");
+    CK(cudaSetDevice(e->cfg.device));
+    e->rp.n_trains += 1;
+    e->rp.memory_index = 0;
+    e->rp.last_training_episode = (int)current_episode;
+    return rp_set_count(e, 0);
+}
+
+// the first n rows of the memory, copied to a DEVICE buffer without emptying it (the arrays the reference hands to train(): m_state ... [:memory_index])
+extern "C" int b200_replay_peek_dev(b200_engine *e, void *out_dev, int n) {
+    if (!e || !out_dev || n < 0 || !e->A.replay || n > e->replay_alloc) return fail(B200_ERR_BAD_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    if (n > 0) CK(cudaMemcpyAsync(out_dev, e->A.replay, (size_t)n * 212, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return B200_OK;
 }

@@ -499,22 +499,36 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
         // store_nodes (agents/ValueSim.py:122-159, agent.cpp:777-819): freed observations with visit >= min_visits_to_store and not
         // `end` go to the replay memory before their statistics are zeroed; storing stops when the memory is full (ValueSim.py:152-154)
         if (A.replay) {
-            for (int i = t; i < no; i += GC_THREADS) {
-                const int o = ofree[i];
-                const int4 st = statb[o];
-                if (st.x < A.replay_min_visits || st.x == 0 || st.w != 0) continue;
-                const int slot = atomicAdd(A.replay_count, 1);
-                if (slot >= A.replay_cap) { atomicSub(A.replay_count, 1); continue; }
-                uint8_t *dst = A.replay + (size_t)slot * 212;
-                const uint32_t *k = A.key + ((size_t)g * M + o) * KEY_WORDS;
-                for (int r = 0; r < 20; ++r) {
-                    const uint32_t row = (k[r >> 1] >> ((r & 1) * 16)) & 0x3ffu;
-                    for (int c = 0; c < 10; ++c) dst[r * 10 + c] = (uint8_t)((row >> c) & 1u);
+            // in ascending index order like the reference's loop (rows of one collection are contiguous and ordered; the memory stops
+            // taking rows when it is full: `if(++memory_index == memory_size) break;`, agent.cpp:817 / ValueSim.py:152-154)
+            for (int base = 0; base < no; base += GC_THREADS) {
+                const int i = base + t;
+                int o = 0; int4 st = make_int4(0, 0, 0, 0);
+                bool keep = false;
+                if (i < no) {
+                    o = ofree[i];
+                    st = statb[o];
+                    keep = !(st.x < A.replay_min_visits || st.x == 0 || st.w != 0);
                 }
-                for (int j = 0; j < 4; ++j) dst[(k[10] >> (8 * j)) & 0xffu] = 0xff;            // int8 -1: the falling piece
-                const float f[3] = {__int_as_float(st.y), __int_as_float(st.z), (float)st.x};
-                memcpy(dst + 200, f, 12);
+                int tot;
+                const int r = block_excl_scan(keep ? 1 : 0, s_warp, tot);
+                if (t == 0) s_n[0] = tot ? atomicAdd(A.replay_count, tot) : 0;
+                __syncthreads();
+                const int slot = s_n[0] + r;
+                if (keep && slot < A.replay_cap) {
+                    uint8_t *dst = A.replay + (size_t)slot * 212;
+                    const uint32_t *k = A.key + ((size_t)g * M + o) * KEY_WORDS;
+                    for (int rr = 0; rr < 20; ++rr) {
+                        const uint32_t row = (k[rr >> 1] >> ((rr & 1) * 16)) & 0x3ffu;
+                        for (int c = 0; c < 10; ++c) dst[rr * 10 + c] = (uint8_t)((row >> c) & 1u);
+                    }
+                    for (int j = 0; j < 4; ++j) dst[(k[10] >> (8 * j)) & 0xffu] = 0xff;            // int8 -1: the falling piece
+                    const float f[3] = {__int_as_float(st.y), __int_as_float(st.z), (float)st.x};
+                    memcpy(dst + 200, f, 12);
+                }
+                __syncthreads();
             }
+            if (t == 0 && *A.replay_count > A.replay_cap) atomicMin(A.replay_count, A.replay_cap);   // rows past the capacity were not stored
             __syncthreads();
         }
         for (int i = t; i < no; i += GC_THREADS) statb[ofree[i]] = make_int4(0, 0, 0, 0);

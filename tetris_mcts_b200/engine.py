@@ -200,6 +200,22 @@ class BatchedEngine:
         L.check(L.lib().b200_replay_drain_dev(self.h, C.c_void_p(int(dev_ptr)), int(capacity), L.ptr(cnt)))
         return int(cnt[0])
 
+    def replay_policy(self, accumulation_policy, episodes_per_train=25, memory_growth_rate=5000):
+        """OnlineMCTSAgent(accumulation_policy=, episodes_per_train=, memory_growth_rate=) (agent.cpp:588-617) on the memory of replay_enable."""
+        L.check(L.lib().b200_replay_policy(self.h, int(accumulation_policy), int(episodes_per_train), int(memory_growth_rate)))
+
+    def replay_policy_step(self, current_episode):
+        """The decision of OnlineMCTSAgent::remove_nodes after storing (agent.cpp:632-702) -> (train_now, memory_index)."""
+        t, m = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        L.check(L.lib().b200_replay_policy_step(self.h, int(current_episode), L.ptr(t), L.ptr(m)))
+        return bool(t[0]), int(m[0])
+
+    def replay_policy_trained(self, current_episode):
+        L.check(L.lib().b200_replay_policy_trained(self.h, int(current_episode)))
+
+    def replay_peek_into(self, dev_ptr, n_rows):
+        L.check(L.lib().b200_replay_peek_dev(self.h, C.c_void_p(int(dev_ptr)), int(n_rows)))
+
     def collect_samples_into(self, dev_ptr, capacity, min_visits):
         """ValueSim.store_nodes-style samples (agents/ValueSim.py:122-159) written to a DEVICE buffer of 212-byte rows."""
         cnt = np.zeros(1, np.int32)
