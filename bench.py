@@ -32,7 +32,7 @@ BASE_SEED = 123                                  # SURVEY §8d (echoes agent.cpp
 
 
 TC_ISSUED_FLOP_PER_BOARD = 2 * 128 * 16 * (96 * 36 + 64 * 2)   # k_tc_conv: 2x18 MMAs of 128x96x16 + 2 of 128x64x16 per board
-ARENA_BYTES_PER_SLOT = 324
+ARENA_BYTES_PER_SLOT = 304
 
 
 def _ncu_traffic_file():
@@ -549,6 +549,34 @@ def run_b200(args, cfg):
             out["also_configs1_vanilla"] = {"workload": "BASELINE configs[1]: Vanilla MCTS, %d games/GPU, %d sims/move" % (G2, sims2), "value": d2["sims"] / (ms2 / 1e3),
                                             "unit": "sims/s", "ms_per_step": ms2 / max(args.steps, 1), "rollout_steps_per_sim": d2["rollout_steps"] / max(d2["sims"], 1),
                                             "mean_trace_len": d2["trace_levels"] / max(d2["sims"], 1)}
+    # ---- BASELINE configs[3] proper (65536 games over 8 GPUs = 8192 per GPU) and configs[4] (distributional head, 16384 games over 8 GPUs =
+    # 2048 per GPU, 1500 sims/move): the per-GPU shares, a few moves each, so that the default line carries every BASELINE configuration
+    if cfg["mode"] == "lp" and not args.no_secondary and cfg["games_per_gpu"] == 16384:
+        def short_run(tag, label, n_games, n_sims, max_nodes, mode, eval_kind, w=None, dw=None, moves=3, warm=3):
+            e3 = BatchedEngine(n_games, max_nodes=max_nodes, mode=mode, eval_kind=eval_kind, weights=w, dist_weights=dw, env_args=ENV_ARGS,
+                               seed=BASE_SEED + 7919 * rank, device=local_rank, overflow_reset=True)
+            e3.set_games(PT.new_games(n_games, ENV_ARGS, D.shard_seeds(BASE_SEED, n_games * world, rank, world)))
+            e3.set_gc_headroom(max_nodes * 5 // 32)
+            for _ in range(warm):
+                e3.play_move(n_sims, auto_reset=True, want_stats=False)
+            q0 = e3.counters()
+            D.barrier()
+            torch.cuda.synchronize()
+            e3.timer_start()
+            for _ in range(moves):
+                e3.play_move(n_sims, auto_reset=True, want_stats=False)
+            ms3 = D.max_over_ranks(e3.timer_stop(), dev)
+            q1 = e3.counters()
+            d3 = D.sum_over_ranks({k: q1[k] - q0[k] for k in q1 if k != "max_trace_len"}, dev)
+            e3.close()
+            if out is not None:
+                out[tag] = {"workload": label, "value": d3["sims"] / (ms3 / 1e3), "unit": "sims/s", "ms_per_step": ms3 / moves, "moves_timed": moves,
+                            "warmup_moves": warm, "mean_trace_len": d3["trace_levels"] / max(d3["sims"], 1), "tree_resets_per_step": d3["tree_resets"] / moves}
+        short_run("also_configs3_8192_games_per_gpu", "BASELINE configs[3] per-GPU share: ValueSimLP + value net (net_tc), 8192 games/GPU (65536 over 8 GPUs), 500 sims/move",
+                  8192, 500, 16384, "lp", cfg["eval"], w=weights)
+        from tetris_mcts_b200.agents.DistValueSimOnline import init_dist_weights
+        short_run("also_configs4_distributional", "BASELINE configs[4] per-GPU share: distributional head (agents/core_distributional.py; network on fp32 CUDA cores), "
+                  "2048 games/GPU (16384 over 8 GPUs), 1500 sims/move", 2048, 1500, 32768, "dist", "net", dw=init_dist_weights(0, 50), moves=2, warm=2)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -182,7 +182,8 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     Arena &A = e->A;
     memset(&A, 0, sizeof(A));
     A.G = cfg->n_games; A.M = cfg->max_nodes;
-    int H = 16; while (H < 2 * A.M) H <<= 1;
+    int H = A.M + A.M / 2;                       // load factor <= 2/3 (tombstones only live inside k_gc, which rebuilds both tables)
+    if (H < 16) H = 16;
     A.H = H; A.trace_max = cfg->trace_max > 0 ? cfg->trace_max : 512;
     A.mode = cfg->mode; A.low = cfg->low; A.lp_end_from_obs = cfg->lp_end_from_obs; A.lp_var_gamma2 = cfg->lp_var_gamma2;
     A.stale_pop = cfg->stale_pop; A.eval_kind = cfg->eval_kind; A.overflow_reset = cfg->overflow_reset; A.gc_min_gain = cfg->overflow_reset ? cfg->max_nodes / 8 : 0; A.gamma = cfg->gamma; A.rollout_variance = cfg->rollout_variance;
@@ -199,7 +200,10 @@ extern "C" int b200_engine_create(const b200_config *cfg, b200_engine **out) {
     rc |= dalloc(e, &A.root, G); rc |= dalloc(e, &A.episode, G); rc |= dalloc(e, &A.status, G); rc |= dalloc(e, &A.srng, G);
     rc |= dalloc(e, &A.trace, G * A.trace_max); rc |= dalloc(e, &A.trace_len, G); rc |= dalloc(e, &A.leaf_kind, G);
     rc |= dalloc(e, &A.trace_meta, G * A.trace_max);
-    rc |= dalloc(e, &A.nmark, GM); rc |= dalloc(e, &A.omark, GM); rc |= dalloc(e, &A.gc_queue, GM * 2);
+    {   // collection scratch: one set per k_gc CTA (gc_blocks), not per game
+        const size_t pool = (size_t)(e->n_sm * 4 < A.G ? e->n_sm * 4 : A.G) * A.M;
+        rc |= dalloc(e, &A.nmark, pool); rc |= dalloc(e, &A.omark, pool); rc |= dalloc(e, &A.gc_queue, pool * 2);
+    }
     rc |= dalloc(e, &A.cur, G * REC_WORDS);
     rc |= dalloc(e, &A.req, G * 8); rc |= dalloc(e, &A.n_req, 2);
     rc |= dalloc(e, &A.gc_list, G); rc |= dalloc(e, &A.pending, G); rc |= dalloc(e, &A.resume_a, G);

@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
     const int M = A.M, H = A.H;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int g = A.gc_list[item];
-        uint8_t *nmark = A.nmark + (size_t)g * M, *omark = A.omark + (size_t)g * M;
-        int32_t *q0 = A.gc_queue + (size_t)g * 2 * M, *q1 = q0 + M;
+        uint8_t *nmark = A.nmark + (size_t)blockIdx.x * M, *omark = A.omark + (size_t)blockIdx.x * M;   // scratch of this CTA (a pool of gridDim.x sets,
+        int32_t *q0 = A.gc_queue + (size_t)blockIdx.x * 2 * M, *q1 = q0 + M;                            // not one per game: 10 bytes per slot saved)
         int32_t *rowb = A.row + (size_t)g * M * ROW_WORDS;
         uint2 *ntab = A.ntab + (size_t)g * H, *otab = A.otab + (size_t)g * H;
         const uint32_t *recb = A.rec + (size_t)g * M * REC_WORDS;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
                 uint32_t w[REC_WORDS] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w,
                                          m3.x, m3.y, m3.z, m3.w, m4.x, m4.y, m4.z, m4.w};
                 uint32_t h = fold32(hash_words(w, REC_WORDS));
-                uint32_t p = h & (uint32_t)(H - 1);
+                uint32_t p = tab_home(h, H);
                 for (;;) {
                     uint2 e = ntab[p];
                     if (e.y == 0u) break;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
                                   c4.z == m4.z && c4.w == m4.w;
                         if (eq) { ntab[p].y = 0xffffffffu; break; }
                     }
-                    p = (p + 1) & (uint32_t)(H - 1);
+                    p = tab_next(p, H);
                 }
             }
         } else {
@@ -477,8 +477,8 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
             const int cnt = s_n[0];
             for (int j = t; j < cnt; j += GC_THREADS) {      // keys are unique, so the claim order is free
                 uint2 e = list[j];
-                uint32_t p = e.x & (uint32_t)(H - 1);
-                while (atomicCAS(&tab[p].y, 0u, e.y) != 0u) p = (p + 1) & (uint32_t)(H - 1);
+                uint32_t p = tab_home(e.x, H);
+                while (atomicCAS(&tab[p].y, 0u, e.y) != 0u) p = tab_next(p, H);
                 tab[p].x = e.x;
             }
             __syncthreads();

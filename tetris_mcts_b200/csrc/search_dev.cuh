@@ -43,7 +43,7 @@ constexpr int NSTAT_WORDS = 8;    // node_stats row: {visit, mean, reward, varia
 //   stat     [G][M]     int4     observation statistics {visit, value, variance, end}  (one 128-bit load/store)
 //   rec      [G][M][20] u32      packed game (SPEC §6), the node key
 //   key      [G][M][12] u32      observation key (SPEC §6), the statistics key
-//   ntab/otab[G][H]     uint2    open-addressing tables {hash32, index}; index 0 empty, 0xffffffff deleted
+//   ntab/otab[G][H]     uint2    open-addressing tables {hash32, index}, H = 1.5 M; index 0 empty, 0xffffffff deleted
 //   nfree/ofree [G][M]  i32      free lists, popped from the back (agents/agent.py:72,99)
 struct Arena {
     int G, M, H, trace_max;
@@ -428,13 +428,16 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
 
 // ------------------------------------------------------------------ hash tables
 __device__ __forceinline__ uint32_t fold32(uint64_t h) { uint32_t x = (uint32_t)(h ^ (h >> 32)); return x ? x : 1u; }
+// open addressing over H slots, H any size (1.5 x max_nodes: a power of two would cost up to 2.67 x): home slot by multiply-shift, linear probing
+__device__ __forceinline__ uint32_t tab_home(uint32_t h, int H) { return __umulhi(h, (uint32_t)H); }
+__device__ __forceinline__ uint32_t tab_next(uint32_t p, int H) { return p + 1u == (uint32_t)H ? 0u : p + 1u; }
 
 // Find `words` (nw of them, held identically by every lane) in a table whose entries index `store` records.
 // Group-cooperative: lane j compares uint4 j of the candidate record.  Returns index or 0.
 template <int NW>
 __device__ __forceinline__ int table_find(const Grp &gp, const uint2 *tab, int H, const uint32_t *store, size_t base,
                                           const uint32_t (&words)[NW], uint32_t h, int *slot_out = nullptr) {
-    uint32_t p = h & (uint32_t)(H - 1);
+    uint32_t p = tab_home(h, H);
     for (;;) {
         uint2 e = tab[p];
         if (e.y == 0u) return 0;
@@ -452,17 +455,17 @@ __device__ __forceinline__ int table_find(const Grp &gp, const uint2 *tab, int H
             }
             if (gp.ballot(eq) == 0xffu) { if (slot_out) *slot_out = (int)p; return (int)e.y; }
         }
-        p = (p + 1) & (uint32_t)(H - 1);
+        p = tab_next(p, H);
     }
 }
 
 __device__ __forceinline__ void table_insert(const Grp &gp, uint2 *tab, int H, uint32_t h, int idx) {
     if (gp.lane == 0) {
-        uint32_t p = h & (uint32_t)(H - 1);
+        uint32_t p = tab_home(h, H);
         for (;;) {
             uint32_t y = tab[p].y;
             if (y == 0u || y == 0xffffffffu) break;
-            p = (p + 1) & (uint32_t)(H - 1);
+            p = tab_next(p, H);
         }
         tab[p] = make_uint2(h, (uint32_t)idx);
     }
@@ -621,8 +624,8 @@ __device__ __forceinline__ void warm_expand(const Arena &A, const Grp &gp, int g
 #if B200_WARM_EXPAND
     const int M = A.M, H = A.H;
     if (gp.lane < 7) {
-        const uint2 e1 = touch64(A.ntab + (size_t)g * H + (h & (uint32_t)(H - 1)));
-        const uint2 e2 = touch64(A.otab + (size_t)g * H + (hk & (uint32_t)(H - 1)));
+        const uint2 e1 = touch64(A.ntab + (size_t)g * H + tab_home(h, H));
+        const uint2 e2 = touch64(A.otab + (size_t)g * H + tab_home(hk, H));
         if (e1.y != 0u && e1.y != 0xffffffffu && e1.x == h) {       // probable transposition: its record (80 B) and its row's own fields
             const uint32_t *r = A.rec + ((size_t)g * M + e1.y) * REC_WORDS;
             touch32(r); touch32(r + REC_WORDS - 1);
