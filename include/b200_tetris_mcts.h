@@ -177,6 +177,7 @@ int b200_replay_policy(b200_engine *e, int accumulation_policy, int episodes_per
 int b200_replay_policy_step(b200_engine *e, int64_t current_episode, int32_t *train_now, int32_t *memory_index);
 int b200_replay_policy_trained(b200_engine *e, int64_t current_episode);
 int b200_replay_peek_dev(b200_engine *e, void *out_dev, int n_rows);
+int b200_replay_append(b200_engine *e, const uint8_t *rows_host, int n_rows);   /* rows join the memory as a collection's would: in order, until it is full */
 
 /* --- value-network training step: Model_VV._loss / Model.train / Yogi.step / Model_VV.train_data of the reference
  *     (model/model_vv.py:94-153,227-231, model/model.py:52-119, model/yogi.py:39-90) on the device.  weights = the state_dict vector of

@@ -323,10 +323,8 @@ def gen_agent_cpp_online(pt, policy):
             game.reset()
             ag.update_root(game)
     out["actions"] = np.array(acts, np.int32)
-    out["n_calls"] = len(calls)
-    out["call_moves"] = np.array([c[0] for c in calls], np.int32)
-    for i, c in enumerate(calls):
-        out["t%d_state" % i], out["t%d_value" % i], out["t%d_variance" % i], out["t%d_visit" % i] = c[1], c[2], c[3], c[4]
+    # only the actions are kept: the memories handed to train() depend on a defect of TreeAgent::update_available (agent.cpp:300-301, stale
+    # `occupied` entries in std::unordered_set order; oracle/agent_probe.cpp) and are pinned through the probe instead (gen_replay_policy)
     for k, v in cs.items():
         out["cfg_" + k] = v
     np.savez_compressed(os.path.join(HERE, "_online_p%d.npz" % policy), **out)
@@ -342,6 +340,66 @@ def merge_online():
             out["p%d_%s" % (p, k)] = z[k]
         os.remove(f)
     np.savez_compressed(os.path.join(HERE, "agent_online_golden.npz"), **out)
+
+
+
+PROBE_CASES = {0: dict(memory_size=300, ept=3, growth=100, min_visit=3), 1: dict(memory_size=300, ept=3, growth=100, min_visit=3),
+               2: dict(memory_size=300, ept=3, growth=100, min_visit=3), 3: dict(memory_size=300, ept=3, growth=70, min_visit=3)}
+
+
+def gen_replay_policy(policy):
+    """replay_policy_golden: the reference's own OnlineMCTSAgent::remove_nodes (store_nodes incl. the policy-0 random drop, accumulation policies
+    0-3, weighted_trimming, random_trimming, the train callback; agent.cpp:619-819, compiled UNCHANGED by inclusion into oracle/_ref/agent_probe)
+    driven with scripted collections: each one frees a seeded list of observations (index, visit, value, variance, end, state) at a given
+    episode count.  Recorded: memory_index / n_trains after every collection and the memory handed to every train() call.  One process per policy
+    (std::mt19937 mt(123) and random_trimming's IntSampler are process-global in the reference)."""
+    probe = O.load_ref_module("agent_probe")
+    cs = PROBE_CASES[policy]
+    M = 4000
+    calls = []
+
+    def train(state, value, variance, visit, n):
+        calls.append((np.array(state[:n, 0], np.int8), np.array(value[:n, 0], np.float32), np.array(variance[:n, 0], np.float32), np.array(visit[:n, 0], np.float32)))
+
+    pr = probe.Probe(policy, cs["memory_size"], cs["ept"], cs["growth"], cs["min_visit"], M, train)
+    rng = np.random.default_rng(100 + policy)
+    out = {"n_collections": 36}
+    episode = 0
+    for c in range(36):
+        k = int(rng.integers(20, 150))
+        idx = np.sort(rng.choice(np.arange(1, M), k, replace=False)).astype(np.int32)
+        visit = rng.integers(1, 220, k).astype(np.int32)
+        visit[rng.random(k) < 0.3] = rng.integers(1, 12, int((rng.random(k) < 0.3).sum()) or 1)[0]
+        value = rng.uniform(0, 90, k).astype(np.float32)
+        variance = rng.uniform(0.05, 500, k).astype(np.float32)
+        end = (rng.random(k) < 0.08).astype(np.int32)
+        states = ((idx[:, None].astype(np.int64) * 31 + np.arange(200)[None, :] * 17 + c) % 3 - 1).astype(np.int8)   # a formula, so the fixture stays small
+        if c % 3 == 2:
+            episode += 1
+        n_before = len(calls)
+        pr.collect(idx.tolist(), visit.tolist(), value.tolist(), variance.tolist(), end.tolist(), states, episode)
+        p = "c%d_" % c
+        out[p + "idx"], out[p + "visit"], out[p + "value"], out[p + "variance"], out[p + "end"], out[p + "states"] = idx, visit, value, variance, end, states
+        out[p + "episode"], out[p + "memory_index"], out[p + "n_trains"], out[p + "trained"] = episode, pr.memory_index(), pr.n_trains(), len(calls) - n_before
+    out["n_calls"] = len(calls)
+    for i, cl in enumerate(calls):
+        out["t%d_state" % i], out["t%d_value" % i], out["t%d_variance" % i], out["t%d_visit" % i] = cl
+    for kk, v in cs.items():
+        out["cfg_" + kk] = v
+    np.savez_compressed(os.path.join(HERE, "_probe_p%d.npz" % policy), **out)
+    print("replay_policy %d: %d train calls, rows %s, memory_index trail %s" % (policy, len(calls), [len(c[1]) for c in calls],
+                                                                                 [int(out["c%d_memory_index" % c]) for c in range(36)][:14]))
+
+
+def merge_probe():
+    out = {}
+    for p in range(4):
+        f = os.path.join(HERE, "_probe_p%d.npz" % p)
+        z = np.load(f)
+        for k in z.files:
+            out["p%d_%s" % (p, k)] = z[k]
+        os.remove(f)
+    np.savez_compressed(os.path.join(HERE, "replay_policy_golden.npz"), **out)
 
 
 def legacy_torch_overloads():
@@ -511,6 +569,13 @@ if __name__ == "__main__":
         gen_train()
     elif "--agent-online" in sys.argv:
         gen_agent_cpp_online(pt, int(sys.argv[sys.argv.index("--agent-online") + 1]))
+    elif "--replay-policy" in sys.argv:
+        gen_replay_policy(int(sys.argv[sys.argv.index("--replay-policy") + 1]))
+    elif "--replay-policy-all" in sys.argv:
+        import subprocess
+        for pol in range(4):
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--replay-policy", str(pol)], check=True, stderr=subprocess.DEVNULL)
+        merge_probe()
     elif "--agent-online-all" in sys.argv:
         import subprocess
         for pol in range(4):
@@ -532,4 +597,5 @@ if __name__ == "__main__":
         gen_train()
         import subprocess
         subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-online-all"], check=True)
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--replay-policy-all"], check=True)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--agent-modes"], check=True)

@@ -1299,6 +1299,20 @@ extern "C" int b200_replay_policy_trained(b200_engine *e, int64_t current_episod
     return rp_set_count(e, 0);
 }
 
+// Append n rows (HOST, 212 bytes each, the format k_gc stores) to the memory exactly as a collection would: in order, until the memory is full
+// (agent.cpp:817).  Seeds the memory from a dump file (ValueSim.py:176-177) or from another process; the policy tests script collections with it.
+extern "C" int b200_replay_append(b200_engine *e, const uint8_t *rows, int n) {
+    if (!e || !e->A.replay || (n > 0 && !rows) || n < 0) return fail(B200_ERR_BAD_ARG, "replay memory not enabled / bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    int32_t count = 0;
+    int rc = rp_count(e, &count);
+    if (rc) return rc;
+    int take = e->A.replay_cap - count;
+    if (take > n) take = n;
+    if (take > 0) CK(cudaMemcpyAsync(e->A.replay + (size_t)count * 212, rows, (size_t)take * 212, cudaMemcpyHostToDevice, e->stream));
+    return rp_set_count(e, count + (take > 0 ? take : 0));
+}
+
 // the first n rows of the memory, copied to a DEVICE buffer without emptying it (the arrays the reference hands to train(): m_state ... [:memory_index])
 extern "C" int b200_replay_peek_dev(b200_engine *e, void *out_dev, int n) {
     if (!e || !out_dev || n < 0 || !e->A.replay || n > e->replay_alloc) return fail(B200_ERR_BAD_ARG, "bad argument");

@@ -213,6 +213,11 @@ class BatchedEngine:
     def replay_policy_trained(self, current_episode):
         L.check(L.lib().b200_replay_policy_trained(self.h, int(current_episode)))
 
+    def replay_append(self, rows):
+        """rows uint8[n,212] join the memory as the rows of a collection would (in order, until the memory is full)."""
+        r = np.ascontiguousarray(rows, np.uint8).reshape(-1, 212)
+        L.check(L.lib().b200_replay_append(self.h, L.ptr(r), len(r)))
+
     def replay_peek_into(self, dev_ptr, n_rows):
         L.check(L.lib().b200_replay_peek_dev(self.h, C.c_void_p(int(dev_ptr)), int(n_rows)))
 
