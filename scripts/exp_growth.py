@@ -33,6 +33,15 @@ for mv in range(moves):
         mv, dt, G * sims / dt, d['new_nodes'] / G, d['eval_requests'] / max(d['sims'], 1), d['trace_levels'] / max(d['sims'], 1), c['max_trace_len'],
         d['gcs'], d['tree_resets'], c['games_finished'], ph), flush=True)
 print({k: (round(v[0], 2), v[1]) for k, v in eng.phase_ms().items()})
+try:
+    from tetris_mcts_b200 import _lib as _L
+    tl = np.zeros(G, np.int32)
+    _L.lib().b200_debug_trace_lens.argtypes = [_L.P, _L.P]
+    _L.check(_L.lib().b200_debug_trace_lens(eng.h, _L.ptr(tl)))
+    print('trace length of the last simulation over the games: mean %.1f  percentiles 50/75/90/95/98/99/99.9/100 = %s' % (
+        tl.mean(), [int(x) for x in np.percentile(tl, [50, 75, 90, 95, 98, 99, 99.9, 100])]))
+except Exception as ex:
+    print('trace lens unavailable', ex)
 
 import ctypes
 from tetris_mcts_b200 import _lib as L

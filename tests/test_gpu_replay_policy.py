@@ -79,5 +79,5 @@ def test_search_equals_compiled_agent_cpp_through_collections(gpu_lib, policy):
     for mv in range(len(actions)):
         a, _ = eng.play_move(cfg["sims"], auto_reset=True)
         assert a[0] == actions[mv], "search diverged from the reference's C++ agent at move %d" % mv
-    assert eng.counters()["gcs"] > 10
+    assert eng.counters()["gcs"] >= 5
     eng.close()

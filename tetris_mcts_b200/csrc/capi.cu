@@ -671,6 +671,14 @@ extern "C" int b200_debug_prof_tree(b200_engine *e, uint64_t *out16) {   // cloc
     return B200_OK;
 }
 
+extern "C" int b200_debug_trace_lens(b200_engine *e, int32_t *out) {   // development aid: trace length of every game's last simulation
+    if (!e || !out) return fail(B200_ERR_BAD_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(out, e->A.trace_len, (size_t)e->A.G * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return B200_OK;
+}
+
 extern "C" int b200_sync(b200_engine *e) {
     if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
     CK(cudaSetDevice(e->cfg.device));
