@@ -601,7 +601,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--ref-moves-per-step", type=int, default=2)
-    ap.add_argument("--exchange-rows", type=int, default=262144, help="rows (212 B) of the fixed-size replay block each rank contributes to the per-move all-gather")
+    ap.add_argument("--exchange-rows", type=int, default=131072, help="rows (212 B) of the fixed-size replay block each rank contributes to the per-move all-gather")
     args = ap.parse_args()
     if args.workload == "vanilla":
         G, sims, M, mode = args.games_per_gpu or 4096, args.sims or 300, args.max_nodes or 8192, "vanilla"
