@@ -326,8 +326,9 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
 __global__ void __launch_bounds__(TPB) k_expand_resume(Arena A) {
     __shared__ __align__(16) uint32_t s_stage[GROUPS_PER_BLOCK * STAGE_GROUP_WORDS];
     Grp gp;
-    int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
-    if (g >= A.G) return;
+    const int item = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);       // the games this step's k_select_expand queued for k_gc
+    if (item >= A.n_req[1]) return;
+    const int g = A.gc_list[item];
     if (A.pending[g] != PEND_EXPAND) return;
     gp.sync();
     if (gp.lane == 0) A.pending[g] = PEND_NONE;
