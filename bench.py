@@ -473,11 +473,15 @@ def run_b200(args, cfg):
                          "peak_src": peaks["src"]}
         if cfg["mode"] == "dist":
             conv_ms, conv_n = phases["conv"]
-            flop = 121856 + 16 * 4 * 32 * 512 * 2          # conv1 + conv2 on the 22x10 input of model_distributional.py:27
+            flop = 19 * 7 * 32 * 16 * 2 + 16 * 4 * 32 * 512 * 2   # conv1 (19x7 pixels) + conv2 (16x4) on the 22x10 input of model_distributional.py:27
             ach = pdelta["eval_requests"] * flop / max(conv_ms / 1e3, 1e-9) / 1e12
+            fc_ms, fc_n = phases["fc"]
             roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
-                    "kernel": "k_dn_conv", "ms_per_launch": conv_ms / max(conv_n, 1), "share_of_step": conv_ms / ms_instr,
-                    "note": "fp32 CUDA-core kernel (the distributional head is not on tensor cores yet); bf16 peak shown as the driver-measured denominator"}
+                    "kernel": "k_tdc_conv" if cfg["eval"] == "net_tc" else "k_dn_conv", "ms_per_launch": conv_ms / max(conv_n, 1),
+                    "share_of_step": conv_ms / ms_instr, "peak_src": peaks["src"] + " bf16 dense, sustained",
+                    "fc_kernel_tflops": pdelta["eval_requests"] * 2 * 2048 * 128 / (fc_ms / 1e3) / 1e12 if fc_ms > 0 else None,
+                    "note": "achieved counts ALGORITHMIC conv FLOPs (2 233 344 per board).  eval=net_tc: tcgen05 kind::f16 with the fp32 operands split into two "
+                            "scaled fp16 terms (k_tdc_conv / k_tdc_fc, csrc/distnet_tc.cuh); eval=net: fp32 CUDA cores (k_dn_conv / k_dn_fc)"}
         elif cfg["mode"] != "vanilla":
             conv_ms, conv_n = phases["conv"]
             fc_ms, fc_n = phases["fc"]
@@ -575,8 +579,9 @@ def run_b200(args, cfg):
         short_run("also_configs3_8192_games_per_gpu", "BASELINE configs[3] per-GPU share: ValueSimLP + value net (net_tc), 8192 games/GPU (65536 over 8 GPUs), 500 sims/move",
                   8192, 500, 16384, "lp", cfg["eval"], w=weights)
         from tetris_mcts_b200.agents.DistValueSimOnline import init_dist_weights
-        short_run("also_configs4_distributional", "BASELINE configs[4] per-GPU share: distributional head (agents/core_distributional.py; network on fp32 CUDA cores), "
-                  "2048 games/GPU (16384 over 8 GPUs), 1500 sims/move", 2048, 1500, 32768, "dist", "net", dw=init_dist_weights(0, 50), moves=2, warm=2)
+        short_run("also_configs4_distributional", "BASELINE configs[4] per-GPU share: distributional head (agents/core_distributional.py; network on tcgen05: "
+                  "k_tdc_conv / k_tdc_fc), 2048 games/GPU (16384 over 8 GPUs), 1500 sims/move", 2048, 1500, 32768, "dist", cfg["eval"],
+                  dw=init_dist_weights(0, 50), moves=2, warm=2)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -609,8 +614,6 @@ def main():
     elif args.workload == "dist":
         G, sims, M, mode = args.games_per_gpu or 2048, args.sims or 1500, args.max_nodes or 32768, "dist"
         name = "BASELINE configs[4]: distributional head (agents/core_distributional.py), %d games/GPU (16384 over 8 GPUs), %d sims/move" % (G, sims)
-        if args.eval == "net_tc":
-            args.eval = "net"
     else:
         G, sims, M, mode = args.games_per_gpu or 16384, args.sims or 500, args.max_nodes or 16384, "lp"
         name = "BASELINE configs[2]: ValueSimLP + value net, %d games/GPU, %d sims/move" % (G, sims)

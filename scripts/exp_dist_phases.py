@@ -1,12 +1,12 @@
 """Phase split of the distributional configuration (BASELINE configs[4]), development aid:  python scripts/exp_dist_phases.py 2048 32768 1500 3"""
-import sys, time
+import os, sys, time
 import numpy as np
 sys.path.insert(0, '.')
 from tetris_mcts_b200 import pyTetris as PT
 from tetris_mcts_b200.engine import BatchedEngine
 from tetris_mcts_b200.agents.DistValueSimOnline import init_dist_weights
 G, M, sims, moves = (int(x) for x in sys.argv[1:5])
-eng = BatchedEngine(G, max_nodes=M, mode='dist', eval_kind='net', dist_weights=init_dist_weights(0, 50), overflow_reset=True)
+eng = BatchedEngine(G, max_nodes=M, mode='dist', eval_kind=os.environ.get("DIST_EVAL", "net_tc"), dist_weights=init_dist_weights(0, 50), overflow_reset=True)
 eng.set_games(PT.new_games(G, (1, 0, 0), np.arange(123, 123 + G, dtype=np.uint32)))
 eng.set_gc_headroom(M * 5 // 32)
 for timing in (False, True):

@@ -86,24 +86,44 @@ def test_dist_engine_matches_oracle_agent(gpu_lib, oracle):
     eng.close()
 
 
-def test_dist_network_matches_reference_golden(gpu_lib, oracle):
-    """model/model_distributional.py Net (torch CPU) outputs recorded in tests/golden/distnet_golden.npz."""
+@pytest.mark.parametrize("kind", ["net", "net_tc"])
+def test_dist_network_matches_reference_golden(gpu_lib, oracle, kind):
+    """model/model_distributional.py Net (torch CPU) outputs recorded in tests/golden/distnet_golden.npz; fp32 CUDA cores ("net") and the
+    tcgen05 path ("net_tc": fp16 x 2 operand split, north_star's 1e-5 on the probabilities)."""
     from tetris_mcts_b200.engine import BatchedEngine
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "distnet_golden.npz"))
     w = oracle.seeded_dist_weights(int(z["seed"]))
-    eng = BatchedEngine(1, max_nodes=64, mode="dist", eval_kind="net", dist_weights=w)
+    eng = BatchedEngine(1, max_nodes=64, mode="dist", eval_kind=kind, dist_weights=w)
     got = eng.distnet(z["states"])
-    assert np.allclose(got, z["dist"], rtol=1e-5, atol=1e-7), np.abs(got - z["dist"]).max()
-    assert np.allclose(got, oracle.distnet_forward(w, z["states"]), rtol=1e-5, atol=1e-7)
+    atol = 1e-7 if kind == "net" else 1e-6
+    assert np.allclose(got, z["dist"], rtol=1e-5, atol=atol), np.abs(got - z["dist"]).max()
+    assert np.allclose(got, oracle.distnet_forward(w, z["states"]), rtol=1e-5, atol=atol)
     assert np.allclose(got.sum(axis=1), 1.0, atol=1e-5)
     eng.close()
 
 
-def test_dist_engine_runs_with_network(gpu_lib, oracle):
+def test_dist_network_tensor_core_path_matches_cuda_core_path(gpu_lib, oracle):
+    """Every batch size from one board to several 128-board tiles per CTA, position-independent."""
+    from arena_gen import boards
+    from tetris_mcts_b200.engine import BatchedEngine
+    w = oracle.seeded_dist_weights(3)
+    et = BatchedEngine(1, max_nodes=64, mode="dist", eval_kind="net_tc", dist_weights=w)
+    es = BatchedEngine(1, max_nodes=64, mode="dist", eval_kind="net", dist_weights=w)
+    for n in (1, 2, 3, 5, 127, 129, 700, 20000):
+        s = boards(n, n)
+        a, b = et.distnet(s), es.distnet(s)
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-6), (n, np.abs(a - b).max())
+        if n == 700:
+            assert np.array_equal(et.distnet(s[::-1])[::-1], a)
+    et.close(); es.close()
+
+
+@pytest.mark.parametrize("kind", ["net", "net_tc"])
+def test_dist_engine_runs_with_network(gpu_lib, oracle, kind):
     from tetris_mcts_b200 import pyTetris as PT
     from tetris_mcts_b200.engine import BatchedEngine
     n = 256
-    eng = BatchedEngine(n, max_nodes=2048, mode="dist", eval_kind="net", dist_weights=oracle.seeded_dist_weights(0), overflow_reset=True)
+    eng = BatchedEngine(n, max_nodes=2048, mode="dist", eval_kind=kind, dist_weights=oracle.seeded_dist_weights(0), overflow_reset=True)
     eng.set_games(PT.new_games(n, (1, 0, 0), np.arange(1, n + 1, dtype=np.uint32)))
     for _ in range(3):
         actions, stats = eng.play_move(100, auto_reset=True)

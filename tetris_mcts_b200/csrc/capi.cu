@@ -17,6 +17,7 @@
 #include "replay_policy.cuh"
 #ifdef B200_WITH_TC
 #include "valuenet_tc.cuh"
+#include "distnet_tc.cuh"
 #endif
 
 using namespace b200;
@@ -52,7 +53,7 @@ struct b200_engine {
     float *d_wraw = nullptr;
     NetWeights W{};
     float *d_act3 = nullptr; size_t act3_rows = 0;
-    void *tc_state = nullptr;
+    void *tc_state = nullptr; void *dn_tc_state = nullptr;
     bool have_dist_weights = false; float *d_dnw = nullptr; DistNetWeights DW{}; float *d_dn_act = nullptr; size_t dn_rows = 0;
     int n_sm = 148;
     // timing
@@ -247,6 +248,7 @@ extern "C" int b200_engine_destroy(b200_engine *e) {
     if (e->step_exec) cudaGraphExecDestroy(e->step_exec);
 #ifdef B200_WITH_TC
     tc_destroy(e->tc_state);
+    dn_tc_destroy(e->dn_tc_state);
 #endif
     for (void *p : e->allocs) cudaFree(p);
     for (auto &ev : e->ev) cudaEventDestroy(ev);
@@ -371,6 +373,9 @@ extern "C" int b200_load_dist_weights(b200_engine *e, const float *w, int atoms)
     e->DW = dn_pointers(e->d_dnw, atoms);
     CK(cudaFuncSetAttribute(k_dn_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_CONV_SMEM));
     CK(cudaFuncSetAttribute(k_dn_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_FC_SMEM));
+#ifdef B200_WITH_TC
+    if (dn_tc_prepare(&e->dn_tc_state, w, atoms, e->stream)) return fail(B200_ERR_CUDA, "tensor-core weight preparation (distributional network) failed");
+#endif
     e->have_dist_weights = true;
     drop_step_graph(e);
     return B200_OK;
@@ -378,6 +383,24 @@ extern "C" int b200_load_dist_weights(b200_engine *e, const float *w, int atoms)
 
 static int launch_distnet_on(b200_engine *e, const uint2 *req, const int32_t *n_req, const uint32_t *keys, int M, float *out, size_t max_rows) {
     if (!e->have_dist_weights) return fail(B200_ERR_NO_WEIGHTS, "b200_load_dist_weights was not called");
+#ifdef B200_WITH_TC
+    if (e->cfg.eval_kind == B200_EVAL_NET_TC) {
+        DnTcState *st = (DnTcState *)e->dn_tc_state;
+        bool moved = false;
+        if (dn_tc_ensure_act2(st, max_rows, e->stream, &moved)) return fail(B200_ERR_CUDA, "act2 (tensor-core layout) allocation failed");
+        if (moved) drop_step_graph(e);
+        {
+            PhaseTimer t(e, PH_CONV);
+            k_tdc_conv<<<e->n_sm, TDC_THREADS, TDC_SMEM, e->stream>>>(e->DW, st->TW, req, n_req, keys, M, st->d_act2, (int)st->tiles);
+        }
+        {
+            PhaseTimer t(e, PH_FC);
+            k_tdc_fc<<<e->n_sm, TDF_THREADS, TDF_SMEM, e->stream>>>(e->DW, st->TW, st->d_act2, (int)st->tiles, req, n_req, out);
+        }
+        CK(cudaGetLastError());
+        return B200_OK;
+    }
+#endif
     if (e->dn_rows < max_rows) {
         const bool had = e->d_dn_act != nullptr;
         if (had) { cudaStreamSynchronize(e->stream); dfree(e, e->d_dn_act); e->d_dn_act = nullptr; e->dn_rows = 0; }

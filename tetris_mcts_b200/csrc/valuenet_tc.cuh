@@ -360,7 +360,9 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     constexpr int NS = TCC_SLOTS;
     uint64_t *bar_c1 = bars, *bar_c2 = bars + NS, *bar_c3 = bars + 2 * NS;             // tensor core -> workers: layer of slot done
     uint64_t *bar_a0 = bars + 3 * NS, *bar_a1 = bars + 4 * NS, *bar_a2 = bars + 5 * NS; // workers -> issuer: operand of slot written
+#if B200_CONV3_PAIR
     uint64_t *bar_e3 = bars + 6 * NS;                                                   // workers -> conv3 issuer: the pair accumulator has been read
+#endif
     uint32_t *sKey = reinterpret_cast<uint32_t *>(smem + TCC_OFF_KEY);
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(smem + TCC_OFF_BAR + 7 * NS * 8);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
