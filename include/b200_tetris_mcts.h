@@ -83,6 +83,11 @@ int b200_update_root(b200_engine *e, int auto_reset);
 int b200_remove_nodes(b200_engine *e, int min_free);
 int b200_set_gc_headroom(b200_engine *e, int min_free);
 
+/* --- scheduling only (no reference counterpart, no effect on any result): the up to max_games games whose last trace was longest walk the tree
+ * on a second stream, so that a simulation step of the other games does not last as long as the deepest walk of all (ValueSim / ValueSimLP with
+ * B200_EVAL_NET_TC; ignored otherwise).  0 (default) = one lane. */
+int b200_set_deep_lane(b200_engine *e, int max_games);
+
 /* --- TreeAgent.mcts (agents/ValueSimLP.py:13, ValueSim.py:52, Vanilla.py:17): `sims` simulations on every game */
 int b200_run_sims(b200_engine *e, int sims);
 

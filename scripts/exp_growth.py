@@ -11,6 +11,8 @@ eng = BatchedEngine(G, max_nodes=M, mode='lp', eval_kind=ev, weights=init_weight
 eng.set_games(PT.new_games(G, (1, 0, 0), np.arange(123, 123 + G, dtype=np.uint32)))
 eng.set_gc_headroom(int(os.environ.get('GC_HEADROOM', '0')))
 import os
+eng.set_deep_lane(int(os.environ.get('DEEP_LANE', '0')))
+import os
 TIMING = os.environ.get('NO_TIMING') != '1'
 eng.set_timing(TIMING)
 prev = eng.counters()

@@ -287,10 +287,10 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     __syncthreads();
     Grp gp;
 #if B200_GAMES_PER_WARP < 4
-    const int g = (threadIdx.x & 31) < 8 * B200_GAMES_PER_WARP
-                      ? blockIdx.x * SE_GAMES_PER_BLOCK + (threadIdx.x >> 5) * B200_GAMES_PER_WARP + ((threadIdx.x & 31) >> 3) : A.G;
+    const int g = lane_game(A, (threadIdx.x & 31) < 8 * B200_GAMES_PER_WARP
+                                   ? blockIdx.x * SE_GAMES_PER_BLOCK + (threadIdx.x >> 5) * B200_GAMES_PER_WARP + ((threadIdx.x & 31) >> 3) : A.G);
 #else
-    const int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
+    const int g = lane_game(A, blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3));
 #endif
     GroupOut out{false, 0, 0, 0, 0, 0};
     select_expand_group(A, gp, g, s_z, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS, out);
@@ -573,6 +573,41 @@ __global__ void k_gc_request(Arena A, int min_free) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= A.G || A.status[g] != ST_OK || A.pending[g] != PEND_NONE) return;
     if (A.n_nfree[g] < min_free) A.gc_list[atomicAdd(A.n_req + 1, 1)] = g;
+}
+
+// ---------------------------------------------------------------- deep lane (b200_set_deep_lane)
+// A simulation step's k_select_expand lasts as long as its DEEPEST walk (every game is resident, a level costs ~4.8 k clk), and a game's trace
+// length is predictable from its previous one (correlation 0.98, profiles/exp_trace_corr_r2.txt).  Once per move the games whose last trace
+// was longest (at most deep_cap of them) get a lane of their own: their select / collect / resume kernels run on a second stream next to the
+// other games' select AND network kernels, and join them before the (small) second network launch.  One CTA: histogram, threshold, two lists.
+__global__ void __launch_bounds__(1024) k_classify(Arena A, int deep_cap, int32_t *glist0, int32_t *n0, int32_t *glist1, int32_t *n1) {
+    __shared__ int hist[514];
+    __shared__ int s_thr, s_c0, s_c1;
+    for (int i = threadIdx.x; i < 514; i += 1024) hist[i] = 0;
+    if (threadIdx.x == 0) { s_c0 = 0; s_c1 = 0; }
+    __syncthreads();
+    for (int g = threadIdx.x; g < A.G; g += 1024) { const int d = A.trace_len[g]; atomicAdd(&hist[d < 0 ? 0 : (d > 512 ? 512 : d)], 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int above = 0, thr = 512;
+        while (thr > 0 && above + hist[thr] <= deep_cap) { above += hist[thr]; --thr; }      // games with D > thr: `above` <= deep_cap
+        s_thr = thr;
+    }
+    __syncthreads();
+    const int thr = s_thr;
+    for (int g = threadIdx.x; g < A.G; g += 1024) {        // (the order inside a list is arbitrary: a game's results do not depend on its slot)
+        if (A.trace_len[g] > thr) glist1[atomicAdd(&s_c1, 1)] = g; else glist0[atomicAdd(&s_c0, 1)] = g;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *n0 = s_c0; *n1 = s_c1; }
+}
+
+// the deep lane's evaluation requests behind the main lane's: n_req[0] += n_deep, n_req[2] = where they start (k_tc_conv's second launch)
+__global__ void k_merge_requests(uint2 *req, int32_t *n_req, const uint2 *req_deep, const int32_t *n_req_deep) {
+    const int n_main = n_req[0], n_deep = n_req_deep[0];
+    for (int i = threadIdx.x; i < n_deep; i += blockDim.x) req[n_main + i] = req_deep[i];
+    __syncthreads();
+    if (threadIdx.x == 0) { n_req[2] = n_main; n_req[0] = n_main + n_deep; }
 }
 
 // ---------------------------------------------------------------- test evaluator (shared definition with oracle/mcts_oracle.c)

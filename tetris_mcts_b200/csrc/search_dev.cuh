@@ -72,6 +72,8 @@ struct Arena {
     float *rollout_val;            // [G]
     // distributional mode (agents/core_distributional.py; BASELINE config 5): node-indexed statistics and value histograms
     float *nstat; float *ndist; float *dist_eval; int dist_bins; double dist_vmin, dist_vmax;   // [G][M][8], [G][M][bins], [G][bins]
+    // lanes (b200_set_deep_lane): the select / collect / resume kernels of a lane work on the games glist[0 .. *n_list); nullptr: every game
+    const int32_t *glist; const int32_t *n_list;
     unsigned long long *counters;  // [8] 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels 5 rollout steps 6 new nodes
     unsigned long long *prof;      // timing mode only: clock64 sums of k_select_expand {select, leaf load, expand, finish, groups sampled}
 };
@@ -106,6 +108,11 @@ struct GrpW {
 };
 
 __device__ __forceinline__ size_t node_at(const Arena &A, int g, int i) { return (size_t)g * A.M + i; }
+// the game that slot `slot` of a lane's k_select_expand works on (A.G = none)
+__device__ __forceinline__ int lane_game(const Arena &A, int slot) {
+    if (!A.glist) return slot < A.G ? slot : A.G;
+    return slot < *A.n_list ? A.glist[slot] : A.G;
+}
 
 // ------------------------------------------------------------------ exact arithmetic (see header comment)
 __device__ __forceinline__ float ztab(const Arena &A, int n) {

@@ -351,8 +351,8 @@ __device__ __forceinline__ void issue_conv3_pair(uint32_t tmem_d, uint32_t a_add
 #endif
 
 __global__ void __launch_bounds__(TCC_THREADS, 1)
-k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr, const uint32_t *keys, int M, uint8_t *act3, int n_tiles,
-          unsigned long long *prof) {
+k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr, const int32_t *first_ptr, const uint32_t *keys, int M, uint8_t *act3,
+          int n_tiles, unsigned long long *prof) {
 #define PROF_T(i) do { if (prof && do_prof) { long long _n = clock64(); pacc[i] += _n - ptick; ptick = _n; } } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
     float *sB = reinterpret_cast<float *>(smem + TCC_OFF_BIAS);
@@ -387,7 +387,8 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const int n_req = *n_req_ptr;
+    const int first = first_ptr ? *first_ptr : 0;      // this launch evaluates the requests [first, *n_req_ptr) (the deep lane's: see k_merge_requests)
+    const int n_req = *n_req_ptr - first;
     // Boards are handed out in runs of TCC_RUN consecutive requests (neighbouring act3 rows get written close in time; short runs keep
     // the CTAs' board counts within TCC_RUN of each other: with runs of 8 the last CTAs had 4 % more work); board i of
     // this CTA's sequence lives in slot i % 4.  Four boards are in flight at different stages (software pipeline):
@@ -399,7 +400,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
     const int n_runs = (n_req + TCC_RUN - 1) / TCC_RUN;
     int n_local = 0;
     for (int run = blockIdx.x; run < n_runs; run += gridDim.x) n_local += min(TCC_RUN, n_req - run * TCC_RUN);
-    auto board_of = [&](int i) -> int { return ((i / TCC_RUN) * (int)gridDim.x + (int)blockIdx.x) * TCC_RUN + (i % TCC_RUN); };
+    auto board_of = [&](int i) -> int { return first + ((i / TCC_RUN) * (int)gridDim.x + (int)blockIdx.x) * TCC_RUN + (i % TCC_RUN); };
     if (warp == TCC_ISSUER) {
         // ===================================================== MMA issuer
         if (lane == 0) {

@@ -96,6 +96,10 @@ class BatchedEngine:
         """update_root() then collects every game with fewer than min_free free slots (0 = the reference's lazy collection only)."""
         L.check(L.lib().b200_set_gc_headroom(self.h, int(min_free)))
 
+    def set_deep_lane(self, max_games):
+        """Scheduling only: the max_games games with the longest traces walk on a second stream (b200_set_deep_lane); 0 = off."""
+        L.check(L.lib().b200_set_deep_lane(self.h, int(max_games)))
+
     def update_root(self, auto_reset=False):
         L.check(L.lib().b200_update_root(self.h, int(auto_reset)))
 
