@@ -60,7 +60,7 @@ __device__ __forceinline__ void tmem_ld_conv4_sum(uint32_t taddr, float (&v)[8])
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const float s1 = __shfl_down_sync(0xffffffffu, d1[e], 1), s2 = __shfl_down_sync(0xffffffffu, d2[e], 2), s3 = __shfl_down_sync(0xffffffffu, d3[e], 3);
-        v[e] = (((s3 + s2) + s1) + d0[e]) * TC_UNSCALE;
+        v[e] = ((s3 + s2) + s1) + d0[e];   // still scaled by 2^10 (see k_tc_conv: the scaling is folded into the bias fma)
     }
 }
 
@@ -202,9 +202,10 @@ k_tdc_conv(DistNetWeights W, DnTcWeights TW, const uint2 *req, const int32_t *n_
         // workers (512 threads): TMEM lane quadrant q, 8-cout chunk cq, pixel row m
         const int q = warp & 3, cq = warp >> 2, m = q * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 8;
-        float bias1[8], bias2[8];
+        float bias1[8], bias2[8];                                  // pre-scaled by 16: leaky(x * 2^-10 + b) * 16 == leaky(fma(x, 2^-6, 16 b)) bit for bit
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { bias1[e] = sB[cq * 8 + e]; bias2[e] = sB[32 + cq * 8 + e]; }
+        for (int e = 0; e < 8; ++e) { bias1[e] = sB[cq * 8 + e] * TC_SCALE_A; bias2[e] = sB[32 + cq * 8 + e] * TC_SCALE_A; }
+        constexpr float K2 = TC_UNSCALE * TC_SCALE_A, K1 = TC_SCALE_A / TC_SCALE_W;
         for (int i = 0; i < n_local + 2; ++i) {
             // ---- E2(i-2): conv2 epilogue: dx sum + bias + LeakyReLU + split -> act2 in HBM (FC tile layout)
             if (i >= 2) {
@@ -217,7 +218,7 @@ k_tdc_conv(DistNetWeights W, DnTcWeights TW, const uint2 *req, const int32_t *n_
                 if (x < 4) {
                     float o[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = leaky(v[e] + bias2[e]) * TC_SCALE_A;
+                    for (int e = 0; e < 8; ++e) o[e] = leaky(fmaf(v[e], K2, bias2[e]));
                     uint4 c1, c2;
                     split8(o, c1, c2);
                     const int kc = (y * 4 + x) * 4 + cq;
@@ -236,7 +237,7 @@ k_tdc_conv(DistNetWeights W, DnTcWeights TW, const uint2 *req, const int32_t *n_
                     float w1[8], w2[8], o[8];
                     tmem_ld8x2(t_lane + slot * 128, w1, w2);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = leaky((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + bias1[e]) * TC_SCALE_A;
+                    for (int e = 0; e < 8; ++e) o[e] = leaky(fmaf(w2[e] + w1[e], K1, bias1[e]));
                     uint4 c1, c2;
                     split8(o, c1, c2);
                     *reinterpret_cast<uint4 *>(abase + m * 16) = c1;
@@ -247,7 +248,7 @@ k_tdc_conv(DistNetWeights W, DnTcWeights TW, const uint2 *req, const int32_t *n_
                     tmem_ld8x2(t_lane + slot * 128 + 64, w1, w2);
                     if (lane < 24) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = leaky((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + bias1[e]) * TC_SCALE_A;
+                        for (int e = 0; e < 8; ++e) o[e] = leaky(fmaf(w2[e] + w1[e], K1, bias1[e]));
                         uint4 c1, c2;
                         split8(o, c1, c2);
                         *reinterpret_cast<uint4 *>(abase + (128 + lane) * 16) = c1;

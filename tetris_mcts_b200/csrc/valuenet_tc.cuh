@@ -310,7 +310,7 @@ __device__ __forceinline__ void tmem_ld_conv_sum(uint32_t taddr, float (&v)[8]) 
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const float s1 = __shfl_down_sync(0xffffffffu, d1[e], 1), s2 = __shfl_down_sync(0xffffffffu, d2[e], 2);
-        v[e] = ((s2 + s1) + d0[e]) * TC_UNSCALE;
+        v[e] = (s2 + s1) + d0[e];          // still carries the operand scaling 2^10: the callers fold TC_UNSCALE into their bias fma
     }
 }
 
@@ -539,9 +539,12 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
         long long pacc[16] = {0}, ptick = clock64();
         const int q = warp & 3, cq = warp >> 2, m = q * 32 + lane;       // TMEM lane quadrant, 8-cout chunk, pixel row
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + cq * 8;
-        float bias1[8], bias2[8], bias3[8];                               // this warp's 8 couts, all three layers
+        // this warp's 8 couts, all three layers.  relu(x * 2^-10 + b) * 16 == relu(fma(x, 2^-6, 16 b)) bit for bit (scaling by a power of two commutes
+        // with rounding): the biases are kept pre-scaled and an epilogue value costs one fma + one max instead of mul, add, max, mul
+        float bias1[8], bias2[8], bias3[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { bias1[e] = sB[cq * 8 + e]; bias2[e] = sB[32 + cq * 8 + e]; bias3[e] = sB[64 + cq * 8 + e]; }
+        for (int e = 0; e < 8; ++e) { bias1[e] = sB[cq * 8 + e] * TC_SCALE_A; bias2[e] = sB[32 + cq * 8 + e] * TC_SCALE_A; bias3[e] = sB[64 + cq * 8 + e] * TC_SCALE_A; }
+        constexpr float K23 = TC_UNSCALE * TC_SCALE_A, K1 = TC_SCALE_A / TC_SCALE_W;
 #if B200_CONV3_PAIR
         const int n_iter = 2 * ((n_local + 1) / 2) + 3;                   // the last pair's E3 runs at iteration 2k+4
 #else
@@ -559,7 +562,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                 {
                     float o[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + bias2[e], 0.f) * TC_SCALE_A;
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(fmaf(v[e], K23, bias2[e]), 0.f);
                     uint4 c1, c2;
                     split8(o, c1, c2);
 #if !B200_CONV3_PAIR
@@ -622,7 +625,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
 #endif
                     float o[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + bias3[e], 0.f) * TC_SCALE_A;
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(fmaf(v[e], K23, bias3[e]), 0.f);
                     uint4 c1, c2;
                     split8(o, c1, c2);
                     const int kc = (y * 4 + x) * 4 + cq;
@@ -656,7 +659,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     float w1[8], w2[8], o[8];
                     tmem_ld8x2(t_c1, w1, w2);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + bias1[e], 0.f) * TC_SCALE_A;
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(fmaf(w2[e] + w1[e], K1, bias1[e]), 0.f);
                     uint4 c1, c2;
                     split8(o, c1, c2);
                     *reinterpret_cast<uint4 *>(abase + m * 16) = c1;
@@ -667,7 +670,7 @@ k_tc_conv(NetWeights W, TcWeights TW, const uint2 *req, const int32_t *n_req_ptr
                     tmem_ld8x2(t_c1 + 64, w1, w2);
                     if (lane < 16) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = fmaxf((w2[e] + w1[e]) * (1.f / TC_SCALE_W) + bias1[e], 0.f) * TC_SCALE_A;
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf(fmaf(w2[e] + w1[e], K1, bias1[e]), 0.f);
                         uint4 c1, c2;
                         split8(o, c1, c2);
                         *reinterpret_cast<uint4 *>(abase + (128 + lane) * 16) = c1;
