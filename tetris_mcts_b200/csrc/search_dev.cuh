@@ -200,6 +200,9 @@ __device__ __forceinline__ uint32_t link_word(const Uniq &u) {
 #ifndef B200_L2_HOT_LEVELS
 #define B200_L2_HOT_LEVELS 16
 #endif
+#ifndef B200_ROLL_PREFETCH
+#define B200_ROLL_PREFETCH 0   // 1: rolling L2 prefetch along the previous simulation's trace inside the walk (select_trace)
+#endif
 #ifndef B200_ROW_HINT
 #define B200_ROW_HINT 1        // 0: the walk loads its row words without an L2 policy (the statistics keep theirs)
 #endif
@@ -324,6 +327,17 @@ struct ArenaAcc {
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return (zs && n >= 0 && n < ZS_N) ? zs[n] : ztab(A, n); }
     __device__ __forceinline__ unsigned long long *level_prof() const { return (A.prof && (g & 63) == 0) ? A.prof + 8 : nullptr; }
+    // rolling prefetch along the PREVIOUS simulation's trace (B200_ROLL_PREFETCH): its length, one of its levels, and the L2 requests for a level
+    __device__ __forceinline__ int prev_trace_len() const { return A.trace_len[g]; }
+    __device__ __forceinline__ void prev_trace(int lv, int &idx, int &o) const { idx = traceg[lv]; o = tmetag[lv].x; }
+    __device__ __forceinline__ void prefetch_level(int idx, int o) const {
+        const char *r = reinterpret_cast<const char *>(rowg + (size_t)idx * ROW_WORDS);
+        prefetch_l2(r + 32); prefetch_l2(r + 96);                                     // the walk reads words 8..31 of the row line
+        const char *st = reinterpret_cast<const char *>(statg + o);                   // siblings' observation ids are consecutive (free-list pops):
+        const char *lo = reinterpret_cast<const char *>(statg), *hi = lo + (size_t)A.M * sizeof(int4) - 1;   // their statistics surround the chosen one's
+        const char *a = st - 64, *b = st + 64;
+        prefetch_l2(st); prefetch_l2(a < lo ? lo : a); prefetch_l2(b > hi ? hi : b);
+    }
 };
 
 struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
@@ -350,6 +364,9 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = *rng; uint32_t r = rng_next(sr); *rng = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return ztab(*A, n); }
     __device__ __forceinline__ unsigned long long *level_prof() const { return nullptr; }
+    __device__ __forceinline__ int prev_trace_len() const { return 0; }
+    __device__ __forceinline__ void prev_trace(int, int &idx, int &o) const { idx = 0; o = 0; }
+    __device__ __forceinline__ void prefetch_level(int, int) const {}
 };
 
 // ------------------------------------------------------------------ select (core.h:167-224)
@@ -366,6 +383,16 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
     const GrpW gp;
     int idx = root, D = 0;
     bool walking = active;
+#if B200_ROLL_PREFETCH
+    // A game's walk mostly retraces its previous simulation's path, and every level is two DEPENDENT misses.  The previous trace is known
+    // (trace / trace_meta are overwritten level by level as this walk advances), so lanes 0..3 of a group request, every four levels, the row
+    // lines and statistics lines of the old path's levels +2..+5 from L2: where the new walk follows the old path it finds them there.  A
+    // short look-ahead keeps the footprint at ~16 MB for 16384 games (requesting the whole old path before the walk — B200_PV_PREFETCH —
+    // is 277 MB per step against a 126 MB L2 and was slower).  The old entries are loaded one batch earlier than they are used.
+    const int prev_len = active ? acc.prev_trace_len() : 0;
+    int pf_idx = 0, pf_o = 0, it = 0;
+    if (gp.lane < 4 && 2 + gp.lane < prev_len) acc.prev_trace(2 + gp.lane, pf_idx, pf_o);
+#endif
 #if B200_SELECT_PROF
     unsigned long long *lp = (active && gp.lane == 0) ? acc.level_prof() : nullptr;
     long long lt = lp ? clock64() : 0;
@@ -375,6 +402,15 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
 #endif
     while (__any_sync(0xffffffffu, walking)) {
         if (walking && D >= trace_max) { status = ST_TRACE_FULL; walking = false; }
+#if B200_ROLL_PREFETCH
+        if ((it & 3) == 0) {                                             // (warp-uniform: the walking groups of a warp are at the same level)
+            if (walking && pf_idx > 0) acc.prefetch_level(pf_idx, pf_o);
+            pf_idx = 0;
+            const int lv = it + 6 + gp.lane;
+            if (walking && gp.lane < 4 && lv < prev_len) acc.prev_trace(lv, pf_idx, pf_o);
+        }
+        ++it;
+#endif
         if (walking) {
             if (gp.lane == 0) acc.put_trace(D, idx);
             ++D;
