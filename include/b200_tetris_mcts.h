@@ -6,7 +6,7 @@
  *   - extern "C", plain pointers and sizes, no C++/torch types; the caller owns every buffer it passes;
  *   - pointers are HOST pointers unless the name says `_dev`;
  *   - every function returns 0 on success or a B200_ERR_* code; b200_last_error() gives the text;
- *   - one host thread per engine; all work of an engine is issued on its own CUDA stream;
+ *   - one host thread per engine; all work of an engine is issued on ONE CUDA stream: its own, or the caller's (b200_engine_set_stream);
  *   - there is no CPU fallback: without a CUDA device every compute entry point returns B200_ERR_CUDA.
  * Games travel as the 80-byte packed record of SPEC_PYTETRIS.md §6 (20 uint32 words).
  */
@@ -67,6 +67,14 @@ int b200_device_count(void);
 /* --- engine lifetime: replaces TreeAgent.__init__/init_array (agents/agent.py:36-88), Agent.close (:303-307) */
 int b200_engine_create(const b200_config *cfg, b200_engine **out);
 int b200_engine_destroy(b200_engine *e);
+/* --- SURVEY 8(b).5 "explicit cudaStream_t" (no reference counterpart: the reference is synchronous CPU code).  cuda_stream is a
+ *     cudaStream_t passed as void* so that this header needs no CUDA include: from now on ALL work of the engine (kernels, the captured
+ *     simulation step, async copies, the event timers) is issued on it; NULL = a private non-blocking stream again (the default).  The
+ *     engine drains its previous stream inside the call; the caller owns its stream.  The legacy default stream cannot be captured into
+ *     a CUDA graph: with it the step falls back to direct launches.  b200_engine_get_stream returns the stream in use, so that a caller
+ *     that produces or consumes `_dev` buffers on its own stream can order against it (cudaStreamWaitEvent). */
+int b200_engine_set_stream(b200_engine *e, void *cuda_stream);
+int b200_engine_get_stream(b200_engine *e, void **cuda_stream_out);
 
 /* --- Model.load (model/model.py:163-174): weights = the state_dict tensors concatenated (B200_N_WEIGHTS floats) */
 int b200_load_weights(b200_engine *e, const float *weights);

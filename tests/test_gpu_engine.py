@@ -346,6 +346,49 @@ def test_graph_replay_equals_direct_launches(gpu_lib):
         assert np.array_equal(g0, g1)
 
 
+def test_engine_on_the_callers_stream(gpu_lib):
+    """SURVEY 8(b).5 explicit cudaStream_t: the same moves on the engine's private stream, on a torch stream handed over with
+    b200_engine_set_stream (switched in the middle of a game, graph re-captured), and back on a private stream give identical results;
+    work the caller enqueues on ITS stream before a move (the upload of the games) is ordered before the engine's kernels."""
+    import torch
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    n, M, sims, moves = 64, 1024, 20, 9
+    recs = PT.new_games(n, ARGS, np.arange(11, 11 + n, dtype=np.uint32))
+    res = []
+    for external in (False, True):
+        eng = BatchedEngine(n, max_nodes=M, mode="lp", eval_kind="synthetic", seed=9, overflow_reset=True)
+        own = eng.get_stream()
+        assert own != 0
+        ts = torch.cuda.Stream()
+        eng.set_games(recs)
+        out = []
+        for mv in range(moves):
+            if external and mv == 2:
+                eng.set_stream(ts)
+                assert eng.get_stream() == ts.cuda_stream
+            if external and mv == 6:
+                eng.set_stream(None)
+                assert eng.get_stream() not in (0, ts.cuda_stream)
+            if external and mv == 4:       # caller-side work on the shared stream right before the move: a long kernel, then the engine's step
+                with torch.cuda.stream(ts):
+                    junk = torch.empty(1 << 26, device="cuda").normal_()
+                    del junk
+            actions, stats = eng.play_move(sims, auto_reset=True)
+            out.append((actions.copy(), stats.copy()))
+        res.append((out, eng.counters(), eng.export_game(3), eng.get_games().copy()))
+        eng.close()
+        ts.synchronize()                   # the caller's stream survives the engine
+    (o0, c0, e0, g0), (o1, c1, e1, g1) = res
+    for (a0, s0), (a1, s1) in zip(o0, o1):
+        assert np.array_equal(a0, a1) and np.array_equal(s0, s1)
+    for k in ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "new_nodes"):
+        assert c0[k] == c1[k], k
+    for k in e0:
+        assert np.array_equal(e0[k], e1[k]), k
+    assert np.array_equal(g0, g1)
+
+
 def test_replay_memory_filled_at_garbage_collection(gpu_lib, oracle):
     """ValueSim.remove_nodes -> store_nodes(obs_available) (agents/ValueSim.py:101-159): the observations a collection frees,
     with visit >= min_visits_to_store and not end, as 212-byte rows.  The device stores them in arbitrary order, the

@@ -47,6 +47,8 @@ def lib():
         L.b200_last_error.restype = C.c_char_p
         L.b200_engine_create.argtypes = [C.POINTER(Config), C.POINTER(P)]
         L.b200_engine_destroy.argtypes = [P]
+        L.b200_engine_set_stream.argtypes = [P, P]
+        L.b200_engine_get_stream.argtypes = [P, C.POINTER(P)]
         L.b200_load_weights.argtypes = [P, P]
         L.b200_set_games.argtypes = [P, P]
         L.b200_get_games.argtypes = [P, P]

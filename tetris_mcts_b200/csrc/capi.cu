@@ -43,7 +43,7 @@ enum { PH_SELECT = 0, PH_CONV, PH_FC, PH_BACKUP, PH_ROLLOUT, PH_SYNTH, PH_MISC, 
 struct b200_engine {
     b200_config cfg;
     Arena A;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; bool own_stream = true;   // own_stream false: the caller's stream (b200_engine_set_stream), never destroyed here
     std::vector<void *> allocs;
     uint32_t *d_default_rec = nullptr;
     float *d_stats = nullptr; int32_t *d_action = nullptr;
@@ -262,8 +262,31 @@ extern "C" int b200_engine_destroy(b200_engine *e) {
     if (e->t0) { cudaEventDestroy(e->t0); cudaEventDestroy(e->t1); }
     if (e->stream1) cudaStreamDestroy(e->stream1);
     if (e->ev_fork) { cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
+    return B200_OK;
+}
+
+// SURVEY 8(b).5 "explicit cudaStream_t": all work of the engine is issued on `cuda_stream` from now on (nullptr: a private non-blocking
+// stream again).  The engine drains its current stream first, so nothing of it is in flight on two streams at once; the captured
+// simulation step is dropped and re-captured on the new stream.  The caller keeps ownership of its stream and must keep it alive.
+extern "C" int b200_engine_set_stream(b200_engine *e, void *cuda_stream) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->stream1) CK(cudaStreamSynchronize(e->stream1));
+    drop_step_graph(e);
+    cudaStream_t ns = (cudaStream_t)cuda_stream;
+    const bool own = ns == nullptr;
+    if (own) CK(cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking));
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    e->stream = ns; e->own_stream = own;
+    return B200_OK;
+}
+
+extern "C" int b200_engine_get_stream(b200_engine *e, void **cuda_stream_out) {
+    if (!e || !cuda_stream_out) return fail(B200_ERR_BAD_ARG, "null argument");
+    *cuda_stream_out = (void *)e->stream;
     return B200_OK;
 }
 

@@ -136,6 +136,19 @@ class BatchedEngine:
     def sync(self):
         L.check(L.lib().b200_sync(self.h))
 
+    # ------------------------------------------------------------------ explicit cudaStream_t
+    def set_stream(self, stream):
+        """Issue all work of this engine on the caller's CUDA stream: a raw cudaStream_t handle (int), an object with a `cuda_stream`
+        attribute (torch.cuda.Stream), or None for a private stream again.  The caller keeps the stream alive."""
+        handle = 0 if stream is None else int(getattr(stream, "cuda_stream", stream))
+        L.check(L.lib().b200_engine_set_stream(self.h, C.c_void_p(handle)))
+
+    def get_stream(self):
+        """The cudaStream_t (int) the engine issues its work on — e.g. torch.cuda.ExternalStream(engine.get_stream())."""
+        out = C.c_void_p()
+        L.check(L.lib().b200_engine_get_stream(self.h, C.byref(out)))
+        return int(out.value or 0)
+
     def status(self):
         st = np.zeros(self.n_games, np.int32)
         L.check(L.lib().b200_status(self.h, L.ptr(st)))
