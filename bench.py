@@ -471,6 +471,17 @@ def run_b200(args, cfg):
                          "algorithmic_bytes_per_launch_pair": tree_bytes / max(sel_n, 1),
                          "kernels": "k_select_expand + k_backup", "mean_trace_len": D_mean, "ms_per_launch_pair": (sel_ms + bk_ms) / max(sel_n, 1),
                          "peak_src": peaks["src"]}
+            # The walk is a chain of RANDOM accesses, so the streaming-copy peak is not its ceiling.  scripts/probe/mem_probe.cu measured what this
+            # memory system delivers for independent random 64-byte bursts that miss L2 (profiles/mem_probe_r2.txt): 40 G bursts/s (2.6 TB/s) at
+            # 1 GB, 31-36 G/s at 8 GB — and 6-10 G/s over a 128 GB footprint (2 MB pages: TLB reach).  The kernels' own DRAM traffic (ncu, same
+            # regime) divided by 64 B and by the measured launch time is their burst rate against that ceiling.
+            if tr_s and tr_b:
+                cap = 40.0e9
+                roof_tree["random_access"] = {"ceiling_gbursts_per_s": cap / 1e9, "ceiling_src": "profiles/mem_probe_r2.txt: random 64-byte bursts, 1 GB footprint, 32-64 warps/SM",
+                                              "k_select_expand_gbursts_per_s": tr_s / 64.0 / (sel_ms / max(sel_n, 1) / 1e3) / 1e9,
+                                              "k_backup_gbursts_per_s": tr_b / 64.0 / (bk_ms / max(bk_n, 1) / 1e3) / 1e9,
+                                              "frac_select": tr_s / 64.0 / (sel_ms / max(sel_n, 1) / 1e3) / cap,
+                                              "frac_backup": tr_b / 64.0 / (bk_ms / max(bk_n, 1) / 1e3) / cap}
         if cfg["mode"] == "dist":
             conv_ms, conv_n = phases["conv"]
             flop = 19 * 7 * 32 * 16 * 2 + 16 * 4 * 32 * 512 * 2   # conv1 (19x7 pixels) + conv2 (16x4) on the 22x10 input of model_distributional.py:27
@@ -530,29 +541,53 @@ def run_b200(args, cfg):
                               "roofline.*: the same K steps on a second identical engine with an event pair around every kernel (direct launches), "
                               "instrumented_ms_per_step long",
                "counters_per_step": {k: v / steps for k, v in delta.items()}, "longest_trace_last_step": longest_trace}
-    # ---- BASELINE configs[1] alongside (Vanilla MCTS, random rollouts, no value net): short, so it rides in the same line
+    # ---- BASELINE configs[1] alongside (Vanilla MCTS, random rollouts, no value net): short, so it rides in the same line.  A Vanilla
+    # episode on this environment is short and front-loaded: the CLT policy commits to ONE line of play within ~4 moves, from then on
+    # nearly every simulation walks the kept tree to a terminal node and rolls nothing out (the CPU oracle shows the same: 40 / 28 / 13 / 2 /
+    # <0.1 playout steps per simulation on moves 0 / 1 / 2 / 3 / 4+, game over after ~37 moves).  Timing moves W.. of a running game (round 1)
+    # therefore measured almost no k_rollout work.  The line now times WHOLE EPISODES from fresh games (every phase in its natural share)
+    # and reports the rollout-heavy opening (moves 0-2, where k_rollout's integer-issue-bound playouts dominate) separately.
     if cfg["mode"] == "lp" and not args.no_secondary:
-        G2, sims2 = 4096, 300
-        e2 = BatchedEngine(G2, max_nodes=8192, mode="vanilla", eval_kind="synthetic", env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank,
-                           device=local_rank, rollout_variance=1e3, overflow_reset=True)
-        e2.set_games(PT.new_games(G2, ENV_ARGS, D.shard_seeds(BASE_SEED, G2 * world, rank, world)))
-        e2.set_gc_headroom(8192 * 5 // 32)
+        G2, sims2, ep_moves, open_moves = 4096, 300, 40, 3
+
+        def vanilla_engine():
+            e = BatchedEngine(G2, max_nodes=8192, mode="vanilla", eval_kind="synthetic", env_args=ENV_ARGS, seed=BASE_SEED + 7919 * rank,
+                              device=local_rank, rollout_variance=1e3, overflow_reset=True)
+            e.set_games(PT.new_games(G2, ENV_ARGS, D.shard_seeds(BASE_SEED, G2 * world, rank, world)))
+            e.set_gc_headroom(8192 * 5 // 32)
+            return e
+        e2 = vanilla_engine()                      # warm-up on a throwaway engine (kernels loaded, clocks up), then fresh games
         for _ in range(max(args.warmup, 3)):
             e2.play_move(sims2, auto_reset=True, want_stats=False)
+        e2.close()
+        e2 = vanilla_engine()
         k0 = e2.counters()
         D.barrier()
         torch.cuda.synchronize()
         e2.timer_start()
-        for _ in range(max(args.steps, 1)):
+        for _ in range(open_moves):
             e2.play_move(sims2, auto_reset=True, want_stats=False)
-        ms2 = D.max_over_ranks(e2.timer_stop(), dev)
+        ms_open = D.max_over_ranks(e2.timer_stop(), dev)
+        ko = e2.counters()
+        e2.timer_start()
+        for _ in range(ep_moves - open_moves):
+            e2.play_move(sims2, auto_reset=True, want_stats=False)
+        ms2 = ms_open + D.max_over_ranks(e2.timer_stop(), dev)
         k1 = e2.counters()
         d2 = D.sum_over_ranks({k: k1[k] - k0[k] for k in k1 if k != "max_trace_len"}, dev)
+        do = D.sum_over_ranks({k: ko[k] - k0[k] for k in ko if k != "max_trace_len"}, dev)
         e2.close()
         if out is not None:
-            out["also_configs1_vanilla"] = {"workload": "BASELINE configs[1]: Vanilla MCTS, %d games/GPU, %d sims/move" % (G2, sims2), "value": d2["sims"] / (ms2 / 1e3),
-                                            "unit": "sims/s", "ms_per_step": ms2 / max(args.steps, 1), "rollout_steps_per_sim": d2["rollout_steps"] / max(d2["sims"], 1),
-                                            "mean_trace_len": d2["trace_levels"] / max(d2["sims"], 1)}
+            out["also_configs1_vanilla"] = {"workload": "BASELINE configs[1]: Vanilla MCTS, %d games/GPU, %d sims/move, whole episodes from fresh games (%d moves)"
+                                                        % (G2, sims2, ep_moves),
+                                            "value": d2["sims"] / (ms2 / 1e3), "unit": "sims/s", "ms_per_step": ms2 / ep_moves, "moves_timed": ep_moves,
+                                            "rollout_steps_per_sim": d2["rollout_steps"] / max(d2["sims"], 1),
+                                            "mean_trace_len": d2["trace_levels"] / max(d2["sims"], 1), "games_finished": d2["games_finished"],
+                                            "opening_moves_0_2": {"value": do["sims"] / (ms_open / 1e3), "unit": "sims/s", "ms_per_step": ms_open / open_moves,
+                                                                  "rollout_steps_per_sim": do["rollout_steps"] / max(do["sims"], 1),
+                                                                  "board_steps_per_sec": (do["rollout_steps"] + 7 * do["expansions"]) / (ms_open / 1e3),
+                                                                  "mean_trace_len": do["trace_levels"] / max(do["sims"], 1),
+                                                                  "bound": "k_rollout: integer issue (in-register playouts, 0 HBM bytes), SURVEY 8d"}}
     # ---- BASELINE configs[3] proper (65536 games over 8 GPUs = 8192 per GPU) and configs[4] (distributional head, 16384 games over 8 GPUs =
     # 2048 per GPU, 1500 sims/move): the per-GPU shares, a few moves each, so that the default line carries every BASELINE configuration
     if cfg["mode"] == "lp" and not args.no_secondary and cfg["games_per_gpu"] == 16384:
