@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 
 /* ------------------------------------------------------------------ special.h:26-33 */
 double mo_norm_quantile(double t) {
@@ -241,6 +242,13 @@ struct mo_agent {
     /* overflow_reset (the engine's policy beyond the reference, include/b200_tetris_mcts.h; used by bench.py): see drop_tree() */
     int reroot_pending, reset_hit, in_expand; long resets;
     uint32_t live[TO_RECORD_WORDS];       /* the game last handed to update_root (the object play.py owns) */
+    /* CPU model of the engine's PATH CACHE (search_dev.cuh, B200_PATH_CACHE): per level of the last trace the node, its de-duplicated
+     * children and THEIR statistics as the engine keeps them next to the trace.  The model applies the engine's coherence rules (natural-slot
+     * update at backup, invalidation on a transposition inside the path, on collection, re-rooting and tree drop) and CHECKS at every
+     * selection that every cached value still equals the arena's: pc_errors must stay 0.  Diagnostic only (mo_agent_pc_*). */
+    int pc_on, pc_len; long pc_errors, pc_irregular, pc_shared, pc_levels, pc_sims, pc_full_walks;
+    int32_t pc_node[512]; int pc_k[512]; int32_t pc_cn[512][MO_NA], pc_co[512][MO_NA];
+    int32_t pc_visit[512][MO_NA]; float pc_value[512][MO_NA], pc_variance[512][MO_NA];
 };
 
 static uint64_t hash_words(const uint32_t *w, int n) {
@@ -343,10 +351,12 @@ static void drop_tree(mo_agent *a) {
     memset(a->ntab.slot, 0, sizeof(int32_t) * (size_t)a->ntab.cap);
     memset(a->otab.slot, 0, sizeof(int32_t) * (size_t)a->otab.cap);
     a->reroot_pending = 1; a->reset_hit = 1; a->resets += 1;
+    a->pc_len = 0;
 }
 
 static void remove_nodes_ref(mo_agent *a);
 static void remove_nodes(mo_agent *a) {
+    a->pc_len = 0;                  /* path cache: a collection invalidates it (k_gc) */
     remove_nodes_ref(a);
     if (a->cfg.overflow_reset && a->n_avail < a->M / 8) drop_tree(a);
 }
@@ -466,6 +476,7 @@ void mo_agent_update_root(mo_agent *a, const uint32_t *rec20) {
     to_game g;
     to_unpack(&g, rec20);
     memcpy(a->live, rec20, sizeof(a->live));
+    a->pc_len = 0;                  /* path cache: a new root invalidates it (k_update_root) */
     a->reset_hit = 0;
     a->root = new_node(a, &g);      /* a tree dropped earlier (or inside this call) is simply re-rooted here */
     a->reroot_pending = 0;
@@ -487,6 +498,68 @@ static void evaluate(mo_agent *a, const int32_t *obs, int k, float *v, float *va
     }
     if (a->cfg.eval_mode == MO_EVAL_NET) vo_forward(a->cfg.weights, states, k, v, var);
     else a->cfg.eval_cb(a->cfg.eval_ctx, states, k, v, var);
+}
+
+/* ---- path-cache model (see struct mo_agent) */
+static void pc_fill(mo_agent *a, int L, int node) {
+    a->pc_node[L] = node;
+    int k = mo_unique_child_obs(node, a->child, a->score, a->n2o, a->pc_cn[L], a->pc_co[L]);
+    a->pc_k[L] = k;
+    for (int j = 0; j < k; ++j) {
+        int o = a->pc_co[L][j];
+        a->pc_visit[L][j] = a->ovisit[o]; a->pc_value[L][j] = a->ovalue[o]; a->pc_variance[L][j] = a->ovariance[o];
+    }
+}
+static void pc_on_select(mo_agent *a, const int32_t *trace, int D) {
+    if (!a->pc_on) return;
+    int L = 0;
+    while (L < a->pc_len && L < D && a->pc_node[L] == trace[L]) {
+        int32_t cn[MO_NA], co[MO_NA];
+        int k = mo_unique_child_obs(trace[L], a->child, a->score, a->n2o, cn, co);
+        int bad = k != a->pc_k[L];
+        for (int j = 0; j < k && !bad; ++j) {
+            int o = co[j];
+            bad = cn[j] != a->pc_cn[L][j] || o != a->pc_co[L][j] || a->pc_visit[L][j] != a->ovisit[o] ||
+                  memcmp(&a->pc_value[L][j], &a->ovalue[o], 4) != 0 || memcmp(&a->pc_variance[L][j], &a->ovariance[o], 4) != 0;
+        }
+        if (bad) {
+            if (a->pc_errors < 5) fprintf(stderr, "path-cache model: stale entry at level %d of %d (node %d)\n", L, D, trace[L]);
+            a->pc_errors += 1;
+        }
+        ++L;
+    }
+    a->pc_shared += L; a->pc_levels += D; a->pc_sims += 1;
+    if (L == 0) a->pc_full_walks += 1;
+    for (; L < D; ++L) pc_fill(a, L, trace[L]);
+    a->pc_len = D;
+}
+static void pc_on_backup(mo_agent *a, const int32_t *trace, int D, int expanded) {
+    if (!a->pc_on || a->pc_len == 0) return;             /* invalidated since the selection (collection / tree drop inside the expansion) */
+    int newlen = expanded ? D - 1 : D;                   /* the expanded leaf's entry says "no children": stale */
+    /* Stale copies after this backup, by level: (a) an observation twice on the trace (i < j): the backup runs leaf -> root, so the natural copy
+     * of the deeper occurrence (level j-1) holds an intermediate value; (b) a cached child observation that is some trace node's own without
+     * being that level's natural copy.  Everything above the shallowest stale level stays valid: the cache is truncated there. */
+    int stale = newlen;
+    for (int i = 0; i < D; ++i)
+        for (int j = i + 1; j < D; ++j) if (a->n2o[trace[i]] == a->n2o[trace[j]] && j - 1 < stale) stale = j - 1;
+    for (int L = 0; L < stale; ++L)
+        for (int j = 0; j < a->pc_k[L]; ++j) {
+            const int natural = L + 1 < D && a->pc_cn[L][j] == trace[L + 1];
+            if (natural) continue;
+            for (int i = 0; i < D; ++i) if (a->pc_co[L][j] == a->n2o[trace[i]] && L < stale) stale = L;
+        }
+    if (stale < newlen) { a->pc_irregular += 1; newlen = stale; }
+    for (int L = 0; L + 1 < D && L < newlen; ++L)        /* natural copies take the values the backup just wrote */
+        for (int j = 0; j < a->pc_k[L]; ++j)
+            if (a->pc_cn[L][j] == trace[L + 1]) {
+                int o = a->pc_co[L][j];
+                a->pc_visit[L][j] = a->ovisit[o]; a->pc_value[L][j] = a->ovalue[o]; a->pc_variance[L][j] = a->ovariance[o];
+            }
+    a->pc_len = newlen;
+}
+void mo_agent_pc_enable(mo_agent *a, int on) { a->pc_on = on; a->pc_len = 0; }
+void mo_agent_pc_stats(const mo_agent *a, long *out7) {
+    out7[0] = a->pc_errors; out7[1] = a->pc_irregular; out7[2] = a->pc_shared; out7[3] = a->pc_levels; out7[4] = a->pc_sims; out7[5] = a->pc_full_walks; out7[6] = a->pc_len;
 }
 
 int mo_agent_mcts(mo_agent *a, int sims) {
@@ -535,6 +608,7 @@ int mo_agent_mcts(mo_agent *a, int sims) {
         if (D < 0) return -2;
         a->last_D = D;
         a->counters[0] += 1; a->counters[4] += D;
+        if (cf->mode == MO_MODE_LP) pc_on_select(a, a->last_trace, D);
         int leaf = a->last_trace[D - 1];
         to_game lg;
         to_unpack(&lg, a->game + (size_t)leaf * TO_RECORD_WORDS);
@@ -578,6 +652,7 @@ int mo_agent_mcts(mo_agent *a, int sims) {
                 }
             }
             if (cf->lp_end_from_obs) for (int i = 0; i < k; ++i) a->end_scratch[c_nodes[i]] = 0;
+            pc_on_backup(a, a->last_trace, D, !lg.end);
         } else if (cf->mode == MO_MODE_SINGLE) {          /* ValueSim.py:76-94 */
             double _value = (double)lg.score, _variance = 0;
             if (!lg.end) {

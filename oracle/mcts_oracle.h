@@ -80,6 +80,10 @@ void mo_agent_export(const mo_agent *a, int32_t *child, float *score, int32_t *e
                      int32_t *visit, float *value, float *variance, uint8_t *obs_end, uint32_t *game_recs,
                      uint32_t *obs_keys);
 int mo_agent_last_trace(const mo_agent *a, int32_t *trace, int max);
+/* CPU model of the engine's path cache (diagnostic): enable, then out7 = {stale entries found (must be 0), invalidations by a transposition
+ * inside the path, levels served from the cache, levels walked, simulations, simulations that found no cache, current valid length} */
+void mo_agent_pc_enable(mo_agent *a, int on);
+void mo_agent_pc_stats(const mo_agent *a, long *out7);
 void mo_agent_export_dist(const mo_agent *a, float *node_stats, float *node_dist);   /* MO_MODE_DIST: f32[M][5], f32[M][bins] */
 void mo_synthetic_dist(const uint32_t *obskey12, int bins, float *dist);             /* test evaluator shared with the device */
 #ifdef __cplusplus

@@ -322,6 +322,16 @@ class Agent:
         lib().mo_agent_export_dist(self.h, _p(ns), _p(nd))
         return ns, nd
 
+    def pc_enable(self, on=True):                                     # CPU model of the engine's path cache (diagnostic)
+        lib().mo_agent_pc_enable.argtypes = [C.c_void_p, C.c_int]
+        lib().mo_agent_pc_enable(self.h, int(on))
+
+    def pc_stats(self):
+        out = np.zeros(7, np.int64)
+        lib().mo_agent_pc_stats.argtypes = [C.c_void_p, C.c_void_p]
+        lib().mo_agent_pc_stats(self.h, _p(out))
+        return dict(zip(("errors", "irregular", "shared", "levels", "sims", "full_walks", "len"), out.tolist()))
+
     def last_trace(self):
         tr = np.zeros(512, np.int32)
         D = lib().mo_agent_last_trace(self.h, _p(tr), 512)
