@@ -96,6 +96,13 @@ int b200_set_gc_headroom(b200_engine *e, int min_free);
  * B200_EVAL_NET_TC; ignored otherwise).  0 (default) = one lane. */
 int b200_set_deep_lane(b200_engine *e, int max_games);
 
+/* --- memory traffic only (no reference counterpart, no effect on any result): the PATH CACHE.  Consecutive simulations of a game walk almost
+ * the same root-to-leaf path (select_trace_obs, core.h:167-224, restarts at the root every time); with the cache on, a walk leaves next to its
+ * trace the row fields and the children's statistics of every level, the backup (core.h:226-381) refreshes the copies it changes and drops
+ * the ones a transposition made stale, and the next walk serves every level that is still valid from one sequential line instead of two
+ * dependent random accesses.  B200_MODE_LP with max_nodes <= 65536; 192 bytes x trace_max per game.  0 (default) = off. */
+int b200_set_path_cache(b200_engine *e, int on);
+
 /* --- TreeAgent.mcts (agents/ValueSimLP.py:13, ValueSim.py:52, Vanilla.py:17): `sims` simulations on every game */
 int b200_run_sims(b200_engine *e, int sims);
 
@@ -116,7 +123,8 @@ int b200_finished_games(b200_engine *e, int32_t *out4, int cap, int32_t *count_o
 int b200_status(b200_engine *e, int32_t *status);            /* per-game 0 ok / B200_ERR_ARENA_FULL / B200_ERR_TRACE_FULL */
 int b200_counters(b200_engine *e, uint64_t *out16);          /* 0 sims 1 expansions 2 eval requests 3 gcs 4 trace levels
                                                                 5 rollout steps 6 new nodes 7 tree resets 8 games finished 9 score sum 10 lines sum
-                                                                12 longest trace of the last b200_run_sims (not cumulative) */
+                                                                12 longest trace of the last b200_run_sims (not cumulative)
+                                                                13 trace levels served by the path cache (of counter 4) */
 int b200_sync(b200_engine *e);
 int b200_timer_start(b200_engine *e);                        /* CUDA-event stopwatch on the engine's stream (sync, then record) */
 int b200_timer_stop(b200_engine *e, float *ms);              /* record, wait, elapsed milliseconds since b200_timer_start */

@@ -389,6 +389,65 @@ def test_engine_on_the_callers_stream(gpu_lib):
     assert np.array_equal(g0, g1)
 
 
+def test_path_cache_is_exact_against_the_oracle(gpu_lib, oracle):
+    """b200_set_path_cache: the walk serves the levels it shares with the game's previous trace from the entries kept next to the trace
+    (children's statistics refreshed by k_backup, truncated where a transposition made a copy stale, dropped by collections / re-rooting /
+    tree drops).  Same oracle comparison as without it: actions, stats, arenas; with collections in the middle of expansions, explicit
+    collections, dropped trees and games that end."""
+    c = run_pair(oracle, "lp", n=24, M=4096, sims=60, moves=12, engine_kw=dict(path_cache=True))
+    assert c["gcs"] == 0
+    c = run_pair(oracle, "lp", n=12, M=1500, sims=12, moves=100, engine_kw=dict(path_cache=True))
+    assert c["gcs"] >= 12
+    c = run_pair(oracle, "lp", n=8, M=1500, sims=12, moves=140, engine_kw=dict(path_cache=True))
+    assert c["games_finished"] >= 1
+    run_pair(oracle, "lp", n=8, M=2048, sims=40, moves=8, engine_kw=dict(lp_end_from_obs=True, lp_var_gamma2=False, path_cache=True),
+             agent_kw=dict(lp_end_from_obs=1, lp_var_gamma2=0))
+    c = run_pair(oracle, "lp", n=16, M=65536, sims=300, moves=5, engine_kw=dict(path_cache=True), check_arena=False)   # the largest arena the cache serves, deep traces
+
+
+def test_path_cache_on_equals_off_with_the_network_and_dropped_trees(gpu_lib):
+    """Cache on against cache off on the production path (graph replay, net_tc, head-room collections, overflow_reset): every action, statistic,
+    counter, exported arena and live game equal; and the cache must actually serve levels (it is not silently off)."""
+    from tetris_mcts_b200 import pyTetris as PT
+    from tetris_mcts_b200.engine import BatchedEngine
+    from tetris_mcts_b200.model.model_vv import init_weights
+    n, M, sims, moves = 256, 2048, 120, 10
+    recs = PT.new_games(n, ARGS, np.arange(31, 31 + n, dtype=np.uint32))
+    w = init_weights(1)
+    res = []
+    for pc in (False, True):
+        eng = BatchedEngine(n, max_nodes=M, mode="lp", eval_kind="net_tc", weights=w, seed=5, overflow_reset=True, path_cache=pc)
+        eng.set_gc_headroom(M * 5 // 32)
+        eng.set_games(recs)
+        out = []
+        for mv in range(moves):
+            actions, stats = eng.play_move(sims, auto_reset=True)
+            out.append((actions.copy(), stats.copy()))
+        c = eng.counters()
+        res.append((out, c, [eng.export_game(g) for g in (0, n // 2, n - 1)], eng.get_games().copy()))
+        eng.close()
+    (o0, c0, e0, g0), (o1, c1, e1, g1) = res
+    assert c0["gcs"] > 0 and c0["tree_resets"] > 0
+    assert c0["cached_levels"] == 0 and c1["cached_levels"] > 0.6 * c1["trace_levels"], (c1["cached_levels"], c1["trace_levels"])
+    for (a0, s0), (a1, s1) in zip(o0, o1):
+        assert np.array_equal(a0, a1) and np.array_equal(s0, s1)
+    for k in ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "new_nodes", "tree_resets"):
+        assert c0[k] == c1[k], k
+    for x0, x1 in zip(e0, e1):
+        for k in x0:
+            assert np.array_equal(x0[k], x1[k]), k
+    assert np.array_equal(g0, g1)
+
+
+def test_path_cache_refused_where_it_does_not_apply(gpu_lib):
+    from tetris_mcts_b200.engine import BatchedEngine
+    for kw in (dict(mode="vanilla", max_nodes=1024, eval_kind="synthetic"), dict(mode="lp", max_nodes=65540, eval_kind="synthetic")):
+        eng = BatchedEngine(2, **kw)
+        with pytest.raises(gpu_lib.B200Error):
+            eng.set_path_cache(True)
+        eng.close()
+
+
 def test_replay_memory_filled_at_garbage_collection(gpu_lib, oracle):
     """ValueSim.remove_nodes -> store_nodes(obs_available) (agents/ValueSim.py:101-159): the observations a collection frees,
     with visit >= min_visits_to_store and not end, as 212-byte rows.  The device stores them in arbitrary order, the

@@ -62,6 +62,7 @@ def lib():
         L.b200_remove_nodes.argtypes = [P, C.c_int]
         L.b200_set_gc_headroom.argtypes = [P, C.c_int]
         L.b200_set_deep_lane.argtypes = [P, C.c_int]
+        L.b200_set_path_cache.argtypes = [P, C.c_int]
         L.b200_counters.argtypes = [P, P]
         L.b200_sync.argtypes = [P]
         L.b200_set_timing.argtypes = [P, C.c_int]

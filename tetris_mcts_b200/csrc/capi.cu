@@ -68,6 +68,7 @@ struct b200_engine {
     ReplayPolicy rp; uint8_t *d_rp_tmp = nullptr, *d_rp_keep = nullptr; float *d_rp_vis = nullptr; int32_t *d_rp_kept = nullptr; int replay_alloc = 0;
     // one simulation step captured as a CUDA graph (replayed when phase timing is off: ~7 launches + 1 memset per step, 500 steps/move)
     int gc_headroom = 0;           // b200_set_gc_headroom: collect between moves every game with fewer free slots than this
+    uint8_t *d_pc = nullptr; int32_t *d_pc_len = nullptr;   // path cache (b200_set_path_cache): allocated at the first switch-on, A.pc == nullptr while off
     // deep lane (b200_set_deep_lane): the games with the longest traces select / collect / resume on a second stream (kernels.cuh: k_classify)
     int deep_cap = 0; cudaStream_t stream1 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int32_t *d_glist0 = nullptr, *d_glist1 = nullptr, *d_nlist = nullptr, *d_nreq_deep = nullptr, *d_gc_list_deep = nullptr; uint2 *d_req_deep = nullptr;
@@ -83,6 +84,10 @@ static void drop_step_graph(b200_engine *e) {
 }
 
 constexpr int DEEP_GC_BLOCKS = 8;
+
+// k_backup's per-warp bitmap of the trace's observations (path cache on): max_nodes bits, four warps per CTA
+static inline int backup_bitmap_words(const Arena &A) { return A.pc ? (A.M + 31) / 32 : 0; }
+static inline size_t backup_smem(const Arena &A) { return (size_t)4 * backup_bitmap_words(A) * sizeof(unsigned); }
 
 // temporary device buffers of the standalone entry points: freed on every return path
 struct Scratch {
@@ -513,6 +518,26 @@ extern "C" int b200_set_gc_headroom(b200_engine *e, int min_free) {
     return B200_OK;
 }
 
+// Path cache (search_dev.cuh "path cache"): scheduling/memory-traffic only, no effect on any result.  LP mode, max_nodes <= 65536.
+extern "C" int b200_set_path_cache(b200_engine *e, int on) {
+    if (!e) return fail(B200_ERR_BAD_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    if (on) {
+        if (e->A.mode != MODE_LP) return fail(B200_ERR_BAD_ARG, "the path cache serves B200_MODE_LP (its coherence rules rest on the LP backup)");
+        if (e->A.M > PC_MAX_NODES) return fail(B200_ERR_BAD_ARG, "the path cache needs max_nodes <= 65536 (k_backup's bitmap of the trace's observations)");
+        if (B200_FUSED_BACKUP) return fail(B200_ERR_BAD_ARG, "the path cache needs the separate k_backup launch (B200_FUSED_BACKUP=0)");
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    drop_step_graph(e);
+    if (on && !e->d_pc) {
+        if (dalloc(e, &e->d_pc, (size_t)e->A.G * e->A.trace_max * PC_STRIDE, false) || dalloc(e, &e->d_pc_len, (size_t)e->A.G)) return B200_ERR_CUDA;
+    }
+    if (on) CK(cudaMemsetAsync(e->d_pc_len, 0, (size_t)e->A.G * sizeof(int32_t), e->stream));   // nothing is valid until a walk has left its entries
+    e->A.pc = on ? e->d_pc : nullptr;
+    e->A.pc_len = on ? e->d_pc_len : nullptr;
+    return B200_OK;
+}
+
 extern "C" int b200_set_deep_lane(b200_engine *e, int max_games) {
     if (!e || max_games < 0 || max_games > e->A.G) return fail(B200_ERR_BAD_ARG, "0 <= max_games <= n_games");
     CK(cudaSetDevice(e->cfg.device));
@@ -636,7 +661,7 @@ static int enqueue_step_lanes(b200_engine *e) {
     }
     {
         PhaseTimer t(e, PH_BACKUP);
-        k_backup<<<(G + 3) / 4, 128, 0, s0>>>(A);
+        k_backup<<<(G + 3) / 4, 128, backup_smem(A), s0>>>(A, backup_bitmap_words(A));
     }
     CK(cudaGetLastError());
     return B200_OK;
@@ -683,7 +708,7 @@ static int enqueue_step(b200_engine *e) {
     if (A.mode == MODE_DIST || !B200_FUSED_BACKUP) {   // otherwise the next k_select_expand (or run_sims' final k_backup) folds this step's traces
         PhaseTimer t(e, PH_BACKUP);
         if (A.mode == MODE_DIST) k_dist_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
-        else k_backup<<<(G + 3) / 4, 128, 0, e->stream>>>(A);
+        else k_backup<<<(G + 3) / 4, 128, backup_smem(A), e->stream>>>(A, backup_bitmap_words(A));
     }
     return B200_OK;
 }
@@ -728,7 +753,7 @@ extern "C" int b200_run_sims(b200_engine *e, int sims) {
     }
     if (B200_FUSED_BACKUP && A.mode != MODE_DIST && sims > 0) {   // the last simulation's traces (the others were folded by the next step's k_select_expand)
         PhaseTimer t(e, PH_BACKUP);
-        k_backup<<<(A.G + 3) / 4, 128, 0, e->stream>>>(A);
+        k_backup<<<(A.G + 3) / 4, 128, backup_smem(A), e->stream>>>(A, backup_bitmap_words(A));
     }
     CK(cudaGetLastError());
     return B200_OK;

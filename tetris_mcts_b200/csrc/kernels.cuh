@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(TPB) k_update_root(Arena A, int auto_reset, un
     Grp gp;
     int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3);
     if (g >= A.G) return;
+    if (A.pc && gp.lane == 0) A.pc_len[g] = 0;     // path cache: the path starts at another node now
     int status = A.status[g];
     if (only_pending) {
         if (A.pending[g] != PEND_ROOT) return;
@@ -174,10 +175,10 @@ __device__ __forceinline__ Uniq finish_expansion(const Arena &A, const Grp &gp, 
 }
 
 // ---------------------------------------------------------------- select + expand (ValueSimLP.py:45-57 etc.)
-template <int NL> __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask, int lane);   // defined with k_backup below
+template <int NL> __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask, int lane, unsigned *bitmap = nullptr);   // defined with k_backup below
 
 // What one group hands to the CTA-level epilogue of k_select_expand: its evaluation request (per lane) and its counters.
-struct GroupOut { bool ask; int my_o; int sims, D, expanded, new_nodes; };
+struct GroupOut { bool ask; int my_o; int sims, D, expanded, new_nodes, cached; };
 
 // The whole warp calls this together (four games per warp): the walk runs in lockstep over the four groups (select_trace, GrpW);
 // everything around it is per group.  `g` >= A.G marks a group without a game.
@@ -191,9 +192,11 @@ __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &g
     if (valid && status == ST_OK && A.mode != MODE_DIST) backup_game<8>(A, g, gp.mask, gp.lane);
     if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[5], (unsigned long long)(_n - ptick)); ptick = _n; }
 #endif
-    if (valid && (status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) reset_tree(A, gp, g, status);
+    bool tree_reset = false;
+    if (valid && (status == ST_ARENA_FULL || status == ST_RESET_DONE) && A.overflow_reset) { reset_tree(A, gp, g, status); tree_reset = true; }
     const bool active = valid && status == ST_OK;
     ArenaAcc acc(A, valid ? g : 0, s_z);
+    if (A.pc && active && !tree_reset && A.mode == MODE_LP) acc.pc_len = A.pc_len[g];   // valid entries of this game's path cache (0 after anything but a backup)
     int D = 0;
 #define TREE_PROF(i) do { if (do_prof) { const long long _n = clock64(); atomicAdd(&A.prof[i], (unsigned long long)(_n - ptick)); ptick = _n; } } while (0)
 #if B200_PV_PREFETCH
@@ -209,7 +212,7 @@ __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &g
         const int2 *tm = A.trace_meta + (size_t)g * A.trace_max;
         const char *stat_lo = reinterpret_cast<const char *>(acc.statg), *stat_hi = stat_lo + (size_t)A.M * sizeof(int4) - 1;
         for (int d = gp.lane; d < pd; d += 8) {
-            const int idx = tr[d], o = tm[d].x;
+            const int idx = tr[d], o = tm[d].x & (int)TMETA_OBS_MASK;
             const char *r = reinterpret_cast<const char *>(acc.rowg + (size_t)idx * ROW_WORDS);
             prefetch_l2(r + 32);
 #if B200_PV_PREFETCH >= 2
@@ -233,10 +236,10 @@ __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &g
         if (active) leaf = dist_select_group(A, gp, g, A.root[g], D, status);
     } else {
         __syncwarp();
-        leaf = select_trace(acc, active, active ? A.root[g] : 0, A.low, A.trace_max, D, status);
+        leaf = select_trace(acc, active, active ? A.root[g] : 0, A.low, A.trace_max, D, status, &out.cached);
     }
     if (!active) return;
-    if (status != ST_OK) { if (gp.lane == 0) A.status[g] = status; return; }
+    if (status != ST_OK) { if (gp.lane == 0) { A.status[g] = status; if (A.pc) A.pc_len[g] = 0; } return; }
     TREE_PROF(0);
     uint32_t w[REC_WORDS];
     load_rec(A.rec + node_at(A, g, leaf) * REC_WORDS, w);
@@ -267,6 +270,9 @@ __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &g
     if (gp.lane == 0) {
         A.trace_len[g] = D; A.leaf_kind[g] = kind;
         if (status != ST_OK) A.status[g] = status;
+        // path cache: entries 0..D-1 describe this trace; the entry of a leaf that was just expanded says "no children" and is dropped;
+        // k_backup refreshes the statistics the backup changes and truncates further if a copy went stale (search_dev.cuh "path cache")
+        if (A.pc) A.pc_len[g] = (A.mode == MODE_LP && status == ST_OK && kind != LEAF_SUSPENDED) ? (kind == LEAF_EXPANDED ? D - 1 : D) : 0;
     }
     out.sims = 1; out.D = D;
     TREE_PROF(3);
@@ -280,10 +286,10 @@ __device__ __forceinline__ void select_expand_group(const Arena &A, const Grp &g
 __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
     __shared__ float s_z[ZS_N];
     __shared__ __align__(16) uint32_t s_stage[GROUPS_PER_BLOCK * STAGE_GROUP_WORDS];
-    __shared__ unsigned s_cnt[5];          // sims, trace levels, expansions, new nodes, longest trace of this CTA
+    __shared__ unsigned s_cnt[6];          // sims, trace levels, expansions, new nodes, longest trace of this CTA, levels served by the path cache
     __shared__ int s_wreq[TPB / 32 + 1];   // requests per warp, then the CTA's base in the request list
     for (int i = threadIdx.x; i < ZS_N; i += TPB) s_z[i] = A.ztable[i];
-    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0u;
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
     Grp gp;
 #if B200_GAMES_PER_WARP < 4
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
 #else
     const int g = lane_game(A, blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 3));
 #endif
-    GroupOut out{false, 0, 0, 0, 0, 0};
+    GroupOut out{false, 0, 0, 0, 0, 0, 0};
     select_expand_group(A, gp, g, s_z, s_stage + (threadIdx.x >> 3) * STAGE_GROUP_WORDS, out);
     __syncwarp();
     const unsigned askmask = __ballot_sync(0xffffffffu, out.ask);
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
         atomicAdd(&s_cnt[0], 1u); atomicAdd(&s_cnt[1], (unsigned)out.D); atomicMax(&s_cnt[4], (unsigned)out.D);
         if (out.expanded) atomicAdd(&s_cnt[2], 1u);
         if (out.new_nodes) atomicAdd(&s_cnt[3], (unsigned)out.new_nodes);
+        if (out.cached) atomicAdd(&s_cnt[5], (unsigned)out.cached);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(TPB, 8) k_select_expand(Arena A) {
         if (s_cnt[0]) { atomicAdd(&A.counters[0], (unsigned long long)s_cnt[0]); atomicAdd(&A.counters[4], (unsigned long long)s_cnt[1]); }
         if (s_cnt[2]) atomicAdd(&A.counters[1], (unsigned long long)s_cnt[2]);
         if (s_cnt[3]) atomicAdd(&A.counters[6], (unsigned long long)s_cnt[3]);
+        if (s_cnt[5]) atomicAdd(&A.counters[13], (unsigned long long)s_cnt[5]);
         if (s_cnt[4] > (unsigned)A.counters[12]) atomicMax(&A.counters[12], (unsigned long long)s_cnt[4]);   // longest trace since b200_run_sims began
     }
     __syncthreads();
@@ -385,6 +393,7 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc(Arena A) {
     const int M = A.M, H = A.H;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int g = A.gc_list[item];
+        if (A.pc && t == 0) A.pc_len[g] = 0;       // path cache: a collection (or the tree drop that may follow it) invalidates it
         uint8_t *nmark = A.nmark + (size_t)blockIdx.x * M, *omark = A.omark + (size_t)blockIdx.x * M;   // scratch of this CTA (a pool of gridDim.x sets,
         int32_t *q0 = A.gc_queue + (size_t)blockIdx.x * 2 * M, *q1 = q0 + M;                            // not one per game: 10 bytes per slot saved)
         int32_t *rowb = A.row + (size_t)g * M * ROW_WORDS;
@@ -665,18 +674,22 @@ __global__ void k_rollout(Arena A) {
 //   NL = 32  k_backup, one warp per game: after the LAST simulation of b200_run_sims (and in distributional mode's twin).
 // leaf_kind[g] is set to LEAF_DONE once the trace is folded, which makes the two callers idempotent.
 template <int NL>
-__device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask, int lane) {
+__device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask, int lane, unsigned *bitmap) {
     ArenaAcc acc(A, g);
     const int D = A.trace_len[g];
     const int kind = A.leaf_kind[g];
     if (kind == LEAF_SUSPENDED || kind == LEAF_DONE || D <= 0) return;
+    // path cache (search_dev.cuh): pcl = the entries the walk left valid (0: off, or invalidated by a collection since); `stale` = this lane's
+    // shallowest level whose entry holds an out-of-date copy after this backup (min-reduced at the end)
+    const int pcl = (NL == 32 && bitmap && acc.pcg) ? A.pc_len[g] : 0;
+    int stale = pcl;
     // ---- early loads: trace entries of the first window, then their node fields + the leaf's child row + evaluator outputs
     const int n0 = D < NL ? D : NL;
     int tidx = 0;
     if (lane == 0) tidx = acc.get_trace(D - 1);
     const bool lp_children = A.mode == MODE_LP && kind == LEAF_EXPANDED;
-    int wo = -1 - lane; float wsc = 0.f;                      // this lane's level of the current window: observation, score
-    if (lane < n0) acc.get_trace_meta(D - 1 - lane, wo, wsc); // recorded by the walk: one coalesced read instead of a gather per level
+    int wo = -1 - lane; float wsc = 0.f;                      // this lane's level of the current window: observation (| the walk's pick << 28), score
+    if (lane < n0) acc.get_trace_meta_raw(D - 1 - lane, wo, wsc); // recorded by the walk: one coalesced read instead of a gather per level
     const int leaf = __shfl_sync(mask, tidx, 0, NL);
     int c = 0, o = 0; float s = 0.f;
     float2 ev = make_float2(0.f, 0.f);
@@ -730,7 +743,8 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
     // ---- core.h:244-259 along the trace, NL levels per round
     for (int top = D - 1; top >= 0; top -= NL) {
         const int n = top + 1 < NL ? top + 1 : NL;      // levels top, top-1, ..., top-n+1 -> lanes 0..n-1
-        const int o = wo; const float sc = wsc;
+        const int oraw = wo;
+        const int o = oraw < 0 ? oraw : (oraw & (int)TMETA_OBS_MASK); const float sc = wsc;
         int4 st = make_int4(0, 0, 0, 0);
         const bool dup = __popc(__match_any_sync(mask, o)) > 1;
         const bool any_dup = __any_sync(mask, dup);
@@ -738,7 +752,21 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
         {   // the next window's node fields, in flight while this window is folded
             const int ntop = top - NL;
             wo = -1 - lane; wsc = 0.f;
-            if (ntop >= 0 && lane <= ntop) acc.get_trace_meta(ntop - lane, wo, wsc);
+            if (ntop >= 0 && lane <= ntop) acc.get_trace_meta_raw(ntop - lane, wo, wsc);
+        }
+        // path cache: the entry of level i-1 holds a copy of this level's statistics in the slot the walk picked there (bits 28-30 of
+        // level i-1's trace_meta word: the next lane's, or lane 0 of the next window)
+        int pick_up = 0;
+        if (NL == 32 && pcl > 0) {
+            const int from_next = __shfl_sync(mask, wo, 0, NL), from_lane = __shfl_down_sync(mask, oraw, 1, NL);
+            const int praw = lane == NL - 1 ? from_next : from_lane;
+            pick_up = (praw >> 28) & 7;
+            if (lane < n) {                             // bitmap of the trace's own observations; a bit already set by a DEEPER window = the same observation
+                const unsigned bit = 1u << (o & 31);    // twice on the trace: the deeper natural copy holds an intermediate value
+                const unsigned old = atomicOr(&bitmap[o >> 5], bit);
+                if ((old & bit) && top - lane < stale) stale = top - lane;
+            }
+            if (any_dup && top - n < stale) stale = top - n < 0 ? 0 : top - n;   // the same inside this window: no natural copies are written for it
         }
         if (any_dup) {                                  // shared observation inside the window: scalar walk for this window
             if (lane == 0) {
@@ -763,8 +791,41 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
             if (lane == j) vin = v;
             v = __dadd_rn(__dmul_rn(A.gamma, __dsub_rn(v, scj)), scj);
         }
-        if (lane < n) { welford_level(st, vin, var, sc, A.gamma); acc.set_stat(o, st, top - lane); }
+        if (lane < n) {
+            welford_level(st, vin, var, sc, A.gamma); acc.set_stat(o, st, top - lane);
+            const int up = top - lane - 1;              // the natural copy, one level up
+            if (NL == 32 && pcl > 0 && up >= 0 && up < pcl) {
+                uint8_t *e = acc.pcg + (size_t)up * PC_STRIDE;
+                *reinterpret_cast<int2 *>(e + pick_up * 16 + 8) = make_int2(st.x, st.y);
+                *reinterpret_cast<int *>(e + PC_OFF_VAR + pick_up * 4) = st.z;
+            }
+        }
         __syncwarp(mask);
+    }
+    if (NL == 32 && pcl > 0) {
+        // ---- staleness scan: a cached child observation that is some trace node's own WITHOUT being its level's natural copy (the same
+        // observation under two nodes of the path: statistics are shared between nodes, agent.py:116-128) was not refreshed above.
+        // Four levels per round: lane = (level & 3) * 8 + child slot.
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) stale = min(stale, __shfl_xor_sync(mask, stale, d, NL));
+        const int upto = stale;                         // entries at or beyond a stale level are dropped anyway
+        int stale2 = upto;
+        for (int L0 = 0; L0 < upto; L0 += 4) {
+            const int L = L0 + (lane >> 3), a = lane & 7;
+            if (L < upto && a < 7) {
+                const int ow = *reinterpret_cast<const int *>(acc.pcg + (size_t)L * PC_STRIDE + PC_OFF_OBS + a * 4);
+                if (ow < 0) {                           // bit 31: first occurrence in the node's child list = a slot the walk reads
+                    const int oc = ow & (int)TMETA_OBS_MASK;
+                    if ((bitmap[oc >> 5] >> (oc & 31)) & 1u) {
+                        const int pk = (acc.tmetag[L].x >> 28) & 7;
+                        if (a != pk && L < stale2) stale2 = L;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) stale2 = min(stale2, __shfl_xor_sync(mask, stale2, d, NL));
+        if (lane == 0 && stale2 < pcl) A.pc_len[g] = stale2;
     }
     if (lane == 0) A.leaf_kind[g] = LEAF_DONE;
     __syncwarp(mask);
@@ -773,10 +834,15 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
 #ifndef B200_BACKUP_MINB
 #define B200_BACKUP_MINB 9      // resident 128-thread blocks per SM the register budget is cut for (9 = what 56 registers give)
 #endif
-__global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A) {
+// Dynamic shared memory: with the path cache on, one bitmap of max_nodes bits per warp (the observations of the game's trace), else none.
+__global__ void __launch_bounds__(128, B200_BACKUP_MINB) k_backup(Arena A, int bitmap_words) {
+    extern __shared__ unsigned s_bitmap[];
     const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    unsigned *bm = bitmap_words ? s_bitmap + (threadIdx.x >> 5) * bitmap_words : nullptr;
+    for (int i = threadIdx.x & 31; i < bitmap_words; i += 32) bm[i] = 0u;
+    __syncwarp();
     if (g >= A.G || A.status[g] != ST_OK) return;
-    backup_game<32>(A, g, 0xffffffffu, threadIdx.x & 31);
+    backup_game<32>(A, g, 0xffffffffu, threadIdx.x & 31, bm);
 }
 
 // ---------------------------------------------------------------- distributional mode (config 5): evaluator + backup

@@ -58,6 +58,10 @@ struct Arena {
     int2 *trace_meta;              // [G][trace_max] {own observation, own score bits} of every node on the trace, written by the walk (it has
                                    // both in lane 7 of the level it just loaded) so that the backup needs no second gather per level
     uint8_t *nmark, *omark; int32_t *gc_queue;
+    // path cache (b200_set_path_cache; LP mode): [G][trace_max] entries of PC_STRIDE bytes — for every level of the game's last trace the
+    // node, its row fields and the STATISTICS OF ITS CHILDREN, so that the next walk, which retraces ~93 % of that path, reads one
+    // sequential line per level instead of chasing a row line and seven statistics; pc_len[g] = how many leading entries are valid
+    uint8_t *pc; int32_t *pc_len;
     uint32_t *cur;                 // [G][20] the live game of each tree (the object play.py owns)
     const float *ztable;
     uint2 *req; int32_t *n_req;    // evaluation requests {game, obs | slot<<28}; n_req[0] = count, n_req[1] = games queued for k_gc
@@ -245,17 +249,52 @@ __device__ __forceinline__ uint2 touch64(const void *p) {
     return v;
 }
 
+// ------------------------------------------------------------------ path cache
+// Consecutive simulations of a game walk almost the same path (CPU model in oracle/mcts_oracle.c: 90-94 % of the levels are a shared
+// prefix; the walks differ in their last ~4 levels), and every level of a walk costs two DEPENDENT random accesses into an 82 GB arena.
+// The walk therefore leaves, next to the trace, everything a level needs (PC_STRIDE bytes per level, sequential per game):
+//     bytes   0..127   lane a: int4 {link word u[a], score s[a], visit, value}   (lane 7: {0, own score, own observation, NODE id})
+//     bytes 128..159   lane a: variance
+//     bytes 160..191   lane a: child observation | is_first << 31                 (read by k_backup's staleness scan only)
+// A level whose entry is valid and whose node id matches is served from the entry: same values, same arithmetic, same pick.
+// Coherence (the row fields of an expanded node never change; only statistics do, and only k_backup writes them for live observations):
+//   * k_backup writes the new statistics of trace level i+1 into the entry of level i, slot = the lane the walk picked there (the
+//     "natural copy"; the pick travels in bits 28-30 of trace_meta.x);
+//   * a copy that is NOT the natural one — the same observation under another path node (transposition), or twice on the trace — goes
+//     stale: k_backup finds those with a bitmap of the trace's own observations and truncates pc_len at the shallowest stale level;
+//   * the entry of a leaf that gets expanded says "no children": the walk leaves pc_len = D - 1;
+//   * k_update_root, k_gc (collections and dropped trees) and reset_tree set pc_len = 0.
+// The CPU model applies exactly these rules and checks every cached value against the arena at every selection (tests/test_cpu_path_cache_model.py).
+constexpr int PC_STRIDE = 192, PC_OFF_VAR = 128, PC_OFF_OBS = 160;
+constexpr int PC_MAX_NODES = 65536;   // k_backup's bitmap of the trace's observations is exact (one bit per slot, shared memory): larger arenas run without the cache
+constexpr uint32_t TMETA_OBS_MASK = 0x0fffffffu;   // trace_meta.x = own observation | pick << 28
+
 // ------------------------------------------------------------------ accessors
 // The engine keeps the packed arena above; the single-call twins of agents/cppmodule/core.cpp:20-26 work on the
 // reference's own array layout (agents/agent.py:58-88).  Both run the same select / backup code through these.
 constexpr int ZS_N = 2048;   // z(n) entries staged in shared memory by k_select_expand (deep nodes have small n)
 
 struct ArenaAcc {
+    static constexpr bool has_pc = true;
     const Arena &A; int g; const float *zs;
     const int32_t *rowg; int4 *statg; int32_t *traceg; int2 *tmetag;   // this game's slices of the arena (address arithmetic hoisted out of the loops)
+    uint8_t *pcg; int pc_len;                                          // path cache of this game (nullptr: off) and its valid length for THIS walk (set by the caller)
     __device__ __forceinline__ ArenaAcc(const Arena &A_, int g_, const float *zs_ = nullptr)
         : A(A_), g(g_), zs(zs_), rowg(A_.row + (size_t)g_ * A_.M * ROW_WORDS), statg(A_.stat + (size_t)g_ * A_.M),
-          traceg(A_.trace + (size_t)g_ * A_.trace_max), tmetag(A_.trace_meta + (size_t)g_ * A_.trace_max) {}
+          traceg(A_.trace + (size_t)g_ * A_.trace_max), tmetag(A_.trace_meta + (size_t)g_ * A_.trace_max),
+          pcg(A_.pc ? A_.pc + (size_t)g_ * A_.trace_max * PC_STRIDE : nullptr), pc_len(0) {}
+    __device__ __forceinline__ void pc_load(int L, int lane, int4 &e, int &var) const {
+        const uint8_t *p = pcg + (size_t)L * PC_STRIDE;
+        e = *reinterpret_cast<const int4 *>(p + lane * 16);
+        var = *reinterpret_cast<const int *>(p + PC_OFF_VAR + lane * 4);
+    }
+    __device__ __forceinline__ void pc_prefetch(int L, int sector) const { prefetch_l2(pcg + (size_t)L * PC_STRIDE + sector * 32); }
+    __device__ __forceinline__ void pc_store(int L, int lane, int4 e, int var, int oword) const {
+        uint8_t *p = pcg + (size_t)L * PC_STRIDE;
+        *reinterpret_cast<int4 *>(p + lane * 16) = e;
+        *reinterpret_cast<int *>(p + PC_OFF_VAR + lane * 4) = var;
+        *reinterpret_cast<int *>(p + PC_OFF_OBS + lane * 4) = oword;
+    }
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
         c = row[lane]; o = row[8 + lane]; s = __int_as_float(row[16 + lane]);   // lane 7: own episode / obs / score
@@ -267,9 +306,9 @@ struct ArenaAcc {
     // one level of select: observation of this lane's child, the node's own score, the cached de-duplication.  `on` = this lane's group
     // is still walking (the loads are predicated, the shuffles are executed by every lane: see GrpW)
     template <typename G>
-    __device__ __forceinline__ void level(const G &gp, bool on, int idx, int depth, int &o, float &s_idx, Uniq &u) const {
+    __device__ __forceinline__ void level(const G &gp, bool on, int idx, int depth, int &o, float &s_idx, Uniq &u, float &s, uint32_t &lw) const {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS + gp.lane;
-        float s = 0.f; uint32_t lw = 0u;
+        s = 0.f; lw = 0u;
         o = 0;
         if (on) {
 #if B200_L2_HOT_LEVELS > 0 && B200_ROW_HINT
@@ -323,13 +362,14 @@ struct ArenaAcc {
     __device__ __forceinline__ void put_trace(int d, int idx) const { traceg[d] = idx; }
     __device__ __forceinline__ int get_trace(int d) const { return traceg[d]; }
     __device__ __forceinline__ void put_trace_meta(int d, int o, float s) const { tmetag[d] = make_int2(o, __float_as_int(s)); }
-    __device__ __forceinline__ void get_trace_meta(int d, int &o, float &s) const { const int2 m = tmetag[d]; o = m.x; s = __int_as_float(m.y); }
+    __device__ __forceinline__ void get_trace_meta(int d, int &o, float &s) const { const int2 m = tmetag[d]; o = m.x & (int)TMETA_OBS_MASK; s = __int_as_float(m.y); }
+    __device__ __forceinline__ void get_trace_meta_raw(int d, int &oraw, float &s) const { const int2 m = tmetag[d]; oraw = m.x; s = __int_as_float(m.y); }   // with the pick in bits 28-30
     __device__ __forceinline__ uint32_t rand() const { uint32_t sr = A.srng[g]; uint32_t r = rng_next(sr); A.srng[g] = sr; return r; }
     __device__ __forceinline__ float z(int n) const { return (zs && n >= 0 && n < ZS_N) ? zs[n] : ztab(A, n); }
     __device__ __forceinline__ unsigned long long *level_prof() const { return (A.prof && (g & 63) == 0) ? A.prof + 8 : nullptr; }
     // rolling prefetch along the PREVIOUS simulation's trace (B200_ROLL_PREFETCH): its length, one of its levels, and the L2 requests for a level
     __device__ __forceinline__ int prev_trace_len() const { return A.trace_len[g]; }
-    __device__ __forceinline__ void prev_trace(int lv, int &idx, int &o) const { idx = traceg[lv]; o = tmetag[lv].x; }
+    __device__ __forceinline__ void prev_trace(int lv, int &idx, int &o) const { idx = traceg[lv]; o = tmetag[lv].x & (int)TMETA_OBS_MASK; }
     __device__ __forceinline__ void prefetch_level(int idx, int o) const {
         const char *r = reinterpret_cast<const char *>(rowg + (size_t)idx * ROW_WORDS);
         prefetch_l2(r + 32); prefetch_l2(r + 96);                                     // the walk reads words 8..31 of the row line
@@ -341,6 +381,11 @@ struct ArenaAcc {
 };
 
 struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
+    static constexpr bool has_pc = false;
+    static constexpr uint8_t *pcg = nullptr; static constexpr int pc_len = 0;
+    __device__ __forceinline__ void pc_load(int, int, int4 &, int &) const {}
+    __device__ __forceinline__ void pc_prefetch(int, int) const {}
+    __device__ __forceinline__ void pc_store(int, int, int4, int, int) const {}
     const int32_t *child; int32_t *visit; float *value; float *variance; const float *score; const int32_t *n2o;
     int32_t *trace; uint32_t *rng; const Arena *A;
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
@@ -349,8 +394,9 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
     }
     __device__ __forceinline__ void meta(int idx, int &o, float &s) const { o = n2o[idx]; s = score[idx]; }
     template <typename G>
-    __device__ __forceinline__ void level(const G &gp, bool on, int idx, int, int &o, float &s_idx, Uniq &u) const {
-        int c = 0; float s = 0.f;
+    __device__ __forceinline__ void level(const G &gp, bool on, int idx, int, int &o, float &s_idx, Uniq &u, float &s, uint32_t &lw) const {
+        int c = 0;
+        s = 0.f; lw = 0u;
         o = 0;
         if (on) children(idx, gp.lane, c, o, s);
         s_idx = gp.bcast(s, 7);
@@ -379,7 +425,7 @@ struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[
 // has reached its leaf idles (predicated) until the deepest of the four is done.  Returns the leaf; writes the trace; all 8 lanes of
 // a group return the same values.  The whole warp must call this together.
 template <typename Acc>
-__device__ __forceinline__ int select_trace(const Acc &acc, bool active, int root, int low, int trace_max, int &D_out, int &status) {
+__device__ __forceinline__ int select_trace(const Acc &acc, bool active, int root, int low, int trace_max, int &D_out, int &status, int *cached_levels = nullptr) {
     const GrpW gp;
     int idx = root, D = 0;
     bool walking = active;
@@ -400,6 +446,80 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
 #else
 #define LEVEL_PROF(i) do { } while (0)
 #endif
+    // core.h:65-105 for one level, from the values every lane holds for its child slot (`on`: this lane's group is at a node WITH children):
+    // check_low, then policy_clt.  Shared by the cached and the uncached form of a level, so both pick bit for bit the same child.
+    auto choose = [&](bool on, const Uniq &u, const int4 &st, float s_idx) -> int {
+        const unsigned lowmask = gp.ballot(on && u.is_first && st.x < low);   // core.h:65-77
+        int pick = 0;
+        if (__any_sync(0xffffffffu, lowmask != 0u)) {                   // warp-uniform branch: the draw of every group that needs one
+            uint32_t r = 0;
+            if (lowmask != 0u && gp.lane == 0) r = acc.rand();
+            r = gp.bcast(r, 0);
+            if (lowmask != 0u) pick = (int)__fns(lowmask, 0, (int)(r % (uint32_t)__popc(lowmask)) + 1);
+        }
+        int n = (on && u.is_first) ? st.x : 0;                          // core.h:88 accumulate(visit)
+        n += __shfl_xor_sync(0xffffffffu, n, 1, 8);
+        n += __shfl_xor_sync(0xffffffffu, n, 2, 8);
+        n += __shfl_xor_sync(0xffffffffu, n, 4, 8);
+        const float z = acc.z(n);
+        const bool cmp = on && u.is_first;
+        const float q = cmp ? clt_q(__int_as_float(st.y), u.rep_s, s_idx, z, __int_as_float(st.z), st.x) : 0.f;
+        // core.h:94-101: the first strict maximum in list order = the largest q, the lowest lane on ties, as a 3-step
+        // butterfly.  A NaN never wins a `>`; it is the answer only when it is the first entry of the list.
+        const bool cand = cmp && q == q;
+        float qv = cand ? q : -INFINITY;
+        int ql = cand ? gp.lane : 8 + gp.lane;                           // non-candidates lose every tie
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const float oq = __shfl_xor_sync(0xffffffffu, qv, d, 8);
+            const int ol = __shfl_xor_sync(0xffffffffu, ql, d, 8);
+            const bool take = oq > qv || (oq == qv && ol < ql);
+            qv = take ? oq : qv; ql = take ? ol : ql;
+        }
+        const int first = __ffs(u.first_mask) - 1;
+        const unsigned nanmask = gp.ballot(cmp && q != q);
+        if (lowmask == 0u) pick = (first >= 0 && ((nanmask >> first) & 1u)) ? first : ql;
+        return pick;
+    };
+    if constexpr (Acc::has_pc) {
+        // ---- phase 1: the levels the path cache still holds (see "path cache" above).  Every group follows ITS cached prefix; a group
+        // leaves this phase at the first level whose entry is missing or belongs to another node and idles until the last group is through
+        // (a cached level is ~0.6 k clk: no memory access on the dependent chain, the next entry is loaded one level ahead).
+        const int pcl = (walking && acc.pcg) ? acc.pc_len : 0;          // group-uniform
+        bool fast = pcl > 0;
+        int n_cached = 0;
+        int4 ec = make_int4(0, 0, 0, 0); int vc = 0;
+        if (fast) acc.pc_load(0, gp.lane, ec, vc);
+        while (__any_sync(0xffffffffu, fast)) {
+            const int node = __shfl_sync(0xffffffffu, ec.w, 7, 8);
+            if (fast && node != idx) fast = false;                      // the previous level picked another child than last time: uncached from here
+            int4 en = make_int4(0, 0, 0, 0); int vn = 0;
+            if (fast && D + 1 < pcl) acc.pc_load(D + 1, gp.lane, en, vn);
+            if (fast && D + 6 < pcl && gp.lane < 6) acc.pc_prefetch(D + 6, gp.lane);
+            const float s = __int_as_float(ec.y);
+            const float s_idx = gp.bcast(s, 7);
+            const int o_own = gp.bcast(ec.z, 7);
+            const uint32_t lw = fast ? (uint32_t)ec.x : 0u;
+            Uniq u;
+            u.is_first = lw >> 31; u.rep_lane = (int)((lw >> 28) & 7u); u.rep_c = (int)(lw & LINK_NODE_MASK);
+            u.rep_s = gp.bcast(s, u.rep_lane);
+            u.first_mask = gp.ballot(u.is_first);
+            const bool on = fast && u.first_mask != 0;                   // first_mask == 0: a cached leaf without children (terminal node)
+            const int4 st = make_int4(ec.z, ec.w, vc, 0);
+            const int pick = choose(on, u, st, s_idx);
+            const int next = gp.bcast(u.rep_c, pick);
+            if (fast) {                                                 // trace[D] already holds idx (same node as last time)
+                ++n_cached;
+                if (gp.lane == 7) acc.put_trace_meta(D, o_own | (on ? pick << 28 : 0), s_idx);
+                ++D;
+                if (!on) { walking = false; fast = false; }             // core.h:200
+                else { idx = next; if (D >= pcl) fast = false; }
+            }
+            ec = en; vc = vn;
+        }
+        if (cached_levels) *cached_levels = n_cached;
+    }
+    // ---- phase 2: uncached levels (two dependent random accesses each); with the path cache on, each of them leaves its entry behind
     while (__any_sync(0xffffffffu, walking)) {
         if (walking && D >= trace_max) { status = ST_TRACE_FULL; walking = false; }
 #if B200_ROLL_PREFETCH
@@ -415,48 +535,23 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
             if (gp.lane == 0) acc.put_trace(D, idx);
             ++D;
         }
-        int o; float s_idx;
+        const bool at_level = walking;                                  // this group loads level D - 1 in this round
+        int o; float s_idx, s_own; uint32_t lw;
         Uniq u;
-        acc.level(gp, walking, idx, D - 1, o, s_idx, u);
-        if (walking && gp.lane == 7) acc.put_trace_meta(D - 1, o, s_idx);   // lane 7 holds the node's own observation and score
+        acc.level(gp, walking, idx, D - 1, o, s_idx, u, s_own, lw);
         LEVEL_PROF(0);
         if (u.first_mask == 0) walking = false;                         // core.h:200 no children: leaf (group-uniform)
         int4 st = make_int4(0, 0, 0, 0);
         if (walking && u.is_first) st = acc.stat(o, D);                 // the children live one level below
-        const unsigned lowmask = gp.ballot(walking && u.is_first && st.x < low);   // core.h:65-77
         LEVEL_PROF(1);
-        int pick = 0;
-        if (__any_sync(0xffffffffu, lowmask != 0u)) {                   // warp-uniform branch: the draw of every group that needs one
-            uint32_t r = 0;
-            if (lowmask != 0u && gp.lane == 0) r = acc.rand();
-            r = gp.bcast(r, 0);
-            if (lowmask != 0u) pick = (int)__fns(lowmask, 0, (int)(r % (uint32_t)__popc(lowmask)) + 1);
-        }
-        {
-            int n = (walking && u.is_first) ? st.x : 0;                  // core.h:88 accumulate(visit)
-            n += __shfl_xor_sync(0xffffffffu, n, 1, 8);
-            n += __shfl_xor_sync(0xffffffffu, n, 2, 8);
-            n += __shfl_xor_sync(0xffffffffu, n, 4, 8);
-            const float z = acc.z(n);
-            const bool cmp = walking && u.is_first;
-            const float q = cmp ? clt_q(__int_as_float(st.y), u.rep_s, s_idx, z, __int_as_float(st.z), st.x) : 0.f;
-            // core.h:94-101: the first strict maximum in list order = the largest q, the lowest lane on ties, as a 3-step
-            // butterfly.  A NaN never wins a `>`; it is the answer only when it is the first entry of the list.
-            const bool cand = cmp && q == q;
-            float qv = cand ? q : -INFINITY;
-            int ql = cand ? gp.lane : 8 + gp.lane;                       // non-candidates lose every tie
-#pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                const float oq = __shfl_xor_sync(0xffffffffu, qv, d, 8);
-                const int ol = __shfl_xor_sync(0xffffffffu, ql, d, 8);
-                const bool take = oq > qv || (oq == qv && ol < ql);
-                qv = take ? oq : qv; ql = take ? ol : ql;
-            }
-            const int first = __ffs(u.first_mask) - 1;
-            const unsigned nanmask = gp.ballot(cmp && q != q);
-            if (lowmask == 0u) pick = (first >= 0 && ((nanmask >> first) & 1u)) ? first : ql;
-        }
+        const int pick = choose(walking, u, st, s_idx);
         const int next = gp.bcast(u.rep_c, pick);
+        if (at_level && gp.lane == 7) acc.put_trace_meta(D - 1, o | (walking ? pick << 28 : 0), s_idx);   // lane 7 holds the node's own observation and score
+        if constexpr (Acc::has_pc) {
+            if (at_level && acc.pcg)
+                acc.pc_store(D - 1, gp.lane, make_int4((int)lw, __float_as_int(s_own), gp.lane == 7 ? o : st.x, gp.lane == 7 ? idx : st.y), st.z,
+                             o | (u.is_first ? (int)0x80000000u : 0));
+        }
         if (walking) idx = next;
         LEVEL_PROF(2);
 #if B200_SELECT_PROF
@@ -619,6 +714,7 @@ __device__ __forceinline__ int new_node(const Arena &A, const Grp &gp, int g, co
 // first move of an episode.  Never taken when the arena is sized like the reference's (tests run with it off).
 __device__ __noinline__ void reset_tree(const Arena &A, const Grp &gp, int g, int &status) {
     const int M = A.M, H = A.H;
+    if (A.pc && gp.lane == 0) A.pc_len[g] = 0;     // path cache: the tree is gone
     if (status != ST_RESET_DONE) {        // (k_gc has already cleared the arena with a whole thread block in that case)
         int4 *rows = reinterpret_cast<int4 *>(A.row + (size_t)g * M * ROW_WORDS);
         for (int i = gp.lane; i < M * (ROW_WORDS / 4); i += 8) rows[i] = make_int4(0, 0, 0, 0);

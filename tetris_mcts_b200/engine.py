@@ -3,17 +3,21 @@
 Host-side mirror of the reference's TreeAgent loop (agents/agent.py:147-151 play(), :296-301 update_root(),
 :153-185 compute_stats/get_action) for a batch of games; the compute is entirely in libb200_tetris_mcts.so."""
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import _lib as L
 
 
+PATH_CACHE_DEFAULT = "0"
+
+
 class BatchedEngine:
     def __init__(self, n_games, max_nodes=8192, mode="lp", gamma=None, low=None, eval_kind="net", weights=None,
                  env_args=((20, 10), 1, 0, 0), seed=123, device=0, lp_end_from_obs=False, lp_var_gamma2=True,
                  stale_pop=True, rollout_variance=1e3, trace_max=512, overflow_reset=False, dist_bins=50, dist_vmin=0.0, dist_vmax=5000.0,
-                 dist_weights=None):
+                 dist_weights=None, path_cache=None):
         mode_id = {"lp": L.MODE_LP, "single": L.MODE_SINGLE, "vanilla": L.MODE_VANILLA, "dist": L.MODE_DIST}[mode] if isinstance(mode, str) else int(mode)
         eval_id = {"synthetic": L.EVAL_SYNTHETIC, "net": L.EVAL_NET, "net_tc": L.EVAL_NET_TC}[eval_kind] if isinstance(eval_kind, str) else int(eval_kind)
         if tuple(env_args[0]) != (20, 10):
@@ -37,6 +41,14 @@ class BatchedEngine:
             self.load_weights(weights)
         if dist_weights is not None:
             self.load_dist_weights(dist_weights, dist_bins)
+        # path cache (b200_set_path_cache): None = the default (environment B200_PATH_CACHE, else PATH_CACHE_DEFAULT) wherever it applies
+        # (LP mode, max_nodes <= 65536); True / False = explicit (True raises where it does not apply)
+        if path_cache is None:
+            want = os.environ.get("B200_PATH_CACHE", PATH_CACHE_DEFAULT) not in ("0", "")
+            if want and mode_id == L.MODE_LP and int(max_nodes) <= 65536:
+                self.set_path_cache(True)
+        elif path_cache:
+            self.set_path_cache(True)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -95,6 +107,11 @@ class BatchedEngine:
     def set_gc_headroom(self, min_free):
         """update_root() then collects every game with fewer than min_free free slots (0 = the reference's lazy collection only)."""
         L.check(L.lib().b200_set_gc_headroom(self.h, int(min_free)))
+
+    def set_path_cache(self, on=True):
+        """Keep the children's statistics of every trace level next to the trace, so that the next walk of the game (which retraces ~93 % of the
+        path) reads one sequential line per level instead of two dependent random accesses.  No effect on results.  LP mode, max_nodes <= 65536."""
+        L.check(L.lib().b200_set_path_cache(self.h, int(bool(on))))
 
     def set_deep_lane(self, max_games):
         """Scheduling only: the max_games games with the longest traces walk on a second stream (b200_set_deep_lane); 0 = off."""
@@ -155,7 +172,7 @@ class BatchedEngine:
         return st
 
     COUNTER_NAMES = ("sims", "expansions", "eval_requests", "gcs", "trace_levels", "rollout_steps", "new_nodes", "tree_resets",
-                     "games_finished", "score_sum", "lines_sum", "_11", "max_trace_len")
+                     "games_finished", "score_sum", "lines_sum", "_11", "max_trace_len", "cached_levels")
 
     def counters(self):
         c = np.zeros(16, np.uint64)
