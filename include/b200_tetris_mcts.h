@@ -100,7 +100,7 @@ int b200_set_deep_lane(b200_engine *e, int max_games);
  * the same root-to-leaf path (select_trace_obs, core.h:167-224, restarts at the root every time); with the cache on, a walk leaves next to its
  * trace the row fields and the children's statistics of every level, the backup (core.h:226-381) refreshes the copies it changes and drops
  * the ones a transposition made stale, and the next walk serves every level that is still valid from one sequential line instead of two
- * dependent random accesses.  B200_MODE_LP with max_nodes <= 65536; 192 bytes x trace_max per game.  0 (default) = off. */
+ * dependent random accesses.  B200_MODE_LP with max_nodes <= 65536; 192 bytes x trace_max per game (entry 160 + own record 16 + child ids 16).  0 (default) = off. */
 int b200_set_path_cache(b200_engine *e, int on);
 
 /* --- TreeAgent.mcts (agents/ValueSimLP.py:13, ValueSim.py:52, Vanilla.py:17): `sims` simulations on every game */

@@ -249,6 +249,9 @@ struct mo_agent {
     int pc_on, pc_len; long pc_errors, pc_irregular, pc_shared, pc_levels, pc_sims, pc_full_walks;
     int32_t pc_node[512]; int pc_k[512]; int32_t pc_cn[512][MO_NA], pc_co[512][MO_NA];
     int32_t pc_visit[512][MO_NA]; float pc_value[512][MO_NA], pc_variance[512][MO_NA];
+    /* layout of the engine: the entry of level L keeps the children's statistics as of the walk that FILLED it; the statistics of the child
+     * the walk picked there (pc_pick) are read from the own-statistics record of level L+1, which the backup rewrites every simulation */
+    int pc_pick[512]; int32_t pc_own_visit[512]; float pc_own_value[512], pc_own_variance[512];
 };
 
 static uint64_t hash_words(const uint32_t *w, int n) {
@@ -501,7 +504,12 @@ static void evaluate(mo_agent *a, const int32_t *obs, int k, float *v, float *va
 }
 
 /* ---- path-cache model (see struct mo_agent) */
-static void pc_fill(mo_agent *a, int L, int node) {
+static int pc_pick_of(const mo_agent *a, int L, int next_node) {
+    for (int j = 0; j < a->pc_k[L]; ++j) if (a->pc_cn[L][j] == next_node) return j;
+    return -1;
+}
+static void pc_fill(mo_agent *a, int L, const int32_t *trace, int D) {
+    int node = trace[L];
     a->pc_node[L] = node;
     int k = mo_unique_child_obs(node, a->child, a->score, a->n2o, a->pc_cn[L], a->pc_co[L]);
     a->pc_k[L] = k;
@@ -509,6 +517,7 @@ static void pc_fill(mo_agent *a, int L, int node) {
         int o = a->pc_co[L][j];
         a->pc_visit[L][j] = a->ovisit[o]; a->pc_value[L][j] = a->ovalue[o]; a->pc_variance[L][j] = a->ovariance[o];
     }
+    a->pc_pick[L] = L + 1 < D ? pc_pick_of(a, L, trace[L + 1]) : -1;
 }
 static void pc_on_select(mo_agent *a, const int32_t *trace, int D) {
     if (!a->pc_on) return;
@@ -519,42 +528,49 @@ static void pc_on_select(mo_agent *a, const int32_t *trace, int D) {
         int bad = k != a->pc_k[L];
         for (int j = 0; j < k && !bad; ++j) {
             int o = co[j];
-            bad = cn[j] != a->pc_cn[L][j] || o != a->pc_co[L][j] || a->pc_visit[L][j] != a->ovisit[o] ||
-                  memcmp(&a->pc_value[L][j], &a->ovalue[o], 4) != 0 || memcmp(&a->pc_variance[L][j], &a->ovariance[o], 4) != 0;
+            /* what the engine's walk reads for child j: the entry, except for the child picked last time (own record of the next level) */
+            int32_t vis = a->pc_visit[L][j]; float val = a->pc_value[L][j], var = a->pc_variance[L][j];
+            if (j == a->pc_pick[L]) { vis = a->pc_own_visit[L + 1]; val = a->pc_own_value[L + 1]; var = a->pc_own_variance[L + 1]; }
+            bad = cn[j] != a->pc_cn[L][j] || o != a->pc_co[L][j] || vis != a->ovisit[o] ||
+                  memcmp(&val, &a->ovalue[o], 4) != 0 || memcmp(&var, &a->ovariance[o], 4) != 0;
         }
         if (bad) {
             if (a->pc_errors < 5) fprintf(stderr, "path-cache model: stale entry at level %d of %d (node %d)\n", L, D, trace[L]);
             a->pc_errors += 1;
         }
+        /* the walk picks another child than last time: the old pick's latest statistics go back into the entry, the new pick is recorded */
+        int np = L + 1 < D ? pc_pick_of(a, L, trace[L + 1]) : -1;
+        if (np != a->pc_pick[L]) {
+            int op = a->pc_pick[L];
+            if (op >= 0) { a->pc_visit[L][op] = a->pc_own_visit[L + 1]; a->pc_value[L][op] = a->pc_own_value[L + 1]; a->pc_variance[L][op] = a->pc_own_variance[L + 1]; }
+            a->pc_pick[L] = np;
+        }
         ++L;
     }
     a->pc_shared += L; a->pc_levels += D; a->pc_sims += 1;
     if (L == 0) a->pc_full_walks += 1;
-    for (; L < D; ++L) pc_fill(a, L, trace[L]);
+    for (; L < D; ++L) pc_fill(a, L, trace, D);
     a->pc_len = D;
 }
 static void pc_on_backup(mo_agent *a, const int32_t *trace, int D, int expanded) {
     if (!a->pc_on || a->pc_len == 0) return;             /* invalidated since the selection (collection / tree drop inside the expansion) */
     int newlen = expanded ? D - 1 : D;                   /* the expanded leaf's entry says "no children": stale */
-    /* Stale copies after this backup, by level: (a) an observation twice on the trace (i < j): the backup runs leaf -> root, so the natural copy
-     * of the deeper occurrence (level j-1) holds an intermediate value; (b) a cached child observation that is some trace node's own without
-     * being that level's natural copy.  Everything above the shallowest stale level stays valid: the cache is truncated there. */
+    /* Stale copies after this backup, by level: (a) an observation twice on the trace (i < j): the backup runs leaf -> root, so the own record
+     * of the deeper occurrence (read by level j-1) holds an intermediate value; (b) a cached child observation that is some trace node's own
+     * without being that level's picked child.  Everything above the shallowest stale level stays valid: the cache is truncated there. */
     int stale = newlen;
     for (int i = 0; i < D; ++i)
         for (int j = i + 1; j < D; ++j) if (a->n2o[trace[i]] == a->n2o[trace[j]] && j - 1 < stale) stale = j - 1;
     for (int L = 0; L < stale; ++L)
         for (int j = 0; j < a->pc_k[L]; ++j) {
-            const int natural = L + 1 < D && a->pc_cn[L][j] == trace[L + 1];
-            if (natural) continue;
+            if (j == a->pc_pick[L]) continue;
             for (int i = 0; i < D; ++i) if (a->pc_co[L][j] == a->n2o[trace[i]] && L < stale) stale = L;
         }
     if (stale < newlen) { a->pc_irregular += 1; newlen = stale; }
-    for (int L = 0; L + 1 < D && L < newlen; ++L)        /* natural copies take the values the backup just wrote */
-        for (int j = 0; j < a->pc_k[L]; ++j)
-            if (a->pc_cn[L][j] == trace[L + 1]) {
-                int o = a->pc_co[L][j];
-                a->pc_visit[L][j] = a->ovisit[o]; a->pc_value[L][j] = a->ovalue[o]; a->pc_variance[L][j] = a->ovariance[o];
-            }
+    for (int i = 0; i < D; ++i) {                        /* the backup rewrites the own record of every trace level */
+        int o = a->n2o[trace[i]];
+        a->pc_own_visit[i] = a->ovisit[o]; a->pc_own_value[i] = a->ovalue[o]; a->pc_own_variance[i] = a->ovariance[o];
+    }
     a->pc_len = newlen;
 }
 void mo_agent_pc_enable(mo_agent *a, int on) { a->pc_on = on; a->pc_len = 0; }

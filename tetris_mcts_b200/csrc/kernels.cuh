@@ -754,19 +754,15 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
             wo = -1 - lane; wsc = 0.f;
             if (ntop >= 0 && lane <= ntop) acc.get_trace_meta_raw(ntop - lane, wo, wsc);
         }
-        // path cache: the entry of level i-1 holds a copy of this level's statistics in the slot the walk picked there (bits 28-30 of
-        // level i-1's trace_meta word: the next lane's, or lane 0 of the next window)
-        int pick_up = 0;
+        // path cache: a bitmap of the trace's own observations for the staleness scan below; a bit already set by a DEEPER window = the same
+        // observation twice on the trace: the deeper occurrence's own record holds an intermediate value
         if (NL == 32 && pcl > 0) {
-            const int from_next = __shfl_sync(mask, wo, 0, NL), from_lane = __shfl_down_sync(mask, oraw, 1, NL);
-            const int praw = lane == NL - 1 ? from_next : from_lane;
-            pick_up = (praw >> 28) & 7;
-            if (lane < n) {                             // bitmap of the trace's own observations; a bit already set by a DEEPER window = the same observation
-                const unsigned bit = 1u << (o & 31);    // twice on the trace: the deeper natural copy holds an intermediate value
+            if (lane < n) {
+                const unsigned bit = 1u << (o & 31);
                 const unsigned old = atomicOr(&bitmap[o >> 5], bit);
                 if ((old & bit) && top - lane < stale) stale = top - lane;
             }
-            if (any_dup && top - n < stale) stale = top - n < 0 ? 0 : top - n;   // the same inside this window: no natural copies are written for it
+            if (any_dup && top - n < stale) stale = top - n < 0 ? 0 : top - n;   // the same inside this window: no own records are written for it
         }
         if (any_dup) {                                  // shared observation inside the window: scalar walk for this window
             if (lane == 0) {
@@ -793,35 +789,30 @@ __device__ __forceinline__ void backup_game(const Arena &A, int g, unsigned mask
         }
         if (lane < n) {
             welford_level(st, vin, var, sc, A.gamma); acc.set_stat(o, st, top - lane);
-            const int up = top - lane - 1;              // the natural copy, one level up
-            if (NL == 32 && pcl > 0 && up >= 0 && up < pcl) {
-                uint8_t *e = acc.pcg + (size_t)up * PC_STRIDE;
-                *reinterpret_cast<int2 *>(e + pick_up * 16 + 8) = make_int2(st.x, st.y);
-                *reinterpret_cast<int *>(e + PC_OFF_VAR + pick_up * 4) = st.z;
-            }
+            if (NL == 32 && pcl > 0) acc.pown[top - lane] = make_int4(st.x, st.y, st.z, 0);   // the level's own record: what the walk one level up reads for its picked child
         }
         __syncwarp(mask);
     }
     if (NL == 32 && pcl > 0) {
-        // ---- staleness scan: a cached child observation that is some trace node's own WITHOUT being its level's natural copy (the same
-        // observation under two nodes of the path: statistics are shared between nodes, agent.py:116-128) was not refreshed above.
-        // Four levels per round: lane = (level & 3) * 8 + child slot.
+        // ---- staleness scan: a cached child observation that is some trace node's own WITHOUT being its level's picked child (the same
+        // observation under two nodes of the path: statistics are shared between nodes, agent.py:116-128) still holds its fill-time value.
+        // One level per lane: eight u16 of pc_sib (seven child observations, 0 = not a slot the walk reads; the picked slot).
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) stale = min(stale, __shfl_xor_sync(mask, stale, d, NL));
         const int upto = stale;                         // entries at or beyond a stale level are dropped anyway
         int stale2 = upto;
-        for (int L0 = 0; L0 < upto; L0 += 4) {
-            const int L = L0 + (lane >> 3), a = lane & 7;
-            if (L < upto && a < 7) {
-                const int ow = *reinterpret_cast<const int *>(acc.pcg + (size_t)L * PC_STRIDE + PC_OFF_OBS + a * 4);
-                if (ow < 0) {                           // bit 31: first occurrence in the node's child list = a slot the walk reads
-                    const int oc = ow & (int)TMETA_OBS_MASK;
-                    if ((bitmap[oc >> 5] >> (oc & 31)) & 1u) {
-                        const int pk = (acc.tmetag[L].x >> 28) & 7;
-                        if (a != pk && L < stale2) stale2 = L;
-                    }
-                }
+        const uint4 *sib = reinterpret_cast<const uint4 *>(acc.psib);
+        for (int L = lane; L < upto; L += 32) {
+            const uint4 sv = sib[L];
+            const unsigned wv[4] = {sv.x, sv.y, sv.z, sv.w};
+            const int pk = (int)(sv.w >> 16);
+            bool hit = false;
+#pragma unroll
+            for (int a = 0; a < 7; ++a) {
+                const unsigned oc = (wv[a >> 1] >> ((a & 1) * 16)) & 0xffffu;
+                hit |= oc != 0u && a != pk && ((bitmap[oc >> 5] >> (oc & 31)) & 1u);
             }
+            if (hit) { stale2 = L; break; }             // this lane's levels ascend: the first hit is its shallowest
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) stale2 = min(stale2, __shfl_xor_sync(mask, stale2, d, NL));

@@ -62,6 +62,7 @@ struct Arena {
     // node, its row fields and the STATISTICS OF ITS CHILDREN, so that the next walk, which retraces ~93 % of that path, reads one
     // sequential line per level instead of chasing a row line and seven statistics; pc_len[g] = how many leading entries are valid
     uint8_t *pc; int32_t *pc_len;
+    uint4 *pc_sib; int4 *pc_own;   // [G][trace_max] per level: the children's observation ids (8 x u16, the last = the picked slot) | the level's OWN statistics
     uint32_t *cur;                 // [G][20] the live game of each tree (the object play.py owns)
     const float *ztable;
     uint2 *req; int32_t *n_req;    // evaluation requests {game, obs | slot<<28}; n_req[0] = count, n_req[1] = games queued for k_gc
@@ -252,21 +253,27 @@ __device__ __forceinline__ uint2 touch64(const void *p) {
 // ------------------------------------------------------------------ path cache
 // Consecutive simulations of a game walk almost the same path (CPU model in oracle/mcts_oracle.c: 90-94 % of the levels are a shared
 // prefix; the walks differ in their last ~4 levels), and every level of a walk costs two DEPENDENT random accesses into an 82 GB arena.
-// The walk therefore leaves, next to the trace, everything a level needs (PC_STRIDE bytes per level, sequential per game):
-//     bytes   0..127   lane a: int4 {link word u[a], score s[a], visit, value}   (lane 7: {0, own score, own observation, NODE id})
-//     bytes 128..159   lane a: variance
-//     bytes 160..191   lane a: child observation | is_first << 31                 (read by k_backup's staleness scan only)
-// A level whose entry is valid and whose node id matches is served from the entry: same values, same arithmetic, same pick.
-// Coherence (the row fields of an expanded node never change; only statistics do, and only k_backup writes them for live observations):
-//   * k_backup writes the new statistics of trace level i+1 into the entry of level i, slot = the lane the walk picked there (the
-//     "natural copy"; the pick travels in bits 28-30 of trace_meta.x);
-//   * a copy that is NOT the natural one — the same observation under another path node (transposition), or twice on the trace — goes
-//     stale: k_backup finds those with a bitmap of the trace's own observations and truncates pc_len at the shallowest stale level;
+// The walk therefore leaves, next to the trace, everything a level needs (sequential per game):
+//   pc      PC_STRIDE bytes per level   lane a: int4 {link word u[a], score s[a], visit, value} | lane a: variance       (bytes 0..127 | 128..159)
+//                                       lane 7: {0, own score, own observation, NODE id}       | lane 7: the slot the walk PICKED (7: none)
+//                                       = the node's row fields and its children's statistics AS OF THE WALK THAT FILLED THE ENTRY
+//   pc_own  16 bytes per level          {visit, value, variance} of the level's own observation, rewritten by k_backup every simulation
+//   pc_sib  16 bytes per level          the children's observation ids as 8 x u16 (0: not a first occurrence; the last: the picked slot),
+//                                       read by k_backup's staleness scan only
+// A level whose entry is valid and whose node id matches is served from the entry, with the picked child's statistics taken from the NEXT
+// level's own record (the one statistic of the node's children that changes from simulation to simulation): same values, same
+// arithmetic, same pick.  Coherence (the row fields of an expanded node never change; only statistics do, and only k_backup writes them
+// for live observations):
+//   * k_backup rewrites pc_own of every trace level (one coalesced 16-byte store per level);
+//   * when a cached level picks another child than last time, the old pick's latest statistics go back into the entry first;
+//   * any other copy — the same observation under another node of the path (transposition), or twice on the trace — goes stale:
+//     k_backup finds those with a bitmap of the trace's own observations and truncates pc_len at the shallowest stale level;
 //   * the entry of a leaf that gets expanded says "no children": the walk leaves pc_len = D - 1;
 //   * k_update_root, k_gc (collections and dropped trees) and reset_tree set pc_len = 0.
-// The CPU model applies exactly these rules and checks every cached value against the arena at every selection (tests/test_cpu_path_cache_model.py).
-constexpr int PC_STRIDE = 192, PC_OFF_VAR = 128, PC_OFF_OBS = 160;
-constexpr int PC_MAX_NODES = 65536;   // k_backup's bitmap of the trace's observations is exact (one bit per slot, shared memory): larger arenas run without the cache
+// The CPU model applies exactly these rules and checks every value a cached level would read against the arena at every selection
+// (oracle/mcts_oracle.c pc_*, tests/test_cpu_path_cache_model.py).
+constexpr int PC_STRIDE = 160, PC_OFF_VAR = 128;
+constexpr int PC_MAX_NODES = 65536;   // observation ids as u16 in pc_sib; k_backup's bitmap of the trace's observations is exact (one bit per slot, shared memory)
 constexpr uint32_t TMETA_OBS_MASK = 0x0fffffffu;   // trace_meta.x = own observation | pick << 28
 
 // ------------------------------------------------------------------ accessors
@@ -278,22 +285,37 @@ struct ArenaAcc {
     static constexpr bool has_pc = true;
     const Arena &A; int g; const float *zs;
     const int32_t *rowg; int4 *statg; int32_t *traceg; int2 *tmetag;   // this game's slices of the arena (address arithmetic hoisted out of the loops)
-    uint8_t *pcg; int pc_len;                                          // path cache of this game (nullptr: off) and its valid length for THIS walk (set by the caller)
+    uint8_t *pcg; uint16_t *psib; int4 *pown; int pc_len;              // path cache of this game (nullptr: off) and its valid length for THIS walk (set by the caller)
     __device__ __forceinline__ ArenaAcc(const Arena &A_, int g_, const float *zs_ = nullptr)
         : A(A_), g(g_), zs(zs_), rowg(A_.row + (size_t)g_ * A_.M * ROW_WORDS), statg(A_.stat + (size_t)g_ * A_.M),
           traceg(A_.trace + (size_t)g_ * A_.trace_max), tmetag(A_.trace_meta + (size_t)g_ * A_.trace_max),
-          pcg(A_.pc ? A_.pc + (size_t)g_ * A_.trace_max * PC_STRIDE : nullptr), pc_len(0) {}
-    __device__ __forceinline__ void pc_load(int L, int lane, int4 &e, int &var) const {
+          pcg(A_.pc ? A_.pc + (size_t)g_ * A_.trace_max * PC_STRIDE : nullptr),
+          psib(A_.pc ? reinterpret_cast<uint16_t *>(A_.pc_sib + (size_t)g_ * A_.trace_max) : nullptr),
+          pown(A_.pc ? A_.pc_own + (size_t)g_ * A_.trace_max : nullptr), pc_len(0) {}
+    __device__ __forceinline__ void pc_load(int L, int lane, int4 &e, int &var, int4 &own_next) const {   // entry of level L + the own record of level L + 1
         const uint8_t *p = pcg + (size_t)L * PC_STRIDE;
         e = *reinterpret_cast<const int4 *>(p + lane * 16);
         var = *reinterpret_cast<const int *>(p + PC_OFF_VAR + lane * 4);
+        own_next = pown[L + 1 < A.trace_max ? L + 1 : L];
     }
-    __device__ __forceinline__ void pc_prefetch(int L, int sector) const { prefetch_l2(pcg + (size_t)L * PC_STRIDE + sector * 32); }
-    __device__ __forceinline__ void pc_store(int L, int lane, int4 e, int var, int oword) const {
+    __device__ __forceinline__ void pc_prefetch(int L, int lane) const {
+        if (lane < 5) prefetch_l2(pcg + (size_t)L * PC_STRIDE + lane * 32);
+        else if (lane == 5 && L + 1 < A.trace_max) prefetch_l2(pown + L + 1);
+    }
+    __device__ __forceinline__ void pc_store(int L, int lane, int4 e, int var, uint16_t sib) const {
         uint8_t *p = pcg + (size_t)L * PC_STRIDE;
         *reinterpret_cast<int4 *>(p + lane * 16) = e;
         *reinterpret_cast<int *>(p + PC_OFF_VAR + lane * 4) = var;
-        *reinterpret_cast<int *>(p + PC_OFF_OBS + lane * 4) = oword;
+        psib[(size_t)L * 8 + lane] = sib;
+    }
+    // a cached level picked another child than last time: the old pick's latest statistics return to the entry, the new pick is recorded
+    __device__ __forceinline__ void pc_repick(int L, int lane, int old_pick, int new_pick, const int4 &st) const {
+        uint8_t *p = pcg + (size_t)L * PC_STRIDE;
+        if (lane == old_pick) {
+            *reinterpret_cast<int2 *>(p + lane * 16 + 8) = make_int2(st.x, st.y);
+            *reinterpret_cast<int *>(p + PC_OFF_VAR + lane * 4) = st.z;
+        }
+        if (lane == 7) { *reinterpret_cast<int *>(p + PC_OFF_VAR + 7 * 4) = new_pick; psib[(size_t)L * 8 + 7] = (uint16_t)new_pick; }
     }
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
@@ -383,9 +405,10 @@ struct ArenaAcc {
 struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
     static constexpr bool has_pc = false;
     static constexpr uint8_t *pcg = nullptr; static constexpr int pc_len = 0;
-    __device__ __forceinline__ void pc_load(int, int, int4 &, int &) const {}
+    __device__ __forceinline__ void pc_load(int, int, int4 &, int &, int4 &) const {}
     __device__ __forceinline__ void pc_prefetch(int, int) const {}
-    __device__ __forceinline__ void pc_store(int, int, int4, int, int) const {}
+    __device__ __forceinline__ void pc_store(int, int, int4, int, uint16_t) const {}
+    __device__ __forceinline__ void pc_repick(int, int, int, int, const int4 &) const {}
     const int32_t *child; int32_t *visit; float *value; float *variance; const float *score; const int32_t *n2o;
     int32_t *trace; uint32_t *rng; const Arena *A;
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
@@ -488,34 +511,36 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
         const int pcl = (walking && acc.pcg) ? acc.pc_len : 0;          // group-uniform
         bool fast = pcl > 0;
         int n_cached = 0;
-        int4 ec = make_int4(0, 0, 0, 0); int vc = 0;
-        if (fast) acc.pc_load(0, gp.lane, ec, vc);
+        int4 ec = make_int4(0, 0, 0, 0), oc = ec; int vc = 0;           // entry of the current level, own record of the next one
+        if (fast) acc.pc_load(0, gp.lane, ec, vc, oc);
         while (__any_sync(0xffffffffu, fast)) {
             const int node = __shfl_sync(0xffffffffu, ec.w, 7, 8);
             if (fast && node != idx) fast = false;                      // the previous level picked another child than last time: uncached from here
-            int4 en = make_int4(0, 0, 0, 0); int vn = 0;
-            if (fast && D + 1 < pcl) acc.pc_load(D + 1, gp.lane, en, vn);
+            int4 en = make_int4(0, 0, 0, 0), on_ = en; int vn = 0;
+            if (fast && D + 1 < pcl) acc.pc_load(D + 1, gp.lane, en, vn, on_);
             if (fast && D + 6 < pcl && gp.lane < 6) acc.pc_prefetch(D + 6, gp.lane);
             const float s = __int_as_float(ec.y);
             const float s_idx = gp.bcast(s, 7);
             const int o_own = gp.bcast(ec.z, 7);
+            const int pick_prev = gp.bcast(vc, 7);                      // the slot this level picked last time: its statistics live in the next level's own record
             const uint32_t lw = fast ? (uint32_t)ec.x : 0u;
             Uniq u;
             u.is_first = lw >> 31; u.rep_lane = (int)((lw >> 28) & 7u); u.rep_c = (int)(lw & LINK_NODE_MASK);
             u.rep_s = gp.bcast(s, u.rep_lane);
             u.first_mask = gp.ballot(u.is_first);
             const bool on = fast && u.first_mask != 0;                   // first_mask == 0: a cached leaf without children (terminal node)
-            const int4 st = make_int4(ec.z, ec.w, vc, 0);
+            const int4 st = gp.lane == pick_prev ? make_int4(oc.x, oc.y, oc.z, 0) : make_int4(ec.z, ec.w, vc, 0);
             const int pick = choose(on, u, st, s_idx);
             const int next = gp.bcast(u.rep_c, pick);
             if (fast) {                                                 // trace[D] already holds idx (same node as last time)
                 ++n_cached;
                 if (gp.lane == 7) acc.put_trace_meta(D, o_own | (on ? pick << 28 : 0), s_idx);
+                if (on && pick != pick_prev) acc.pc_repick(D, gp.lane, pick_prev, pick, st);
                 ++D;
                 if (!on) { walking = false; fast = false; }             // core.h:200
                 else { idx = next; if (D >= pcl) fast = false; }
             }
-            ec = en; vc = vn;
+            ec = en; vc = vn; oc = on_;
         }
         if (cached_levels) *cached_levels = n_cached;
     }
@@ -548,9 +573,11 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
         const int next = gp.bcast(u.rep_c, pick);
         if (at_level && gp.lane == 7) acc.put_trace_meta(D - 1, o | (walking ? pick << 28 : 0), s_idx);   // lane 7 holds the node's own observation and score
         if constexpr (Acc::has_pc) {
-            if (at_level && acc.pcg)
-                acc.pc_store(D - 1, gp.lane, make_int4((int)lw, __float_as_int(s_own), gp.lane == 7 ? o : st.x, gp.lane == 7 ? idx : st.y), st.z,
-                             o | (u.is_first ? (int)0x80000000u : 0));
+            if (at_level && acc.pcg) {
+                const int pk = walking ? pick : 7;
+                acc.pc_store(D - 1, gp.lane, make_int4((int)lw, __float_as_int(s_own), gp.lane == 7 ? o : st.x, gp.lane == 7 ? idx : st.y),
+                             gp.lane == 7 ? pk : st.z, gp.lane == 7 ? (uint16_t)pk : (uint16_t)(u.is_first ? o : 0));
+            }
         }
         if (walking) idx = next;
         LEVEL_PROF(2);
