@@ -519,8 +519,73 @@ static void pc_fill(mo_agent *a, int L, const int32_t *trace, int D) {
     }
     a->pc_pick[L] = L + 1 < D ? pc_pick_of(a, L, trace[L + 1]) : -1;
 }
+/* The engine's phase 1 (select_trace, search_dev.cuh) restated lane for lane: eight lanes evaluate eight consecutive cached levels, the walk
+ * follows the cached path up to the first lane that stops.  Returns the number of levels served; *idx_out = the node the walk stands on
+ * afterwards (the leaf if *ended), picks[] = the pick (index into the level's child list) of every served level.  Checked against the true
+ * walk in pc_on_select: a wrong stop rule shows up as pc_errors. */
+static int pc_emulate_phase1(const mo_agent *a, int root, int *idx_out, int *ended_out, int *picks) {
+    int D = 0, idx = root, fast = a->pc_len > 0, ended = 0;
+    const int pcl = a->pc_len;
+    while (fast) {
+        int have[8], e_node[8], pick[8], next[8], leaf[8], bail[8], changed[8];
+        for (int lane = 0; lane < 8; ++lane) {
+            int L = D + lane;
+            have[lane] = L < pcl; e_node[lane] = 0; pick[lane] = 7; next[lane] = 0; leaf[lane] = 0; bail[lane] = 0; changed[lane] = 0;
+            if (!have[lane]) continue;
+            e_node[lane] = a->pc_node[L];
+            int k = a->pc_k[L];
+            if (k == 0) { leaf[lane] = 1; continue; }
+            int32_t vis[MO_NA]; float val[MO_NA], var[MO_NA];
+            int lowhit = 0;
+            for (int j = 0; j < k; ++j) {
+                int32_t v = a->pc_visit[L][j]; float vl = a->pc_value[L][j], vr = a->pc_variance[L][j];
+                if (j == a->pc_pick[L]) { v = a->pc_own_visit[L + 1]; vl = a->pc_own_value[L + 1]; vr = a->pc_own_variance[L + 1]; }
+                if (v < a->cfg.low) lowhit = 1;
+                int c = a->pc_cn[L][j];
+                float t = vl + a->score[c];
+                vis[j] = v; val[j] = t - a->score[a->pc_node[L]]; var[j] = vr;
+            }
+            if (lowhit) { bail[lane] = 1; continue; }
+            int nx = mo_policy_clt(a->pc_cn[L], vis, val, var, k);
+            for (int j = 0; j < k; ++j) if (a->pc_cn[L][j] == nx) pick[lane] = j;
+            next[lane] = nx;
+        }
+        for (int lane = 0; lane < 8; ++lane) {
+            int expect = lane == 0 ? idx : next[lane - 1];
+            if (have[lane] && e_node[lane] != expect) bail[lane] = 1;
+            changed[lane] = have[lane] && !leaf[lane] && !bail[lane] && pick[lane] != a->pc_pick[D + lane];
+        }
+        int first = 8;
+        for (int lane = 7; lane >= 0; --lane) if (!have[lane] || bail[lane] || leaf[lane] || changed[lane]) first = lane;
+        int first_served = first < 8 && have[first] && !bail[first];
+        int served = first + (first_served ? 1 : 0);
+        for (int lane = 0; lane < served; ++lane) picks[D + lane] = leaf[lane] ? -1 : pick[lane];
+        int last_next = next[served > 0 ? served - 1 : 0];
+        ended = first_served && leaf[first];
+        D += served;
+        if (ended) idx = e_node[first];
+        else if (served > 0) idx = last_next;
+        if (ended) fast = 0;
+        else if (first < 8 || D >= pcl) fast = 0;
+    }
+    *idx_out = idx; *ended_out = ended;
+    return D;
+}
+
 static void pc_on_select(mo_agent *a, const int32_t *trace, int D) {
     if (!a->pc_on) return;
+    {   /* the engine's phase 1 must serve a prefix of the TRUE trace, stand on the true next node (or the true leaf), with the true picks */
+        int idx = 0, ended = 0, picks[512];
+        int P = pc_emulate_phase1(a, trace[0], &idx, &ended, picks);
+        int bad = P > D || (ended ? (P != D || idx != trace[D - 1]) : (P < D ? idx != trace[P] : 1));
+        if (P == D && !ended) bad = 1;                       /* a walk that serves every level must have ended on a cached leaf */
+        for (int L = 0; L < P && L + 1 < D && !bad; ++L) bad = picks[L] < 0 || a->pc_cn[L][picks[L]] != trace[L + 1];
+        if (P > 0 && P <= D && !bad && picks[P - 1] < 0 && !ended) bad = 1;
+        if (bad) {
+            if (a->pc_errors < 5) fprintf(stderr, "path-cache model: phase-1 emulation disagrees with the walk (served %d of %d, ended %d, idx %d)\n", P, D, ended, idx);
+            a->pc_errors += 1;
+        }
+    }
     int L = 0;
     while (L < a->pc_len && L < D && a->pc_node[L] == trace[L]) {
         int32_t cn[MO_NA], co[MO_NA];

@@ -292,30 +292,58 @@ struct ArenaAcc {
           pcg(A_.pc ? A_.pc + (size_t)g_ * A_.trace_max * PC_STRIDE : nullptr),
           psib(A_.pc ? reinterpret_cast<uint16_t *>(A_.pc_sib + (size_t)g_ * A_.trace_max) : nullptr),
           pown(A_.pc ? A_.pc_own + (size_t)g_ * A_.trace_max : nullptr), pc_len(0) {}
-    __device__ __forceinline__ void pc_load(int L, int lane, int4 &e, int &var, int4 &own_next) const {   // entry of level L + the own record of level L + 1
+    // One cached level, evaluated by ONE lane: check_low + policy_clt (core.h:65-105) over the seven child slots in list order, on the entry's
+    // values with the slot picked last time read from the next level's own record.  Same float operations per child as clt_q in the
+    // eight-lane form; the argmax is the reference's own loop (first entry, then strict >).  bail: a first child below `low` visits.
+    __device__ __forceinline__ void pc_eval(int L, int low, int &node, int &own_obs, float &s_idx, int &pick_prev, int &pick, int &next,
+                                            bool &leaf, bool &bail, int4 &wb) const {
         const uint8_t *p = pcg + (size_t)L * PC_STRIDE;
-        e = *reinterpret_cast<const int4 *>(p + lane * 16);
-        var = *reinterpret_cast<const int *>(p + PC_OFF_VAR + lane * 4);
-        own_next = pown[L + 1 < A.trace_max ? L + 1 : L];
+        const int4 l7 = *reinterpret_cast<const int4 *>(p + 7 * 16);
+        pick_prev = *reinterpret_cast<const int *>(p + PC_OFF_VAR + 7 * 4);
+        const int4 own = pown[L + 1 < A.trace_max ? L + 1 : L];
+        s_idx = __int_as_float(l7.y); own_obs = l7.z; node = l7.w;
+        int4 e[7];
+#pragma unroll
+        for (int a = 0; a < 7; ++a) e[a] = *reinterpret_cast<const int4 *>(p + a * 16);
+        int n = 0; unsigned fm = 0u; bool lowhit = false;
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+            if (a == pick_prev) { e[a].z = own.x; e[a].w = own.y; }
+            if ((uint32_t)e[a].x >> 31) { fm |= 1u << a; n += e[a].z; lowhit |= e[a].z < low; }
+        }
+        leaf = fm == 0u; bail = lowhit;
+        pick = 7; next = 0;
+        if (leaf || lowhit) return;
+        const float zq = z(n);
+        float bestq = 0.f;
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+            if (!((fm >> a) & 1u)) continue;
+            int var = *reinterpret_cast<const int *>(p + PC_OFF_VAR + a * 4);
+            if (a == pick_prev) { var = own.z; wb = make_int4(own.x, own.y, own.z, 0); }
+            const int rl = (int)(((uint32_t)e[a].x >> 28) & 7u);
+            float rep_s = 0.f;                                          // the representative child's score (link word: rep_lane)
+#pragma unroll
+            for (int b = 0; b < 7; ++b) if (b == rl) rep_s = __int_as_float(e[b].y);
+            const float q = clt_q(__int_as_float(e[a].w), rep_s, s_idx, zq, __int_as_float(var), e[a].z);
+            if (pick == 7 || q > bestq) { pick = a; bestq = q; }       // core.h:94-101: first entry, then the first strict maximum
+        }
+#pragma unroll
+        for (int a = 0; a < 7; ++a) if (a == pick) next = (int)((uint32_t)e[a].x & LINK_NODE_MASK);
     }
-    __device__ __forceinline__ void pc_prefetch(int L, int lane) const {
-        if (lane < 5) prefetch_l2(pcg + (size_t)L * PC_STRIDE + lane * 32);
-        else if (lane == 5 && L + 1 < A.trace_max) prefetch_l2(pown + L + 1);
+    // this lane's cached level picked another child than last time: the old pick's latest statistics return to the entry, the new pick is recorded
+    __device__ __forceinline__ void pc_repick_lane(int L, int old_pick, int new_pick, const int4 &st) const {
+        uint8_t *p = pcg + (size_t)L * PC_STRIDE;
+        *reinterpret_cast<int2 *>(p + old_pick * 16 + 8) = make_int2(st.x, st.y);
+        *reinterpret_cast<int *>(p + PC_OFF_VAR + old_pick * 4) = st.z;
+        *reinterpret_cast<int *>(p + PC_OFF_VAR + 7 * 4) = new_pick;
+        psib[(size_t)L * 8 + 7] = (uint16_t)new_pick;
     }
     __device__ __forceinline__ void pc_store(int L, int lane, int4 e, int var, uint16_t sib) const {
         uint8_t *p = pcg + (size_t)L * PC_STRIDE;
         *reinterpret_cast<int4 *>(p + lane * 16) = e;
         *reinterpret_cast<int *>(p + PC_OFF_VAR + lane * 4) = var;
         psib[(size_t)L * 8 + lane] = sib;
-    }
-    // a cached level picked another child than last time: the old pick's latest statistics return to the entry, the new pick is recorded
-    __device__ __forceinline__ void pc_repick(int L, int lane, int old_pick, int new_pick, const int4 &st) const {
-        uint8_t *p = pcg + (size_t)L * PC_STRIDE;
-        if (lane == old_pick) {
-            *reinterpret_cast<int2 *>(p + lane * 16 + 8) = make_int2(st.x, st.y);
-            *reinterpret_cast<int *>(p + PC_OFF_VAR + lane * 4) = st.z;
-        }
-        if (lane == 7) { *reinterpret_cast<int *>(p + PC_OFF_VAR + 7 * 4) = new_pick; psib[(size_t)L * 8 + 7] = (uint16_t)new_pick; }
     }
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
         const int32_t *row = rowg + (size_t)idx * ROW_WORDS;
@@ -405,10 +433,9 @@ struct ArenaAcc {
 struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
     static constexpr bool has_pc = false;
     static constexpr uint8_t *pcg = nullptr; static constexpr int pc_len = 0;
-    __device__ __forceinline__ void pc_load(int, int, int4 &, int &, int4 &) const {}
-    __device__ __forceinline__ void pc_prefetch(int, int) const {}
+    __device__ __forceinline__ void pc_eval(int, int, int &, int &, float &, int &, int &, int &, bool &, bool &, int4 &) const {}
     __device__ __forceinline__ void pc_store(int, int, int4, int, uint16_t) const {}
-    __device__ __forceinline__ void pc_repick(int, int, int, int, const int4 &) const {}
+    __device__ __forceinline__ void pc_repick_lane(int, int, int, const int4 &) const {}
     const int32_t *child; int32_t *visit; float *value; float *variance; const float *score; const int32_t *n2o;
     int32_t *trace; uint32_t *rng; const Arena *A;
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
@@ -505,42 +532,46 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
         return pick;
     };
     if constexpr (Acc::has_pc) {
-        // ---- phase 1: the levels the path cache still holds (see "path cache" above).  Every group follows ITS cached prefix; a group
-        // leaves this phase at the first level whose entry is missing or belongs to another node and idles until the last group is through
-        // (a cached level is ~0.6 k clk: no memory access on the dependent chain, the next entry is loaded one level ahead).
+        // ---- phase 1: the levels the path cache still holds (see "path cache" above), ONE LANE PER LEVEL.  Given its entry and the next
+        // level's own record, the pick of a cached level does not depend on the levels above it, so the eight lanes of a group evaluate
+        // eight consecutive levels at once, each lane running core.h:83-105 over the seven child slots serially (no shuffles: ~9 x fewer
+        // warp instructions per level than eight lanes per level, which was issue bound at ~1.5 k clk per level).  The walk follows the
+        // cached path up to the first level that picks another child than last time (served, with the new pick), is a leaf (served: the
+        // walk ends), or cannot be served (entry missing, a child below `low` visits: check_low draws from the RNG in the uncached form).
         const int pcl = (walking && acc.pcg) ? acc.pc_len : 0;          // group-uniform
         bool fast = pcl > 0;
         int n_cached = 0;
-        int4 ec = make_int4(0, 0, 0, 0), oc = ec; int vc = 0;           // entry of the current level, own record of the next one
-        if (fast) acc.pc_load(0, gp.lane, ec, vc, oc);
         while (__any_sync(0xffffffffu, fast)) {
-            const int node = __shfl_sync(0xffffffffu, ec.w, 7, 8);
-            if (fast && node != idx) fast = false;                      // the previous level picked another child than last time: uncached from here
-            int4 en = make_int4(0, 0, 0, 0), on_ = en; int vn = 0;
-            if (fast && D + 1 < pcl) acc.pc_load(D + 1, gp.lane, en, vn, on_);
-            if (fast && D + 6 < pcl && gp.lane < 6) acc.pc_prefetch(D + 6, gp.lane);
-            const float s = __int_as_float(ec.y);
-            const float s_idx = gp.bcast(s, 7);
-            const int o_own = gp.bcast(ec.z, 7);
-            const int pick_prev = gp.bcast(vc, 7);                      // the slot this level picked last time: its statistics live in the next level's own record
-            const uint32_t lw = fast ? (uint32_t)ec.x : 0u;
-            Uniq u;
-            u.is_first = lw >> 31; u.rep_lane = (int)((lw >> 28) & 7u); u.rep_c = (int)(lw & LINK_NODE_MASK);
-            u.rep_s = gp.bcast(s, u.rep_lane);
-            u.first_mask = gp.ballot(u.is_first);
-            const bool on = fast && u.first_mask != 0;                   // first_mask == 0: a cached leaf without children (terminal node)
-            const int4 st = gp.lane == pick_prev ? make_int4(oc.x, oc.y, oc.z, 0) : make_int4(ec.z, ec.w, vc, 0);
-            const int pick = choose(on, u, st, s_idx);
-            const int next = gp.bcast(u.rep_c, pick);
-            if (fast) {                                                 // trace[D] already holds idx (same node as last time)
-                ++n_cached;
-                if (gp.lane == 7) acc.put_trace_meta(D, o_own | (on ? pick << 28 : 0), s_idx);
-                if (on && pick != pick_prev) acc.pc_repick(D, gp.lane, pick_prev, pick, st);
-                ++D;
-                if (!on) { walking = false; fast = false; }             // core.h:200
-                else { idx = next; if (D >= pcl) fast = false; }
+            const int L = D + gp.lane;                                  // this lane's level
+            const bool have = fast && L < pcl;
+            int e_node = 0, e_own = 0, pick_prev = 7, pick = 7, next = 0; float s_idx = 0.f;
+            bool leaf = false, bail = false;
+            int4 wb = make_int4(0, 0, 0, 0);                            // the old pick's statistics as read here (written back if the pick changes)
+            if (have) acc.pc_eval(L, low, e_node, e_own, s_idx, pick_prev, pick, next, leaf, bail, wb);
+            // the chain: level D must be the node the walk stands on, level L > D the child level L - 1 picks (true by construction while no pick changes)
+            const int prev_next = __shfl_up_sync(0xffffffffu, next, 1, 8);
+            const int expect = gp.lane == 0 ? idx : prev_next;
+            if (have && e_node != expect) bail = true;
+            const bool changed = have && !leaf && !bail && pick != pick_prev;
+            const unsigned stopmask = gp.ballot(!have || bail || leaf || changed);
+            const int first = stopmask ? __ffs(stopmask) - 1 : 8;       // lanes below `first`: served, pick unchanged
+            const bool first_served = first < 8 && ((gp.ballot(have && !bail) >> first) & 1u);   // the stopping level itself: a leaf or a changed pick
+            const int served = first + (first_served ? 1 : 0);
+            if (fast) {
+                if (gp.lane < served) {
+                    acc.put_trace_meta(L, e_own | (leaf ? 0 : pick << 28), s_idx);
+                    if (changed) acc.pc_repick_lane(L, pick_prev, pick, wb);
+                }
+                n_cached += served;
+                const int last_next = gp.bcast(next, served > 0 ? served - 1 : 0);
+                const bool ended = first_served && gp.bcast(leaf ? 1 : 0, first) != 0;
+                D += served;
+                const int leaf_node = gp.bcast(e_node, first < 8 ? first : 0);
+                if (ended) idx = leaf_node;                             // the walk returns the leaf it stands on
+                else if (served > 0) idx = last_next;
+                if (ended) { walking = false; fast = false; }           // core.h:200: a cached leaf without children (terminal node)
+                else if (first < 8 || D >= pcl) fast = false;           // uncached from level D on
             }
-            ec = en; vc = vn; oc = on_;
         }
         if (cached_levels) *cached_levels = n_cached;
     }
