@@ -357,7 +357,8 @@ def run_b200(args, cfg):
 
     def fresh_engine():
         e = BatchedEngine(G, max_nodes=M, mode=cfg["mode"], eval_kind=cfg["eval"], weights=weights, dist_weights=dist_w, env_args=ENV_ARGS,
-                          seed=BASE_SEED + 7919 * rank, device=local_rank, rollout_variance=1e3, overflow_reset=True)
+                          seed=BASE_SEED + 7919 * rank, device=local_rank, rollout_variance=1e3, overflow_reset=True,
+                          path_cache={"auto": None, "on": True, "off": False}[args.path_cache])
         e.set_games(recs)
         e.set_gc_headroom(cfg["gc_headroom"])
         return e
@@ -365,6 +366,7 @@ def run_b200(args, cfg):
     WORK_KEYS = ("sims", "expansions", "eval_requests", "trace_levels", "new_nodes", "gcs", "tree_resets")
     # ---- pass 1: device-timed region (inputs resident in HBM, no host buffers)
     eng = fresh_engine()
+    eng_path_cache = bool(getattr(eng, "path_cache", False))
     for _ in range(args.warmup):
         eng.play_move(sims, auto_reset=True, want_stats=False)
     eng.sync()
@@ -524,6 +526,9 @@ def run_b200(args, cfg):
             except Exception as ex:   # the oracle/_ref modules are prebuilt; report rather than die
                 cpu = {"value": None, "unit": "sims/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
         config = dict(cfg["config"])
+        config["path_cache"] = ("on: the children's statistics of every trace level are kept next to the trace, the next walk serves the levels it shares with it "
+                                "from there (b200_set_path_cache; results identical, tests/test_gpu_engine.py::test_path_cache_*); %.1f %% of the walked levels"
+                                % (100.0 * delta.get("cached_levels", 0) / max(delta["trace_levels"], 1))) if eng_path_cache else "off"
         config.update({"parallelism": "games sharded x%d, no data-path collective in the search; one exchange step per move (replay rows, all-gather)" % world,
                        "l2": "inputs larger than L2: %.1f GB of arenas per GPU; %.2f GB of activations stream through L2 every sim-step"
                              % (G * M * ARENA_BYTES_PER_SLOT / 1e9, G * 7 * 1792 * 4 / 1e9)})
@@ -640,6 +645,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--path-cache", default="auto", choices=["auto", "on", "off"],
+                    help="b200_set_path_cache (memory traffic only, results identical): auto = the engine's default where it applies (LP mode, max_nodes <= 65536)")
     ap.add_argument("--ref-moves-per-step", type=int, default=2)
     ap.add_argument("--exchange-rows", type=int, default=131072, help="rows (212 B) of the fixed-size replay block each rank contributes to the per-move all-gather")
     args = ap.parse_args()

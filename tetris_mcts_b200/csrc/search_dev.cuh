@@ -553,20 +553,24 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
             const int expect = gp.lane == 0 ? idx : prev_next;
             if (have && e_node != expect) bail = true;
             const bool changed = have && !leaf && !bail && pick != pick_prev;
+            // (every shuffle / vote below is executed by all 32 lanes, unconditionally: the four groups of a warp are in different states, and a
+            // full-mask collective that only some groups reach never completes — session 26/27 hung on a `first < 8 && ballot(...)`)
             const unsigned stopmask = gp.ballot(!have || bail || leaf || changed);
+            const unsigned okmask = gp.ballot(have && !bail);
             const int first = stopmask ? __ffs(stopmask) - 1 : 8;       // lanes below `first`: served, pick unchanged
-            const bool first_served = first < 8 && ((gp.ballot(have && !bail) >> first) & 1u);   // the stopping level itself: a leaf or a changed pick
+            const bool first_served = first < 8 && ((okmask >> first) & 1u) != 0u;   // the stopping level itself: a leaf or a changed pick
             const int served = first + (first_served ? 1 : 0);
+            const int last_next = gp.bcast(next, served > 0 ? served - 1 : 0);
+            const int leaf_at_first = gp.bcast(leaf ? 1 : 0, first < 8 ? first : 0);
+            const int leaf_node = gp.bcast(e_node, first < 8 ? first : 0);
+            const bool ended = first_served && leaf_at_first != 0;
             if (fast) {
                 if (gp.lane < served) {
                     acc.put_trace_meta(L, e_own | (leaf ? 0 : pick << 28), s_idx);
                     if (changed) acc.pc_repick_lane(L, pick_prev, pick, wb);
                 }
                 n_cached += served;
-                const int last_next = gp.bcast(next, served > 0 ? served - 1 : 0);
-                const bool ended = first_served && gp.bcast(leaf ? 1 : 0, first) != 0;
                 D += served;
-                const int leaf_node = gp.bcast(e_node, first < 8 ? first : 0);
                 if (ended) idx = leaf_node;                             // the walk returns the leaf it stands on
                 else if (served > 0) idx = last_next;
                 if (ended) { walking = false; fast = false; }           // core.h:200: a cached leaf without children (terminal node)

@@ -36,6 +36,7 @@ class BatchedEngine:
         self.cfg = cfg
         self.n_games, self.max_nodes, self.mode, self.eval_kind = int(n_games), int(max_nodes), mode_id, eval_id
         self.h = L.P()
+        self.path_cache = False
         L.check(L.lib().b200_engine_create(C.byref(cfg), C.byref(self.h)))
         if weights is not None:
             self.load_weights(weights)
@@ -112,6 +113,7 @@ class BatchedEngine:
         """Keep the children's statistics of every trace level next to the trace, so that the next walk of the game (which retraces ~93 % of the
         path) reads one sequential line per level instead of two dependent random accesses.  No effect on results.  LP mode, max_nodes <= 65536."""
         L.check(L.lib().b200_set_path_cache(self.h, int(bool(on))))
+        self.path_cache = bool(on)
 
     def set_deep_lane(self, max_games):
         """Scheduling only: the max_games games with the longest traces walk on a second stream (b200_set_deep_lane); 0 = off."""
