@@ -63,3 +63,7 @@ if pt[11]:
     lv = float(pt[11])
     print('per level (B200_SELECT_PROF build, sampled groups): levels %d  row line %.0f clk | statistics %.0f clk | pick %.0f clk | total %.0f clk' % (
         int(lv), float(pt[8]) / lv, float(pt[9]) / lv, float(pt[10]) / lv, float(pt[8] + pt[9] + pt[10]) / lv))
+if pt[15]:
+    w = float(pt[15])
+    print('path cache phase 1 (B200_SELECT_PROF build, sampled groups): walks %d  clk per walk %.0f  rounds per walk %.1f  levels served per walk %.1f | uncached levels per walk %.1f' % (
+        int(w), float(pt[12]) / w, float(pt[13]) / w, float(pt[14]) / w, float(pt[11]) / w))

@@ -68,7 +68,7 @@ struct b200_engine {
     ReplayPolicy rp; uint8_t *d_rp_tmp = nullptr, *d_rp_keep = nullptr; float *d_rp_vis = nullptr; int32_t *d_rp_kept = nullptr; int replay_alloc = 0;
     // one simulation step captured as a CUDA graph (replayed when phase timing is off: ~7 launches + 1 memset per step, 500 steps/move)
     int gc_headroom = 0;           // b200_set_gc_headroom: collect between moves every game with fewer free slots than this
-    uint8_t *d_pc = nullptr; int32_t *d_pc_len = nullptr; uint4 *d_pc_sib = nullptr; int4 *d_pc_own = nullptr;   // path cache (b200_set_path_cache): allocated at the first switch-on, A.pc == nullptr while off
+    int4 *d_pc = nullptr; int32_t *d_pc_var = nullptr, *d_pc_len = nullptr; uint4 *d_pc_sib = nullptr; int4 *d_pc_own = nullptr;   // path cache (b200_set_path_cache): allocated at the first switch-on, A.pc == nullptr while off
     // deep lane (b200_set_deep_lane): the games with the longest traces select / collect / resume on a second stream (kernels.cuh: k_classify)
     int deep_cap = 0; cudaStream_t stream1 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int32_t *d_glist0 = nullptr, *d_glist1 = nullptr, *d_nlist = nullptr, *d_nreq_deep = nullptr, *d_gc_list_deep = nullptr; uint2 *d_req_deep = nullptr;
@@ -531,11 +531,12 @@ extern "C" int b200_set_path_cache(b200_engine *e, int on) {
     drop_step_graph(e);
     if (on && !e->d_pc) {
         const size_t levels = (size_t)e->A.G * e->A.trace_max;
-        if (dalloc(e, &e->d_pc, levels * PC_STRIDE, false) || dalloc(e, &e->d_pc_sib, levels, false) || dalloc(e, &e->d_pc_own, levels, false) ||
+        if (dalloc(e, &e->d_pc, levels * 8, false) || dalloc(e, &e->d_pc_var, levels * 8, false) || dalloc(e, &e->d_pc_sib, levels, false) || dalloc(e, &e->d_pc_own, levels, false) ||
             dalloc(e, &e->d_pc_len, (size_t)e->A.G)) return B200_ERR_CUDA;
     }
     if (on) CK(cudaMemsetAsync(e->d_pc_len, 0, (size_t)e->A.G * sizeof(int32_t), e->stream));   // nothing is valid until a walk has left its entries
     e->A.pc = on ? e->d_pc : nullptr;
+    e->A.pc_var = on ? e->d_pc_var : nullptr;
     e->A.pc_len = on ? e->d_pc_len : nullptr;
     e->A.pc_sib = on ? e->d_pc_sib : nullptr;
     e->A.pc_own = on ? e->d_pc_own : nullptr;

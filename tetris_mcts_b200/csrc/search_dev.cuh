@@ -58,10 +58,10 @@ struct Arena {
     int2 *trace_meta;              // [G][trace_max] {own observation, own score bits} of every node on the trace, written by the walk (it has
                                    // both in lane 7 of the level it just loaded) so that the backup needs no second gather per level
     uint8_t *nmark, *omark; int32_t *gc_queue;
-    // path cache (b200_set_path_cache; LP mode): [G][trace_max] entries of PC_STRIDE bytes — for every level of the game's last trace the
-    // node, its row fields and the STATISTICS OF ITS CHILDREN, so that the next walk, which retraces ~93 % of that path, reads one
-    // sequential line per level instead of chasing a row line and seven statistics; pc_len[g] = how many leading entries are valid
-    uint8_t *pc; int32_t *pc_len;
+    // path cache (b200_set_path_cache; LP mode): for every level of the game's last trace the node, its row fields and the STATISTICS OF
+    // ITS CHILDREN, so that the next walk, which retraces ~93 % of that path, reads sequential lines instead of chasing a row line and seven
+    // statistics per level; pc_len[g] = how many leading levels are valid.  Layout: "path cache" below
+    int4 *pc; int32_t *pc_var; int32_t *pc_len;
     uint4 *pc_sib; int4 *pc_own;   // [G][trace_max] per level: the children's observation ids (8 x u16, the last = the picked slot) | the level's OWN statistics
     uint32_t *cur;                 // [G][20] the live game of each tree (the object play.py owns)
     const float *ztable;
@@ -254,9 +254,11 @@ __device__ __forceinline__ uint2 touch64(const void *p) {
 // Consecutive simulations of a game walk almost the same path (CPU model in oracle/mcts_oracle.c: 90-94 % of the levels are a shared
 // prefix; the walks differ in their last ~4 levels), and every level of a walk costs two DEPENDENT random accesses into an 82 GB arena.
 // The walk therefore leaves, next to the trace, everything a level needs (sequential per game):
-//   pc      PC_STRIDE bytes per level   lane a: int4 {link word u[a], score s[a], visit, value} | lane a: variance       (bytes 0..127 | 128..159)
-//                                       lane 7: {0, own score, own observation, NODE id}       | lane 7: the slot the walk PICKED (7: none)
-//                                       = the node's row fields and its children's statistics AS OF THE WALK THAT FILLED THE ENTRY
+//   pc      [8 slots][trace_max] int4   slot a < 7: {link word u[a], score s[a], visit, value} of child slot a AS OF THE WALK THAT FILLED THE LEVEL;
+//                                       slot 7: {0, own score, own observation, NODE id}
+//   pc_var  [8 slots][trace_max] i32    slot a < 7: variance; slot 7: the slot the walk PICKED at this level (7: none)
+//           (slot-major, level-minor: the cached levels are evaluated ONE LANE PER LEVEL, so the eight lanes of a game read eight consecutive
+//            levels of one slot = one 128-byte line per load; level-major entries cost 32 wavefronts per load instruction and were slower)
 //   pc_own  16 bytes per level          {visit, value, variance} of the level's own observation, rewritten by k_backup every simulation
 //   pc_sib  16 bytes per level          the children's observation ids as 8 x u16 (0: not a first occurrence; the last: the picked slot),
 //                                       read by k_backup's staleness scan only
@@ -272,7 +274,7 @@ __device__ __forceinline__ uint2 touch64(const void *p) {
 //   * k_update_root, k_gc (collections and dropped trees) and reset_tree set pc_len = 0.
 // The CPU model applies exactly these rules and checks every value a cached level would read against the arena at every selection
 // (oracle/mcts_oracle.c pc_*, tests/test_cpu_path_cache_model.py).
-constexpr int PC_STRIDE = 160, PC_OFF_VAR = 128;
+constexpr int PC_BYTES_PER_LEVEL = 8 * 16 + 8 * 4 + 16 + 16;   // pc + pc_var + pc_own + pc_sib
 constexpr int PC_MAX_NODES = 65536;   // observation ids as u16 in pc_sib; k_backup's bitmap of the trace's observations is exact (one bit per slot, shared memory)
 constexpr uint32_t TMETA_OBS_MASK = 0x0fffffffu;   // trace_meta.x = own observation | pick << 28
 
@@ -285,31 +287,38 @@ struct ArenaAcc {
     static constexpr bool has_pc = true;
     const Arena &A; int g; const float *zs;
     const int32_t *rowg; int4 *statg; int32_t *traceg; int2 *tmetag;   // this game's slices of the arena (address arithmetic hoisted out of the loops)
-    uint8_t *pcg; uint16_t *psib; int4 *pown; int pc_len;              // path cache of this game (nullptr: off) and its valid length for THIS walk (set by the caller)
+    int4 *pcg; int32_t *pvarg; uint16_t *psib; int4 *pown; int pc_len; // path cache of this game (nullptr: off) and its valid length for THIS walk (set by the caller)
     __device__ __forceinline__ ArenaAcc(const Arena &A_, int g_, const float *zs_ = nullptr)
         : A(A_), g(g_), zs(zs_), rowg(A_.row + (size_t)g_ * A_.M * ROW_WORDS), statg(A_.stat + (size_t)g_ * A_.M),
           traceg(A_.trace + (size_t)g_ * A_.trace_max), tmetag(A_.trace_meta + (size_t)g_ * A_.trace_max),
-          pcg(A_.pc ? A_.pc + (size_t)g_ * A_.trace_max * PC_STRIDE : nullptr),
+          pcg(A_.pc ? A_.pc + (size_t)g_ * A_.trace_max * 8 : nullptr), pvarg(A_.pc ? A_.pc_var + (size_t)g_ * A_.trace_max * 8 : nullptr),
           psib(A_.pc ? reinterpret_cast<uint16_t *>(A_.pc_sib + (size_t)g_ * A_.trace_max) : nullptr),
           pown(A_.pc ? A_.pc_own + (size_t)g_ * A_.trace_max : nullptr), pc_len(0) {}
+    __device__ __forceinline__ int4 *pslot(int a, int L) const { return pcg + (size_t)a * A.trace_max + L; }
+    __device__ __forceinline__ int32_t *pvar(int a, int L) const { return pvarg + (size_t)a * A.trace_max + L; }
+    // the lines the NEXT round of eight levels (Lb .. Lb+7) will read, requested from L2 while this round is evaluated: lane a takes slot a
+    __device__ __forceinline__ void pc_prefetch_round(int Lb, int lane) const {
+        if (Lb >= A.trace_max) return;
+        const int Le = Lb + 7 < A.trace_max ? Lb + 7 : A.trace_max - 1;
+        prefetch_l2(pslot(lane, Lb)); prefetch_l2(pslot(lane, Le));
+        prefetch_l2(pvar(lane, Lb));
+        if (lane == 0) { prefetch_l2(pown + (Lb + 1 < A.trace_max ? Lb + 1 : Lb)); prefetch_l2(pown + Le); }
+    }
     // One cached level, evaluated by ONE lane: check_low + policy_clt (core.h:65-105) over the seven child slots in list order, on the entry's
     // values with the slot picked last time read from the next level's own record.  Same float operations per child as clt_q in the
     // eight-lane form; the argmax is the reference's own loop (first entry, then strict >).  bail: a first child below `low` visits.
     __device__ __forceinline__ void pc_eval(int L, int low, int &node, int &own_obs, float &s_idx, int &pick_prev, int &pick, int &next,
                                             bool &leaf, bool &bail, int4 &wb) const {
-        const uint8_t *p = pcg + (size_t)L * PC_STRIDE;
-        const int4 l7 = *reinterpret_cast<const int4 *>(p + 7 * 16);
-        pick_prev = *reinterpret_cast<const int *>(p + PC_OFF_VAR + 7 * 4);
+        const int4 l7 = *pslot(7, L);
+        pick_prev = *pvar(7, L);
         const int4 own = pown[L + 1 < A.trace_max ? L + 1 : L];
         s_idx = __int_as_float(l7.y); own_obs = l7.z; node = l7.w;
-        int4 e[7];
-#pragma unroll
-        for (int a = 0; a < 7; ++a) e[a] = *reinterpret_cast<const int4 *>(p + a * 16);
         int n = 0; unsigned fm = 0u; bool lowhit = false;
 #pragma unroll
-        for (int a = 0; a < 7; ++a) {
-            if (a == pick_prev) { e[a].z = own.x; e[a].w = own.y; }
-            if ((uint32_t)e[a].x >> 31) { fm |= 1u << a; n += e[a].z; lowhit |= e[a].z < low; }
+        for (int a = 0; a < 7; ++a) {                                   // pass 1: which slots are list entries, accumulate(visit) (core.h:88), check_low
+            const int4 e = *pslot(a, L);
+            const int vis = a == pick_prev ? own.x : e.z;
+            if ((uint32_t)e.x >> 31) { fm |= 1u << a; n += vis; lowhit |= vis < low; }
         }
         leaf = fm == 0u; bail = lowhit;
         pick = 7; next = 0;
@@ -317,32 +326,28 @@ struct ArenaAcc {
         const float zq = z(n);
         float bestq = 0.f;
 #pragma unroll
-        for (int a = 0; a < 7; ++a) {
+        for (int a = 0; a < 7; ++a) {                                   // pass 2 (the lines are in L1 now): q of every list entry, first strict maximum
             if (!((fm >> a) & 1u)) continue;
-            int var = *reinterpret_cast<const int *>(p + PC_OFF_VAR + a * 4);
-            if (a == pick_prev) { var = own.z; wb = make_int4(own.x, own.y, own.z, 0); }
-            const int rl = (int)(((uint32_t)e[a].x >> 28) & 7u);
-            float rep_s = 0.f;                                          // the representative child's score (link word: rep_lane)
-#pragma unroll
-            for (int b = 0; b < 7; ++b) if (b == rl) rep_s = __int_as_float(e[b].y);
-            const float q = clt_q(__int_as_float(e[a].w), rep_s, s_idx, zq, __int_as_float(var), e[a].z);
-            if (pick == 7 || q > bestq) { pick = a; bestq = q; }       // core.h:94-101: first entry, then the first strict maximum
+            int4 e = *pslot(a, L);
+            int var = *pvar(a, L);
+            if (a == pick_prev) { e.z = own.x; e.w = own.y; var = own.z; wb = make_int4(own.x, own.y, own.z, 0); }
+            const int rl = (int)(((uint32_t)e.x >> 28) & 7u);
+            const float rep_s = __int_as_float(pslot(rl, L)->y);        // the representative child's score (link word: rep_lane)
+            const float q = clt_q(__int_as_float(e.w), rep_s, s_idx, zq, __int_as_float(var), e.z);
+            if (pick == 7 || q > bestq) { pick = a; bestq = q; next = (int)((uint32_t)e.x & LINK_NODE_MASK); }   // core.h:94-101: first entry, then the first strict maximum
         }
-#pragma unroll
-        for (int a = 0; a < 7; ++a) if (a == pick) next = (int)((uint32_t)e[a].x & LINK_NODE_MASK);
     }
     // this lane's cached level picked another child than last time: the old pick's latest statistics return to the entry, the new pick is recorded
     __device__ __forceinline__ void pc_repick_lane(int L, int old_pick, int new_pick, const int4 &st) const {
-        uint8_t *p = pcg + (size_t)L * PC_STRIDE;
-        *reinterpret_cast<int2 *>(p + old_pick * 16 + 8) = make_int2(st.x, st.y);
-        *reinterpret_cast<int *>(p + PC_OFF_VAR + old_pick * 4) = st.z;
-        *reinterpret_cast<int *>(p + PC_OFF_VAR + 7 * 4) = new_pick;
+        int4 *e = pslot(old_pick, L);
+        *reinterpret_cast<int2 *>(reinterpret_cast<uint8_t *>(e) + 8) = make_int2(st.x, st.y);
+        *pvar(old_pick, L) = st.z;
+        *pvar(7, L) = new_pick;
         psib[(size_t)L * 8 + 7] = (uint16_t)new_pick;
     }
     __device__ __forceinline__ void pc_store(int L, int lane, int4 e, int var, uint16_t sib) const {
-        uint8_t *p = pcg + (size_t)L * PC_STRIDE;
-        *reinterpret_cast<int4 *>(p + lane * 16) = e;
-        *reinterpret_cast<int *>(p + PC_OFF_VAR + lane * 4) = var;
+        *pslot(lane, L) = e;
+        *pvar(lane, L) = var;
         psib[(size_t)L * 8 + lane] = sib;
     }
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
@@ -432,10 +437,11 @@ struct ArenaAcc {
 
 struct RefAcc {   // child int32[M,7], visit int32[M], value/variance/score f32[M], n_to_o int32[M]  (core.cpp:20-26)
     static constexpr bool has_pc = false;
-    static constexpr uint8_t *pcg = nullptr; static constexpr int pc_len = 0;
+    static constexpr int4 *pcg = nullptr; static constexpr int pc_len = 0;
     __device__ __forceinline__ void pc_eval(int, int, int &, int &, float &, int &, int &, int &, bool &, bool &, int4 &) const {}
     __device__ __forceinline__ void pc_store(int, int, int4, int, uint16_t) const {}
     __device__ __forceinline__ void pc_repick_lane(int, int, int, const int4 &) const {}
+    __device__ __forceinline__ void pc_prefetch_round(int, int) const {}
     const int32_t *child; int32_t *visit; float *value; float *variance; const float *score; const int32_t *n2o;
     int32_t *trace; uint32_t *rng; const Arena *A;
     __device__ __forceinline__ void children(int idx, int lane, int &c, int &o, float &s) const {
@@ -541,12 +547,20 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
         const int pcl = (walking && acc.pcg) ? acc.pc_len : 0;          // group-uniform
         bool fast = pcl > 0;
         int n_cached = 0;
+#if B200_SELECT_PROF
+        const long long p1t = clock64();
+        int p1_rounds = 0;
+#endif
         while (__any_sync(0xffffffffu, fast)) {
+#if B200_SELECT_PROF
+            ++p1_rounds;
+#endif
             const int L = D + gp.lane;                                  // this lane's level
             const bool have = fast && L < pcl;
             int e_node = 0, e_own = 0, pick_prev = 7, pick = 7, next = 0; float s_idx = 0.f;
             bool leaf = false, bail = false;
             int4 wb = make_int4(0, 0, 0, 0);                            // the old pick's statistics as read here (written back if the pick changes)
+            if (fast && D + 8 < pcl) acc.pc_prefetch_round(D + 8, gp.lane);
             if (have) acc.pc_eval(L, low, e_node, e_own, s_idx, pick_prev, pick, next, leaf, bail, wb);
             // the chain: level D must be the node the walk stands on, level L > D the child level L - 1 picks (true by construction while no pick changes)
             const int prev_next = __shfl_up_sync(0xffffffffu, next, 1, 8);
@@ -578,6 +592,9 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
             }
         }
         if (cached_levels) *cached_levels = n_cached;
+#if B200_SELECT_PROF
+        if (lp) { lt = clock64(); atomicAdd(&lp[4], (unsigned long long)(lt - p1t)); atomicAdd(&lp[5], (unsigned long long)p1_rounds); atomicAdd(&lp[6], (unsigned long long)n_cached); atomicAdd(&lp[7], 1ull); }
+#endif
     }
     // ---- phase 2: uncached levels (two dependent random accesses each); with the path cache on, each of them leaves its entry behind
     while (__any_sync(0xffffffffu, walking)) {

@@ -10,7 +10,7 @@ import numpy as np
 from . import _lib as L
 
 
-PATH_CACHE_DEFAULT = "0"
+PATH_CACHE_DEFAULT = "1"   # measured on B200 (profiles/exp_path_cache_r2*.txt): 16384 games x 500 sims, move 0.362 -> 0.340 s; results identical (tests)
 
 
 class BatchedEngine:
