@@ -130,10 +130,11 @@ __device__ __forceinline__ float ztab(const Arena &A, int n) {
 }
 
 // core.h:94 + core.h:213: q = (V[o] + score[c] - score[idx]) + z * sqrt(S2[o] / N[o]), all in float
+__device__ __forceinline__ float clt_val(float V, float sc, float sidx) { return __fsub_rn(__fadd_rn(V, sc), sidx); }
+__device__ __forceinline__ float clt_root(float S2, int N) { return __fsqrt_rn(__fdiv_rn(S2, (float)N)); }
+__device__ __forceinline__ float clt_mix(float val, float z, float root) { return __fadd_rn(val, __fmul_rn(z, root)); }
 __device__ __forceinline__ float clt_q(float V, float sc, float sidx, float z, float S2, int N) {
-    float val = __fsub_rn(__fadd_rn(V, sc), sidx);
-    float root = __fsqrt_rn(__fdiv_rn(S2, (float)N));
-    return __fadd_rn(val, __fmul_rn(z, root));
+    return clt_mix(clt_val(V, sc, sidx), z, clt_root(S2, N));
 }
 
 // core.h:244-258, one trace level.  v is carried in double; stores narrow to float.
@@ -254,9 +255,13 @@ __device__ __forceinline__ uint2 touch64(const void *p) {
 // Consecutive simulations of a game walk almost the same path (CPU model in oracle/mcts_oracle.c: 90-94 % of the levels are a shared
 // prefix; the walks differ in their last ~4 levels), and every level of a walk costs two DEPENDENT random accesses into an 82 GB arena.
 // The walk therefore leaves, next to the trace, everything a level needs (sequential per game):
-//   pc      [8 slots][trace_max] int4   slot a < 7: {link word u[a], score s[a], visit, value} of child slot a AS OF THE WALK THAT FILLED THE LEVEL;
+//   pc      [8 slots][trace_max] int4   slot a < 7: {link word u[a], val, visit, root} of child slot a AS OF THE WALK THAT FILLED THE LEVEL, where
+//                                       val = (value + score) - own score and root = sqrt(variance / visit) are the two z-independent terms of
+//                                       policy_clt's q = val + z * root (core.h:94, 213): stored as computed, so a cached sibling costs one
+//                                       multiply-add pair instead of an IEEE division and square root (13 % of the kernel's samples in ncu);
 //                                       slot 7: {0, own score, own observation, NODE id}
-//   pc_var  [8 slots][trace_max] i32    slot a < 7: variance; slot 7: the slot the walk PICKED at this level (7: none)
+//   pc_var  [8 slots][trace_max] i32    slot a < 7: the score of the slot's representative child (to rebuild val of the picked slot from its live
+//                                       statistics); slot 7: the slot the walk PICKED at this level (7: none)
 //           (slot-major, level-minor: the cached levels are evaluated ONE LANE PER LEVEL, so the eight lanes of a game read eight consecutive
 //            levels of one slot = one 128-byte line per load; level-major entries cost 32 wavefronts per load instruction and were slower)
 //   pc_own  16 bytes per level          {visit, value, variance} of the level's own observation, rewritten by k_backup every simulation
@@ -328,20 +333,22 @@ struct ArenaAcc {
 #pragma unroll
         for (int a = 0; a < 7; ++a) {                                   // pass 2 (the lines are in L1 now): q of every list entry, first strict maximum
             if (!((fm >> a) & 1u)) continue;
-            int4 e = *pslot(a, L);
-            int var = *pvar(a, L);
-            if (a == pick_prev) { e.z = own.x; e.w = own.y; var = own.z; wb = make_int4(own.x, own.y, own.z, 0); }
-            const int rl = (int)(((uint32_t)e.x >> 28) & 7u);
-            const float rep_s = __int_as_float(pslot(rl, L)->y);        // the representative child's score (link word: rep_lane)
-            const float q = clt_q(__int_as_float(e.w), rep_s, s_idx, zq, __int_as_float(var), e.z);
+            const int4 e = *pslot(a, L);
+            float val = __int_as_float(e.y), root = __int_as_float(e.w);
+            if (a == pick_prev) {                                       // the one child whose statistics moved since the entry was filled
+                val = clt_val(__int_as_float(own.y), __int_as_float(*pvar(a, L)), s_idx);
+                root = clt_root(__int_as_float(own.z), own.x);
+                wb = make_int4(__float_as_int(val), own.x, __float_as_int(root), 0);
+            }
+            const float q = clt_mix(val, zq, root);
             if (pick == 7 || q > bestq) { pick = a; bestq = q; next = (int)((uint32_t)e.x & LINK_NODE_MASK); }   // core.h:94-101: first entry, then the first strict maximum
         }
     }
     // this lane's cached level picked another child than last time: the old pick's latest statistics return to the entry, the new pick is recorded
-    __device__ __forceinline__ void pc_repick_lane(int L, int old_pick, int new_pick, const int4 &st) const {
-        int4 *e = pslot(old_pick, L);
-        *reinterpret_cast<int2 *>(reinterpret_cast<uint8_t *>(e) + 8) = make_int2(st.x, st.y);
-        *pvar(old_pick, L) = st.z;
+    __device__ __forceinline__ void pc_repick_lane(int L, int old_pick, int new_pick, const int4 &st) const {   // st = {val, visit, root} of the old pick as evaluated now
+        uint8_t *e = reinterpret_cast<uint8_t *>(pslot(old_pick, L));
+        *reinterpret_cast<int *>(e + 4) = st.x;
+        *reinterpret_cast<int2 *>(e + 8) = make_int2(st.y, st.z);
         *pvar(7, L) = new_pick;
         psib[(size_t)L * 8 + 7] = (uint16_t)new_pick;
     }
@@ -504,7 +511,7 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
 #endif
     // core.h:65-105 for one level, from the values every lane holds for its child slot (`on`: this lane's group is at a node WITH children):
     // check_low, then policy_clt.  Shared by the cached and the uncached form of a level, so both pick bit for bit the same child.
-    auto choose = [&](bool on, const Uniq &u, const int4 &st, float s_idx) -> int {
+    auto choose = [&](bool on, const Uniq &u, const int4 &st, float s_idx, float &val_out, float &root_out) -> int {
         const unsigned lowmask = gp.ballot(on && u.is_first && st.x < low);   // core.h:65-77
         int pick = 0;
         if (__any_sync(0xffffffffu, lowmask != 0u)) {                   // warp-uniform branch: the draw of every group that needs one
@@ -519,7 +526,9 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
         n += __shfl_xor_sync(0xffffffffu, n, 4, 8);
         const float z = acc.z(n);
         const bool cmp = on && u.is_first;
-        const float q = cmp ? clt_q(__int_as_float(st.y), u.rep_s, s_idx, z, __int_as_float(st.z), st.x) : 0.f;
+        val_out = cmp ? clt_val(__int_as_float(st.y), u.rep_s, s_idx) : 0.f;
+        root_out = cmp ? clt_root(__int_as_float(st.z), st.x) : 0.f;
+        const float q = cmp ? clt_mix(val_out, z, root_out) : 0.f;
         // core.h:94-101: the first strict maximum in list order = the largest q, the lowest lane on ties, as a 3-step
         // butterfly.  A NaN never wins a `>`; it is the answer only when it is the first entry of the list.
         const bool cand = cmp && q == q;
@@ -621,14 +630,15 @@ __device__ __forceinline__ int select_trace(const Acc &acc, bool active, int roo
         int4 st = make_int4(0, 0, 0, 0);
         if (walking && u.is_first) st = acc.stat(o, D);                 // the children live one level below
         LEVEL_PROF(1);
-        const int pick = choose(walking, u, st, s_idx);
+        float q_val, q_root;
+        const int pick = choose(walking, u, st, s_idx, q_val, q_root);
         const int next = gp.bcast(u.rep_c, pick);
         if (at_level && gp.lane == 7) acc.put_trace_meta(D - 1, o | (walking ? pick << 28 : 0), s_idx);   // lane 7 holds the node's own observation and score
         if constexpr (Acc::has_pc) {
             if (at_level && acc.pcg) {
                 const int pk = walking ? pick : 7;
-                acc.pc_store(D - 1, gp.lane, make_int4((int)lw, __float_as_int(s_own), gp.lane == 7 ? o : st.x, gp.lane == 7 ? idx : st.y),
-                             gp.lane == 7 ? pk : st.z, gp.lane == 7 ? (uint16_t)pk : (uint16_t)(u.is_first ? o : 0));
+                acc.pc_store(D - 1, gp.lane, gp.lane == 7 ? make_int4(0, __float_as_int(s_own), o, idx) : make_int4((int)lw, __float_as_int(q_val), st.x, __float_as_int(q_root)),
+                             gp.lane == 7 ? pk : __float_as_int(u.rep_s), gp.lane == 7 ? (uint16_t)pk : (uint16_t)(u.is_first ? o : 0));
             }
         }
         if (walking) idx = next;
