@@ -36,7 +36,7 @@ ARENA_BYTES_PER_SLOT = 304
 
 
 def _ncu_traffic_file():
-    for name in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):
+    for name in ("ncu_traffic_r2b.json", "ncu_traffic_r2.json", "ncu_traffic_r1.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             return p

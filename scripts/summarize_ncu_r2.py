@@ -9,7 +9,7 @@ from collections import defaultdict
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 regime = ("bench window: bench.py --steps 1 --warmup 5 (BASELINE configs[2]: 16384 games, 500 sims/move, max_nodes 16384, net_tc, head-room collection), "
           "kernels of move 5 of the `value` pass")
-out = ["# ncu evidence, round 2 (commands: scripts/gpu_profile_r2.sh)", "", "Regime: " + regime + ".", ""]
+out = ["# ncu evidence, round 2, build tag %s (commands: scripts/gpu_profile_r2.sh / gpu_profile_r2b.sh; r2b = the round-end build with the path cache on)" % tag, "", "Regime: " + regime + ".", ""]
 rows = list(csv.reader(open("gpurun_out/launches_%s.csv" % tag)))
 h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[h]
