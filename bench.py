@@ -483,7 +483,10 @@ def run_b200(args, cfg):
                                               "k_select_expand_gbursts_per_s": tr_s / 64.0 / (sel_ms / max(sel_n, 1) / 1e3) / 1e9,
                                               "k_backup_gbursts_per_s": tr_b / 64.0 / (bk_ms / max(bk_n, 1) / 1e3) / 1e9,
                                               "frac_select": tr_s / 64.0 / (sel_ms / max(sel_n, 1) / 1e3) / cap,
-                                              "frac_backup": tr_b / 64.0 / (bk_ms / max(bk_n, 1) / 1e3) / cap}
+                                              "frac_backup": tr_b / 64.0 / (bk_ms / max(bk_n, 1) / 1e3) / cap,
+                                              "note": "DRAM bytes of the ncu capture (traffic_src) / 64 B / this run's launch time.  With the path cache on most of "
+                                                      "k_select_expand's reads are sequential lines (config.path_cache), so its figure mixes streaming and random "
+                                                      "bursts; k_backup's trace records are sequential too (a ratio above 1 is not a contradiction)"}
         if cfg["mode"] == "dist":
             conv_ms, conv_n = phases["conv"]
             flop = 19 * 7 * 32 * 16 * 2 + 16 * 4 * 32 * 512 * 2   # conv1 (19x7 pixels) + conv2 (16x4) on the 22x10 input of model_distributional.py:27
