@@ -318,6 +318,8 @@ struct ArenaAcc {
         pick_prev = *pvar(7, L);
         const int4 own = pown[L + 1 < A.trace_max ? L + 1 : L];
         s_idx = __int_as_float(l7.y); own_obs = l7.z; node = l7.w;
+        const int pp = pick_prev < 7 ? pick_prev : 0;
+        const float rep_s_p = __int_as_float(*pvar(pp, L));            // score of the picked slot's representative child (in flight with the slots below)
         int n = 0; unsigned fm = 0u; bool lowhit = false;
 #pragma unroll
         for (int a = 0; a < 7; ++a) {                                   // pass 1: which slots are list entries, accumulate(visit) (core.h:88), check_low
@@ -328,20 +330,23 @@ struct ArenaAcc {
         leaf = fm == 0u; bail = lowhit;
         pick = 7; next = 0;
         if (leaf || lowhit) return;
+        // the one child whose statistics moved since the entry was filled: its two z-independent terms from the live record, ONCE (inside the
+        // unrolled loop below the division / square root were instantiated seven times: 1 280 instructions per round, 39 % of the kernel's)
+        const float val_p = clt_val(__int_as_float(own.y), rep_s_p, s_idx);
+        const float root_p = clt_root(__int_as_float(own.z), own.x);
+        wb = make_int4(__float_as_int(val_p), own.x, __float_as_int(root_p), 0);
         const float zq = z(n);
         float bestq = 0.f;
 #pragma unroll
-        for (int a = 0; a < 7; ++a) {                                   // pass 2 (the lines are in L1 now): q of every list entry, first strict maximum
-            if (!((fm >> a) & 1u)) continue;
+        for (int a = 0; a < 7; ++a) {                                   // pass 2, branch free (the lines are in L1 now): q of every list entry, first strict maximum
             const int4 e = *pslot(a, L);
-            float val = __int_as_float(e.y), root = __int_as_float(e.w);
-            if (a == pick_prev) {                                       // the one child whose statistics moved since the entry was filled
-                val = clt_val(__int_as_float(own.y), __int_as_float(*pvar(a, L)), s_idx);
-                root = clt_root(__int_as_float(own.z), own.x);
-                wb = make_int4(__float_as_int(val), own.x, __float_as_int(root), 0);
-            }
+            const float val = a == pick_prev ? val_p : __int_as_float(e.y);
+            const float root = a == pick_prev ? root_p : __int_as_float(e.w);
             const float q = clt_mix(val, zq, root);
-            if (pick == 7 || q > bestq) { pick = a; bestq = q; next = (int)((uint32_t)e.x & LINK_NODE_MASK); }   // core.h:94-101: first entry, then the first strict maximum
+            const bool take = ((fm >> a) & 1u) && (pick == 7 || q > bestq);   // core.h:94-101: first entry, then the first strict maximum
+            pick = take ? a : pick;
+            bestq = take ? q : bestq;
+            next = take ? (int)((uint32_t)e.x & LINK_NODE_MASK) : next;
         }
     }
     // this lane's cached level picked another child than last time: the old pick's latest statistics return to the entry, the new pick is recorded
