@@ -9,9 +9,10 @@ import numpy as np
 import pytest
 
 
-def play(oracle, M, sims, moves, seed, overflow_reset=1):
+def play(oracle, M, sims, moves, seed, overflow_reset=1, net=False):
     g = oracle.Game(seed=seed)
-    a = oracle.Agent(max_nodes=M, mode=0, gamma=0.999, low=1, eval_mode=0, overflow_reset=overflow_reset)
+    a = oracle.Agent(max_nodes=M, mode=0, gamma=0.999, low=1, eval_mode=1 if net else 0, weights=oracle.seeded_weights(0) if net else None,
+                     overflow_reset=overflow_reset)
     a.pc_enable(True)
     a.update_root(g.record())
     for _ in range(moves):
@@ -44,3 +45,11 @@ def test_truncation_is_exercised(oracle):
     """Transpositions inside the path do occur (the same observation under two nodes of the path): the runs above must have hit the rule."""
     st = play(oracle, 2048, 200, 60, 99)
     assert st["irregular"] > 0 and st["errors"] == 0
+
+
+def test_with_the_value_network_at_the_bench_arena_size(oracle):
+    """The tree shape of the benchmarked configuration (value network as evaluator, 16384 slots, deep narrow trees): the cache serves ~90 % of the
+    levels and every served value equals the arena's."""
+    st = play(oracle, 16384, 250, 6, 123, net=True)
+    assert st["errors"] == 0, st
+    assert st["shared"] > 0.85 * st["levels"], st
